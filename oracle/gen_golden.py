@@ -1,0 +1,196 @@
+"""Generate ``tests/golden/model_*.npz`` by running the REFERENCE's real Python model code in this container.
+
+TEST INFRASTRUCTURE ONLY.  Runs where ``/root/reference`` exists (the build container); the fixtures it writes
+are committed, so nothing at test/bench time needs the reference.
+
+What runs: the reference's unmodified ``models/unet_pvc.py`` / ``models/pvcnn.py`` / ``models/modules.py`` /
+``models/p2pb.py`` and its six op wrapper files ``third_party/openpoints/models/layers/*.py`` (imported with the
+stub recipe of SURVEY.md App. C), with the wrappers' ``pointnet2_cuda`` bound to the CPU restatement
+``oracle/ops.py`` (the reference's kernels are CUDA-only; those are pinned separately on the GPU by
+``oracle/gen_golden_gpu.py``).  So these fixtures pin everything ABOVE the op layer -- network wiring, layer
+semantics, schedule, sampling loop -- of ``oracle/model.py`` against the reference itself, and they check the
+parameter inventory (``param_shapes``) key-by-key against the reference's real constructor.
+
+Usage:  python -m oracle.gen_golden            (from the repo root)
+"""
+from __future__ import annotations
+
+import copy
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("P2PB_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, ROOT)
+from oracle import model as OM  # noqa: E402
+from oracle import ops as OO  # noqa: E402
+
+
+class AttrDict(dict):
+    """attribute + ``in`` + ``.get`` access, what the reference needs from an OmegaConf node."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    __setattr__ = dict.__setitem__
+
+    @staticmethod
+    def wrap(d):
+        if isinstance(d, dict):
+            return AttrDict({k: AttrDict.wrap(v) for k, v in d.items()})
+        if isinstance(d, list):
+            return [AttrDict.wrap(v) for v in d]
+        return d
+
+
+def import_reference():
+    """SURVEY.md App. C recipe, with the op module swapped for the CPU restatement."""
+    def pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+        return m
+
+    pkg("third_party", f"{REF}/third_party")
+    pkg("third_party.openpoints", f"{REF}/third_party/openpoints")
+    pkg("third_party.openpoints.models", f"{REF}/third_party/openpoints/models")
+    pkg("third_party.openpoints.cpp", f"{REF}/third_party/openpoints/cpp").pointnet2_cuda = OO
+    layers = pkg("third_party.openpoints.models.layers", f"{REF}/third_party/openpoints/models/layers")
+    for sub, name in [("voxelization", "avg_voxelize"), ("devoxelization", "trilinear_devoxelize"),
+                      ("ball_query", "ball_query"), ("interpolatation", "nearest_neighbor_interpolate"),
+                      ("sampling", "furthest_point_sample_pvcnn"), ("group", "pvcnn_grouping")]:
+        full = f"third_party.openpoints.models.layers.{sub}"
+        spec = importlib.util.spec_from_file_location(full, f"{REF}/third_party/openpoints/models/layers/{sub}.py")
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+        setattr(layers, name, getattr(mod, name))
+    ema = types.ModuleType("ema_pytorch")
+
+    class EMA(torch.nn.Module):
+        def __init__(self, model, beta=0.999):
+            super().__init__()
+            self.ema_model = copy.deepcopy(model)
+
+        def forward(self, *a, **k):
+            return self.ema_model(*a, **k)
+
+    ema.EMA = EMA
+    sys.modules["ema_pytorch"] = ema
+    oc = types.ModuleType("omegaconf")
+    oc.DictConfig = dict
+    oc.OmegaConf = object
+    sys.modules["omegaconf"] = oc
+    sys.modules["emd_assignment"] = types.ModuleType("emd_assignment")
+    sys.path.insert(0, REF)
+    from models.p2pb import P2PB  # noqa
+    from models.unet_pvc import PVCNN2Unet  # noqa
+
+    return PVCNN2Unet, P2PB
+
+
+def load_cfg(name, **over):
+    cfg = yaml.safe_load(open(f"{REF}/configs/{name}.yaml"))
+    for k, v in over.items():
+        node = cfg
+        ks = k.split(".")
+        for kk in ks[:-1]:
+            node = node[kk]
+        node[ks[-1]] = v
+    cfg["gpu"] = "cpu"
+    return cfg
+
+
+def make_input(kind, B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "test_xyz":
+        pts = torch.from_numpy(np.loadtxt(f"{REF}/test.xyz").astype(np.float32))[:N]
+        pts = pts - pts.mean(0, keepdim=True)
+        pts = pts / pts.norm(dim=1).max()
+        return pts.t().unsqueeze(0).contiguous()
+    x = torch.randn(B, 3, N, generator=g)
+    x = x / x.norm(dim=1, keepdim=True) * (1 + 0.05 * torch.randn(B, 1, N, generator=g))
+    x = x - x.mean(2, keepdim=True)
+    return (x / x.norm(dim=1).amax(dim=1)[:, None, None]).contiguous()
+
+
+CASES = [
+    # name, config, overrides, input kind, B, N, T, x_cond channels
+    ("pvds_cfg1", "PVDS_PUNet", {}, "test_xyz", 1, 1024, 5, 0),
+    ("pvds_b2", "PVDS_PUNet", {}, "synth", 2, 2048, 2, 0),
+    ("pvdl_xyz", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 0}, "synth", 1, 512, 2, 0),
+    ("pvdl_rgb", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 3}, "synth", 1, 512, 1, 3),
+    ("pvdl_dino", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 387}, "synth", 1, 512, 1, 387),
+]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    PVCNN2Unet, P2PB = import_reference()
+    torch.set_grad_enabled(False)
+    report = []
+    for name, cfgname, over, kind, B, N, T, F in CASES:
+        cfg = load_cfg(cfgname, **over)
+        acfg = AttrDict.wrap(copy.deepcopy(cfg))
+        acfg.model.ema = False
+        net = PVCNN2Unet(acfg)
+        ref_shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        ora_shapes = OM.param_shapes(cfg)
+        assert ref_shapes == ora_shapes, (
+            name, set(ref_shapes) ^ set(ora_shapes), [k for k in ref_shapes if ora_shapes.get(k) != ref_shapes[k]][:5])
+        sd = OM.make_state_dict(cfg, seed=0)
+        net.load_state_dict(sd, strict=True)
+        model = P2PB(acfg, net)
+        x = make_input(kind, B, N, seed=1)
+        xc = None
+        if F:
+            g = torch.Generator().manual_seed(2)
+            xc = torch.cat([torch.rand(B, 3, N, generator=g), torch.randn(B, F - 3, N, generator=g)], 1) if F > 3 \
+                else torch.rand(B, 3, N, generator=g)
+        # ---- reference: one forward at the first sampling step, then the T-step loop
+        sched = OM.build_schedule(cfg)
+        for k in ("std_fwd", "std_bwd", "std_sb", "mu_x0", "mu_x1", "betas", "noise_levels"):
+            assert torch.equal(getattr(model, k).cpu(), sched[k]), k
+        step_hi = OM.space_indices(cfg["diffusion"]["timesteps"], T + 1)[-1]
+        nl = model.noise_levels[torch.full((B,), step_hi, dtype=torch.long)]
+        net.eval()
+        eps_ref = net(x, nl, x_cond=xc)
+        out_ref = model.sample(x_start=x, x_cond=xc, steps=T, log_count=T, verbose=False, use_ema=False)
+        # ---- oracle restatement on the same weights / inputs
+        eps_ora = OM.unet_forward(sd, cfg, x, nl, xc)
+        out_ora = OM.sample(sd, cfg, x, xc, steps=T, log_count=T)
+        d_eps = (eps_ref - eps_ora).abs().max().item()
+        d_x = (out_ref["x_pred"] - out_ora["x_pred"]).abs().max().item()
+        d_chain = (out_ref["x_chain"] - out_ora["x_chain"]).abs().max().item()
+        report.append((name, d_eps, d_x, d_chain, eps_ref.abs().max().item()))
+        print(f"{name}: |eps_ref-eps_oracle|max={d_eps:.3e}  |x_pred diff|max={d_x:.3e}  chain={d_chain:.3e} "
+              f"(|eps|max={eps_ref.abs().max():.3f})")
+        np.savez_compressed(
+            os.path.join(OUT, f"model_{name}.npz"),
+            x_start=x.numpy(), x_cond=(xc.numpy().astype(np.float16) if xc is not None else np.zeros(0)),
+            eps=eps_ref.numpy(), x_pred=out_ref["x_pred"].numpy(), x_chain=out_ref["x_chain"].numpy(),
+            noise_level=nl.numpy(), T=T, cfg_name=cfgname, overrides=yaml.safe_dump(over),
+            n_params=len(ref_shapes))
+    # schedule fixtures for both beta_end settings (p2pb.py:93-130) and the step grids (p2pb.py:16-40)
+    for cfgname in ("PVDS_PUNet", "PVDL_SNPP"):
+        cfg = load_cfg(cfgname)
+        s = OM.build_schedule(cfg)
+        np.savez_compressed(os.path.join(OUT, f"schedule_{cfgname}.npz"), **{k: v.numpy() for k, v in s.items()},
+                            steps5=np.array(OM.space_indices(1000, 6)), steps30=np.array(OM.space_indices(1000, 31)))
+    return report
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,449 @@
+/*
+ * p2pb_oracle.c -- CPU restatement of the reference's CUDA-only point ops.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this
+ * library.  The product path (p2pb_b200/) never calls it and fails loudly if its CUDA library is missing.
+ *
+ * Each function restates one reference kernel, sequentially, in the reference's tensor layout
+ * (channel-first [B,C,N] fp32 / int32), citing the file:line it follows (paths relative to
+ * /root/reference/third_party/openpoints/cpp/pointnet2_batch/src/ unless stated otherwise).
+ *
+ * Floating-point contraction: nvcc contracts a*b+c into FMA by default (-fmad=true) and the reference
+ * is built with plain -O2 (setup.py:32), so distance / interpolation expressions are restated with
+ * explicit fmaf() in the order nvcc emits them (checked against the SASS of the reference's own
+ * extension built by oracle/build_ref.py; see DESIGN.md "oracle pinning").  This file must therefore be
+ * compiled with -ffp-contract=off so that gcc neither adds nor removes contractions.
+ *
+ * Pinned against: the reference's own compiled kernels on a B200 (tests/golden/ref_ops_*.npz, generated
+ * by oracle/gen_golden_gpu.py through oracle/_ref/pointnet2_batch_cuda.so) and the reference's only
+ * known-answer vector for this path (metrics/PyTorchEMD/test_emd_loss.py:6-20, for the EMD metric).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+#define ORA_API __attribute__((visibility("default")))
+
+/* squared distance exactly as nvcc contracts  dx*dx + dy*dy + dz*dz  (fmad=true).  LLVM folds
+ * fadd(fmul(a,a), fmul(b,b)) into fma(a,a, b*b): the SECOND product is rounded, the first is fused.  Verified in
+ * the SASS of the reference's own build (oracle/_ref/pointnet2_batch_cuda.so, ball_query_kernel @0x470-0x4c0,
+ * furthest_point_sampling_kernel @0x1150-0x11a0, three_nearest_neighbors_kernel @0x540-0x5b0):
+ *   FMUL t = dy*dy ; FFMA t = dx*dx + t ; FFMA t = dz*dz + t                                       */
+static inline float sqdist3(float dx, float dy, float dz)
+{
+    float t = dy * dy;
+    t = fmaf(dx, dx, t);
+    t = fmaf(dz, dz, t);
+    return t;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * vox_gpu.cu:18-36 grid_stats_kernel + :50-78 avg_voxelize_kernel  (forward wrapper vox.cpp:17-44)
+ * coords int32 [B,3,N] (already voxel indices 0..r-1), feat [B,C,N] -> out [B,C,r^3], ind [B,N], cnt [B,r^3]
+ * The reference accumulates feat*(1/cnt) with fp32 atomicAdd in arbitrary order; this restatement fixes
+ * the order to ascending point index (one valid schedule of the reference).
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_avg_voxelize_forward(const float *feat, const int32_t *coords, int B, int C, int N, int r,
+                                      float *out, int32_t *ind, int32_t *cnt)
+{
+    const int r2 = r * r, r3 = r2 * r;
+    memset(out, 0, sizeof(float) * (size_t)B * C * r3);
+    memset(cnt, 0, sizeof(int32_t) * (size_t)B * r3);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const int32_t *co = coords + (size_t)b * 3 * N;
+        int32_t *in = ind + (size_t)b * N;
+        int32_t *cn = cnt + (size_t)b * r3;
+        const float *f = feat + (size_t)b * C * N;
+        float *o = out + (size_t)b * C * r3;
+        for (int i = 0; i < N; ++i) {
+            in[i] = co[i] * r2 + co[i + N] * r + co[i + 2 * N];
+            cn[in[i]] += 1;
+        }
+        for (int i = 0; i < N; ++i) {
+            const int pos = in[i];
+            const int cur = cn[pos];
+            if (cur > 0) {
+                /* vox_gpu.cu:70  float div_cur_cnt = 1.0 / static_cast<float>(cur_cnt);  (double divide, rounded) */
+                const float div = (float)(1.0 / (double)(float)cur);
+                for (int j = 0; j < C; ++j) o[(size_t)j * r3 + pos] += f[(size_t)j * N + i] * div;
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * models/pvcnn.py:215-231 Voxelization.forward coordinate preparation (reference: PyTorch ops).
+ *   c = x - mean_N(x);  c / (2*max_N ||c||_2 + eps) + 0.5;  *r;  clamp(0,r-1);  round-half-even -> int32
+ * The mean is accumulated in double and rounded once (order-independent to ~1e-16), the norm is
+ * sqrt(x^2+y^2+z^2) in fp32 without contraction (torch.norm over dim=1 of 3 elements).
+ * Returns the un-rounded clamped coords (fed to devoxelize, pvcnn.py:227,230-231,324) and the int voxel coords.
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_voxel_coords(const float *coords, int B, int N, int r, int normalize, float eps,
+                              float *norm_coords, int32_t *vox_coords)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *c = coords + (size_t)b * 3 * N;
+        float *nc = norm_coords + (size_t)b * 3 * N;
+        int32_t *vc = vox_coords + (size_t)b * 3 * N;
+        float mean[3];
+        for (int a = 0; a < 3; ++a) {
+            double s = 0.0;
+            for (int i = 0; i < N; ++i) s += (double)c[a * N + i];
+            mean[a] = (float)(s / (double)N);
+        }
+        float mx = 0.f;
+        for (int i = 0; i < N; ++i) {
+            const float x = c[i] - mean[0], y = c[N + i] - mean[1], z = c[2 * N + i] - mean[2];
+            float s = x * x;
+            s = s + y * y;
+            s = s + z * z;
+            const float nr = sqrtf(s);
+            if (nr > mx) mx = nr;
+        }
+        const float denom = mx * 2.0f + eps;
+        for (int a = 0; a < 3; ++a)
+            for (int i = 0; i < N; ++i) {
+                float v = c[a * N + i] - mean[a];
+                if (normalize) v = v / denom + 0.5f;
+                else v = (v + 1.0f) / 2.0f;
+                v = v * (float)r;
+                v = fminf(fmaxf(v, 0.0f), (float)(r - 1));
+                nc[a * N + i] = v;
+                vc[a * N + i] = (int32_t)nearbyintf(v); /* torch.round = half to even (default FE_TONEAREST) */
+            }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * trilinear_devox_gpu.cu:21-109 trilinear_devoxelize_kernel (eval: only outs), wrapper trilinear_devox.cpp:18-59
+ * coords f32 [B,3,N] in [0,r-1], feat [B,C,r^3] -> outs [B,C,N]
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_trilinear_devoxelize_forward(const float *coords, const float *feat, int B, int C, int N, int r,
+                                              float *outs)
+{
+    const int r2 = r * r, r3 = r2 * r;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *co = coords + (size_t)b * 3 * N;
+        const float *f = feat + (size_t)b * C * r3;
+        float *o = outs + (size_t)b * C * N;
+        for (int i = 0; i < N; ++i) {
+            const float x = co[i], y = co[i + N], z = co[i + 2 * N];
+            const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+            const float xd1 = x - xl, yd1 = y - yl, zd1 = z - zl;
+            const float xd0 = 1.0f - xd1, yd0 = 1.0f - yd1, zd0 = 1.0f - zd1;
+            const float w000 = xd0 * yd0 * zd0, w001 = xd0 * yd0 * zd1, w010 = xd0 * yd1 * zd0, w011 = xd0 * yd1 * zd1;
+            const float w100 = xd1 * yd0 * zd0, w101 = xd1 * yd0 * zd1, w110 = xd1 * yd1 * zd0, w111 = xd1 * yd1 * zd1;
+            const int xlo = (int)xl, ylo = (int)yl, zlo = (int)zl;
+            const int xh = (xd1 > 0) ? -1 : 0, yh = (yd1 > 0) ? -1 : 0, zh = (zd1 > 0) ? 1 : 0;
+            const int i000 = xlo * r2 + ylo * r + zlo;
+            const int i001 = i000 + zh;
+            const int i010 = i000 + (yh & r);
+            const int i011 = i010 + zh;
+            const int i100 = i000 + (xh & r2);
+            const int i101 = i100 + zh;
+            const int i110 = i100 + (yh & r);
+            const int i111 = i110 + zh;
+            for (int j = 0; j < C; ++j) {
+                const float *fj = f + (size_t)j * r3;
+                /* :101-106 eight-term sum contracted by nvcc into an FMA chain; SASS @0x1220-0x13a0 of the
+                 * reference build: FMUL w001*f001 first, then FFMA w000, w010, w011, w100, w101, w110, w111 */
+                float acc = w001 * fj[i001];
+                acc = fmaf(w000, fj[i000], acc);
+                acc = fmaf(w010, fj[i010], acc);
+                acc = fmaf(w011, fj[i011], acc);
+                acc = fmaf(w100, fj[i100], acc);
+                acc = fmaf(w101, fj[i101], acc);
+                acc = fmaf(w110, fj[i110], acc);
+                acc = fmaf(w111, fj[i111], acc);
+                o[(size_t)j * N + i] = acc;
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * pvcnn_ball_query_gpu.cu:19-56 ball_query_kernel; wrapper pvcnn_ball_query.cpp:6-31 (r2 = radius*radius in fp32,
+ * output zero-initialised).  centers [B,3,M], points [B,3,N] -> idx int32 [B,M,U]
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_ball_query(const float *centers, const float *points, int B, int M, int N, float radius, int U,
+                            int32_t *idx)
+{
+    const float r2 = radius * radius;
+    memset(idx, 0, sizeof(int32_t) * (size_t)B * M * U);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *ce = centers + (size_t)b * 3 * M;
+        const float *po = points + (size_t)b * 3 * N;
+        int32_t *ix = idx + (size_t)b * M * U;
+        for (int j = 0; j < M; ++j) {
+            const float cx = ce[j], cy = ce[j + M], cz = ce[j + 2 * M];
+            int cnt = 0;
+            for (int k = 0; k < N && cnt < U; ++k) {
+                const float d2 = sqdist3(cx - po[k], cy - po[k + N], cz - po[k + 2 * N]);
+                if (d2 < r2) {
+                    if (cnt == 0)
+                        for (int v = 0; v < U; ++v) ix[j * U + v] = k;
+                    ix[j * U + cnt] = k;
+                    ++cnt;
+                }
+            }
+        }
+    }
+}
+
+/* pvcnn_grouping_gpu.cu:18-39 grouping_kernel: out[b,c,j,k] = feat[b,c,idx[b,j,k]] */
+ORA_API void ora_grouping_forward(const float *feat, const int32_t *idx, int B, int C, int N, int M, int U, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c)
+            for (int j = 0; j < M; ++j)
+                for (int k = 0; k < U; ++k)
+                    out[(((size_t)b * C + c) * M + j) * U + k] = feat[((size_t)b * C + c) * N + idx[((size_t)b * M + j) * U + k]];
+}
+
+/* pvcnn_sampling_gpu.cu:17-33 gather_features_kernel: out[b,c,j] = feat[b,c,idx[b,j]] */
+ORA_API void ora_gather_features_forward(const float *feat, const int32_t *idx, int B, int C, int N, int M, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c)
+            for (int j = 0; j < M; ++j) out[((size_t)b * C + c) * M + j] = feat[((size_t)b * C + c) * N + idx[(size_t)b * M + j]];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * pvcnn_sampling_gpu.cu:92-184 furthest_point_sampling_kernel (512 threads per patch), wrapper
+ * pvcnn_sampling.cpp:45-61 (distances initialised to 1e38f, indices zero-initialised).
+ * Tie-break restated exactly: thread t scans k = t, t+512, ... keeping the FIRST strict maximum (:154);
+ * the 9-level tree keeps the LOWER slot on ties (:170).  So the winner is the maximum of d2 with the
+ * lexicographically smallest key (k mod 512, k); threads with no point contribute (best=-1, besti=0).
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_furthest_point_sampling(const float *coords, int B, int N, int M, int32_t *idx)
+{
+    const int BS = 512;
+    memset(idx, 0, sizeof(int32_t) * (size_t)B * (M > 0 ? M : 0));
+    if (M <= 0) return;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *c = coords + (size_t)b * 3 * N;
+        int32_t *ix = idx + (size_t)b * M;
+        float *dist = (float *)malloc(sizeof(float) * (size_t)N);
+        float tb[512];
+        int ti[512];
+        for (int i = 0; i < N; ++i) dist[i] = 1e38f;
+        int old = 0;
+        ix[0] = 0;
+        for (int j = 1; j < M; ++j) {
+            const float x1 = c[old], y1 = c[old + N], z1 = c[old + 2 * N];
+            for (int t = 0; t < BS; ++t) {
+                tb[t] = -1.f;
+                ti[t] = 0;
+            }
+            for (int k = 0; k < N; ++k) {
+                const float d = sqdist3(c[k] - x1, c[k + N] - y1, c[k + 2 * N] - z1);
+                const float d2 = fminf(d, dist[k]);
+                dist[k] = d2;
+                const int t = k % BS;
+                if (d2 > tb[t]) {
+                    tb[t] = d2;
+                    ti[t] = k;
+                }
+            }
+            /* tree reduction, lower slot wins ties (strict <) */
+            float best = tb[0];
+            int besti = ti[0];
+            for (int t = 1; t < BS; ++t)
+                if (best < tb[t]) {
+                    best = tb[t];
+                    besti = ti[t];
+                }
+            old = besti;
+            ix[j] = old;
+        }
+        free(dist);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * pvcnn_neighbor_interpolate_gpu.cu:20-81 three_nearest_neighbors_kernel + :96-124 interpolate kernel,
+ * wrapper pvcnn_neighbor_interpolate.cpp:6-41.
+ * points [B,3,N], centers [B,3,M], cfeat [B,C,M] -> out [B,C,N], idx int32 [B,3,N], w [B,3,N]
+ * Running bests are doubles initialised to 1e40 (:39); weights use SQUARED distances clamped to [1e-10,1e10].
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_three_nn_interpolate_forward(const float *points, const float *centers, const float *cfeat, int B,
+                                              int C, int N, int M, float *out, int32_t *idx, float *w)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *po = points + (size_t)b * 3 * N;
+        const float *ce = centers + (size_t)b * 3 * M;
+        const float *cf = cfeat + (size_t)b * C * M;
+        float *o = out + (size_t)b * C * N;
+        int32_t *ix = idx + (size_t)b * 3 * N;
+        float *ww = w + (size_t)b * 3 * N;
+        for (int j = 0; j < N; ++j) {
+            const float ux = po[j], uy = po[j + N], uz = po[j + 2 * N];
+            double best0 = 1e40, best1 = 1e40, best2 = 1e40;
+            int bi0 = 0, bi1 = 0, bi2 = 0;
+            for (int k = 0; k < M; ++k) {
+                const float d = sqdist3(ux - ce[k], uy - ce[k + M], uz - ce[k + 2 * M]);
+                if (d < best2) {
+                    best2 = d;
+                    bi2 = k;
+                    if (d < best1) {
+                        best2 = best1;
+                        bi2 = bi1;
+                        best1 = d;
+                        bi1 = k;
+                        if (d < best0) {
+                            best1 = best0;
+                            bi1 = bi0;
+                            best0 = d;
+                            bi0 = k;
+                        }
+                    }
+                }
+            }
+            /* :67-69  max(min(1e10f, best), 1e-10f) evaluated in double, then :70-73 float products */
+            best0 = fmax(fmin((double)1e10f, best0), (double)1e-10f);
+            best1 = fmax(fmin((double)1e10f, best1), (double)1e-10f);
+            best2 = fmax(fmin((double)1e10f, best2), (double)1e-10f);
+            const float d0d1 = (float)(best0 * best1);
+            const float d0d2 = (float)(best0 * best2);
+            const float d1d2 = (float)(best1 * best2);
+            const float inv = 1.0f / (d0d1 + d0d2 + d1d2);
+            ww[j] = d1d2 * inv;
+            ix[j] = bi0;
+            ww[j + N] = d0d2 * inv;
+            ix[j + N] = bi1;
+            ww[j + 2 * N] = d0d1 * inv;
+            ix[j + 2 * N] = bi2;
+        }
+        for (int l = 0; l < C; ++l)
+            for (int j = 0; j < N; ++j) {
+                const float w1 = ww[j], w2 = ww[j + N], w3 = ww[j + 2 * N];
+                const int i1 = ix[j], i2 = ix[j + N], i3 = ix[j + 2 * N];
+                /* :118-120  a*w1 + b*w2 + c*w3 contracted (SASS @0x860-0x890): FMUL b*w2 ; FFMA a*w1 ; FFMA c*w3 */
+                float acc = cf[(size_t)l * M + i2] * w2;
+                acc = fmaf(cf[(size_t)l * M + i1], w1, acc);
+                acc = fmaf(cf[(size_t)l * M + i3], w3, acc);
+                o[(size_t)l * N + j] = acc;
+            }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * metrics/chamfer3D/chamfer3D.cu:12-134 NmDistanceKernel: for every point of xyz1 [B,n,3] the squared
+ * distance to (and index of) its nearest neighbour in xyz2 [B,m,3]; ties -> lowest index (strict <).
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_nm_distance(const float *xyz1, const float *xyz2, int B, int n, int m, float *dist, int32_t *idx)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int j = 0; j < n; ++j) {
+            const float x1 = xyz1[((size_t)b * n + j) * 3 + 0], y1 = xyz1[((size_t)b * n + j) * 3 + 1],
+                        z1 = xyz1[((size_t)b * n + j) * 3 + 2];
+            float best = 0.f;
+            int bi = 0;
+            for (int k = 0; k < m; ++k) {
+                const float *q = xyz2 + ((size_t)b * m + k) * 3;
+                const float d = sqdist3(q[0] - x1, q[1] - y1, q[2] - z1);
+                if (k == 0 || d < best) {
+                    best = d;
+                    bi = k;
+                }
+            }
+            dist[(size_t)b * n + j] = best;
+            idx[(size_t)b * n + j] = bi;
+        }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * metrics/PyTorchEMD/cuda/emd_kernel.cu:33-165 approxmatch + :211-253 matchcost (forward only).
+ * xyz1 [B,n,3], xyz2 [B,m,3] -> match [B,m,n] (caller-provided), cost [B] = sum_{l,k} d2(k,l) * match[l,k]
+ * (this fork's matchcost multiplies by the SQUARED distance, :236-237).
+ * Sequential restatement of the annealed soft assignment: levels j=7..-2, level = -4^j (0 at j=-2),
+ * three passes per level (ratioL :55-85, ratioR/remainR :87-121, match/remainL :123-160).
+ * The reference uses __expf and thread-order-dependent fp32 sums, so this pins results to fp tolerance only
+ * (known answer: test_emd_loss.py:6-20 -> 0.30+0.41 = 0.71 per batch element).
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_emd_approxmatch_cost(const float *xyz1, const float *xyz2, int B, int n, int m, float *match,
+                                      float *cost)
+{
+    float multiL, multiR;
+    if (n >= m) {
+        multiL = 1.f;
+        multiR = (float)(n / m); /* integer division, :38 */
+    } else {
+        multiL = (float)(m / n);
+        multiR = 1.f;
+    }
+    for (int b = 0; b < B; ++b) {
+        const float *p1 = xyz1 + (size_t)b * n * 3;
+        const float *p2 = xyz2 + (size_t)b * m * 3;
+        float *mt = match + (size_t)b * m * n;
+        float *remainL = (float *)malloc(sizeof(float) * n);
+        float *remainR = (float *)malloc(sizeof(float) * m);
+        float *ratioL = (float *)malloc(sizeof(float) * n);
+        float *ratioR = (float *)malloc(sizeof(float) * m);
+        for (int i = 0; i < n; ++i) remainL[i] = multiL;
+        for (int i = 0; i < m; ++i) remainR[i] = multiR;
+        memset(mt, 0, sizeof(float) * (size_t)n * m);
+        for (int j = 7; j >= -2; --j) {
+            float level = -powf(4.0f, (float)j);
+            if (j == -2) level = 0.f;
+            for (int k = 0; k < n; ++k) {
+                const float x1 = p1[k * 3], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+                float suml = 1e-9f;
+                for (int l = 0; l < m; ++l) {
+                    const float d = level * sqdist3(p2[l * 3] - x1, p2[l * 3 + 1] - y1, p2[l * 3 + 2] - z1);
+                    suml += expf(d) * remainR[l];
+                }
+                ratioL[k] = remainL[k] / suml;
+            }
+            for (int l = 0; l < m; ++l) {
+                const float x2 = p2[l * 3], y2 = p2[l * 3 + 1], z2 = p2[l * 3 + 2];
+                float sumr = 0.f;
+                for (int k = 0; k < n; ++k) {
+                    const float d = level * sqdist3(x2 - p1[k * 3], y2 - p1[k * 3 + 1], z2 - p1[k * 3 + 2]);
+                    sumr += expf(d) * ratioL[k];
+                }
+                sumr *= remainR[l];
+                const float consumption = fminf(remainR[l] / (sumr + 1e-9f), 1.0f);
+                ratioR[l] = consumption * remainR[l];
+                remainR[l] = fmaxf(0.0f, remainR[l] - sumr);
+            }
+            for (int k = 0; k < n; ++k) {
+                const float x1 = p1[k * 3], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+                const float rl = ratioL[k];
+                float suml = 0.f;
+                for (int l = 0; l < m; ++l) {
+                    const float d = level * sqdist3(p2[l * 3] - x1, p2[l * 3 + 1] - y1, p2[l * 3 + 2] - z1);
+                    const float w = expf(d) * rl * ratioR[l];
+                    mt[(size_t)l * n + k] += w;
+                    suml += w;
+                }
+                remainL[k] = fmaxf(0.0f, remainL[k] - suml);
+            }
+        }
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k)
+            for (int l = 0; l < m; ++l) {
+                const float d = sqdist3(p2[l * 3] - p1[k * 3], p2[l * 3 + 1] - p1[k * 3 + 1], p2[l * 3 + 2] - p1[k * 3 + 2]);
+                acc += (double)(d * mt[(size_t)l * n + k]);
+            }
+        cost[b] = (float)acc;
+        free(remainL);
+        free(remainR);
+        free(ratioL);
+        free(ratioR);
+    }
+}
