@@ -159,6 +159,7 @@ def main():
             g = torch.Generator().manual_seed(2)
             xc = torch.cat([torch.rand(B, 3, N, generator=g), torch.randn(B, F - 3, N, generator=g)], 1) if F > 3 \
                 else torch.rand(B, 3, N, generator=g)
+            xc = xc.half().float()  # stored as fp16 in the fixture: make the values exactly representable
         # ---- reference: one forward at the first sampling step, then the T-step loop
         sched = OM.build_schedule(cfg)
         for k in ("std_fwd", "std_bwd", "std_sb", "mu_x0", "mu_x1", "betas", "noise_levels"):

@@ -1,0 +1,41 @@
+"""ctypes binding of ``libp2pb_b200.so`` (the C ABI declared in ``include/p2pb_b200.h``).
+
+There is no CPU fallback: if the library is missing this raises, and every entry point raises when its
+return code is non-zero (the reference ``exit(-1)``s on launch errors, ``cuda_utils.cuh:30-40``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp2pb_b200.so")
+
+_lib = None
+
+
+class P2PBError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise P2PBError(
+                f"{LIB_PATH} not found: build it with `python -m p2pb_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.p2pb_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().p2pb_last_error().decode("utf-8", "replace")
+        raise P2PBError(f"{what} failed (rc={rc}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    fn = getattr(lib(), name)
+    check(fn(*args), name)

@@ -1,0 +1,33 @@
+// abi_common.cu -- error reporting and device queries shared by every entry point of libp2pb_b200.so
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_last_error[512] = "";
+
+void p2pb_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+// text of the last error raised on the calling thread ("" if none)
+P2PB_API const char* p2pb_last_error() { return g_last_error; }
+
+P2PB_API int p2pb_abi_version() { return 1; }
+
+int p2pb_num_sms()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+P2PB_API int p2pb_device_sm_count() { return p2pb_num_sms(); }

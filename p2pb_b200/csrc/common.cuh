@@ -1,0 +1,96 @@
+// common.cuh -- shared helpers for the p2pb_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define P2PB_API extern "C" __attribute__((visibility("default")))
+
+// error codes returned through the C ABI (include/p2pb_b200.h)
+#define P2PB_OK 0
+#define P2PB_ERR_INVALID (-1)
+#define P2PB_ERR_CUDA (-2)
+#define P2PB_ERR_UNSUPPORTED (-3)
+
+// thread-local last-error text, see p2pb_last_error()
+void p2pb_set_error(const char* fmt, ...);
+
+#define P2PB_CHECK_ARG(cond, ...)             \
+    do {                                      \
+        if (!(cond)) {                        \
+            p2pb_set_error(__VA_ARGS__);      \
+            return P2PB_ERR_INVALID;          \
+        }                                     \
+    } while (0)
+
+#define P2PB_CUDA_OK(expr)                                                                    \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            p2pb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return P2PB_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// launch check: never exit() (the reference does, cuda_utils.cuh:30-40); report through the return code
+#define P2PB_LAUNCH_OK()                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            p2pb_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return P2PB_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+static inline int p2pb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// number of SMs of the current device (148 on B200), cached
+int p2pb_num_sms();
+
+// squared distance with the reference's nvcc contraction order (see oracle/p2pb_oracle.c sqdist3):
+//   t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)
+__device__ __forceinline__ float sqdist3(float dx, float dy, float dz)
+{
+    float t = __fmul_rn(dy, dy);
+    t = __fmaf_rn(dx, dx, t);
+    t = __fmaf_rn(dz, dz, t);
+    return t;
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
+{
+    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+    unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }

@@ -1,0 +1,345 @@
+// ops_points.cu -- point-set ops of the PVCNN hot path: furthest point sampling, gather, ball query, grouping,
+// 3-NN inverse-distance interpolation.  Replaces the reference kernels
+//   third_party/openpoints/cpp/pointnet2_batch/src/pvcnn_sampling_gpu.cu:17-33,92-184
+//   .../pvcnn_ball_query_gpu.cu:19-56, .../pvcnn_grouping_gpu.cu:18-39, .../pvcnn_neighbor_interpolate_gpu.cu:20-124
+// which all launch <<<B, <=512>>> (one block per patch => at most B of the 148 SMs busy).  Here every kernel is
+// gridded over (patch x tile) so the whole chip is used, coordinates are staged in shared memory, neighbour
+// search uses warp ballots / shuffles, and gathers are coalesced.  Index results are bit-exact to the reference
+// (same fp32 contraction order, same tie-breaks); see oracle/p2pb_oracle.c.
+//
+// Feature tensors come in two layouts selected by `cl`:
+//   cl = 0  channel-first  [B, C, N]  (the reference's layout; used by the drop-in op API)
+//   cl = 1  channels-last  [B, N, ld] (rows; used by the fused engine, ld >= C)
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// Furthest point sampling.  One CTA per patch, the patch's points live in REGISTERS (P per thread), the running
+// min-distance too; per iteration: update + local argmax, one shuffle reduction, one barrier (double-buffered
+// exchange slots), second shuffle reduction.  The reference needs a strided smem/global scan plus a 9-level
+// __syncthreads tree per iteration (pvcnn_sampling_gpu.cu:122-182).
+// Tie-break of the reference restated as a key: winner = max d2, then min (k mod 512, k)  (see oracle).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fps_tie_key(int k)
+{
+    // smaller is better; (k mod 512) major, (k div 512) minor; inverted so that a u64 max picks the minimum
+    return 0xffffffffu - ((((unsigned)k & 511u) << 23) | ((unsigned)k >> 9));
+}
+__device__ __forceinline__ int fps_key_to_index(unsigned key)
+{
+    unsigned t = 0xffffffffu - key;
+    return (int)(((t & 0x7fffffu) << 9) | (t >> 23));
+}
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1) fps_reg_kernel(const float* __restrict__ coords, int N, int M,
+                                                       int* __restrict__ idx, float* __restrict__ centers)
+{
+    extern __shared__ float s_xyz[];  // [3][N]
+    __shared__ unsigned long long s_slot[2][32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int NW = T / 32;
+    coords += (size_t)b * 3 * N;
+    idx += (size_t)b * M;
+    float px[P], py[P], pz[P], pd[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int k = t + i * T;
+        if (k < N) {
+            px[i] = coords[k];
+            py[i] = coords[k + N];
+            pz[i] = coords[k + 2 * N];
+            s_xyz[k] = px[i];
+            s_xyz[k + N] = py[i];
+            s_xyz[k + 2 * N] = pz[i];
+        } else {
+            px[i] = py[i] = pz[i] = 0.f;
+        }
+        pd[i] = 1e38f;  // pvcnn_sampling.cpp:56
+    }
+    __syncthreads();
+    int old = 0;
+    if (t == 0) {
+        idx[0] = 0;
+        if (centers) {
+            centers[((size_t)b * 3 + 0) * M] = s_xyz[0];
+            centers[((size_t)b * 3 + 1) * M] = s_xyz[N];
+            centers[((size_t)b * 3 + 2) * M] = s_xyz[2 * N];
+        }
+    }
+    for (int j = 1; j < M; ++j) {
+        const float x1 = s_xyz[old], y1 = s_xyz[old + N], z1 = s_xyz[old + 2 * N];
+        unsigned long long best = 0ull;  // below any real candidate (d2 >= 0 has key bits > 0)
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int k = t + i * T;
+            const float d = sqdist3(px[i] - x1, py[i] - y1, pz[i] - z1);
+            const float d2 = fminf(d, pd[i]);
+            pd[i] = d2;
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(d2) << 32) | fps_tie_key(k);
+            if (k < N && cand > best) best = cand;
+        }
+        best = warp_max_u64(best);
+        if (lane == 0) s_slot[j & 1][warp] = best;
+        __syncthreads();
+        unsigned long long v = lane < NW ? s_slot[j & 1][lane] : 0ull;
+        v = warp_max_u64(v);
+        old = fps_key_to_index((unsigned)v);
+        if (t == 0) {
+            idx[j] = old;
+            if (centers) {
+                centers[((size_t)b * 3 + 0) * M + j] = s_xyz[old];
+                centers[((size_t)b * 3 + 1) * M + j] = s_xyz[old + N];
+                centers[((size_t)b * 3 + 2) * M + j] = s_xyz[old + 2 * N];
+            }
+        }
+    }
+}
+
+// Large clouds (object-level seed / merge FPS, N up to millions): distances in global memory, coordinates read
+// through L1/L2; same selection rule.  One CTA of 1024 threads per cloud.
+__global__ void __launch_bounds__(1024, 1) fps_global_kernel(const float* __restrict__ coords, int N, int M,
+                                                             float* __restrict__ dist, int* __restrict__ idx)
+{
+    __shared__ unsigned long long s_slot[2][32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    coords += (size_t)b * 3 * N;
+    dist += (size_t)b * N;
+    idx += (size_t)b * M;
+    for (int k = t; k < N; k += 1024) dist[k] = 1e38f;
+    __syncthreads();
+    int old = 0;
+    if (t == 0) idx[0] = 0;
+    for (int j = 1; j < M; ++j) {
+        const float x1 = coords[old], y1 = coords[old + N], z1 = coords[old + 2 * N];
+        unsigned long long best = 0ull;
+        for (int k = t; k < N; k += 1024) {
+            const float d = sqdist3(coords[k] - x1, coords[k + N] - y1, coords[k + 2 * N] - z1);
+            const float d2 = fminf(d, dist[k]);
+            dist[k] = d2;
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(d2) << 32) | fps_tie_key(k);
+            if (cand > best) best = cand;
+        }
+        best = warp_max_u64(best);
+        if (lane == 0) s_slot[j & 1][warp] = best;
+        __syncthreads();
+        unsigned long long v = s_slot[j & 1][lane];
+        v = warp_max_u64(v);
+        old = fps_key_to_index((unsigned)v);
+        if (t == 0) idx[j] = old;
+    }
+}
+
+template <int P, int T>
+static int launch_fps_reg(const float* coords, int B, int N, int M, int* idx, float* centers, cudaStream_t s)
+{
+    const size_t smem = (size_t)3 * N * sizeof(float);
+    if (smem > 48 * 1024)
+        P2PB_CUDA_OK(cudaFuncSetAttribute(fps_reg_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_reg_kernel<P, T><<<B, T, smem, s>>>(coords, N, M, idx, centers);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// coords [B,3,N] -> idx int32 [B,M] (+ optional centers [B,3,M] = coords gathered at idx, fused)
+// scratch: only needed when N > 16384 (B*N floats)
+P2PB_API int p2pb_furthest_point_sampling(const float* coords, int B, int N, int M, int* idx, float* centers,
+                                          float* scratch, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    P2PB_CHECK_ARG(B >= 0 && N > 0 && M >= 0, "fps: bad sizes B=%d N=%d M=%d", B, N, M);
+    if (B == 0 || M == 0) return P2PB_OK;
+    if (N <= 256) return launch_fps_reg<1, 256>(coords, B, N, M, idx, centers, s);
+    if (N <= 512) return launch_fps_reg<2, 256>(coords, B, N, M, idx, centers, s);
+    if (N <= 1024) return launch_fps_reg<4, 256>(coords, B, N, M, idx, centers, s);
+    if (N <= 2048) return launch_fps_reg<8, 256>(coords, B, N, M, idx, centers, s);
+    if (N <= 4096) return launch_fps_reg<8, 512>(coords, B, N, M, idx, centers, s);
+    if (N <= 8192) return launch_fps_reg<8, 1024>(coords, B, N, M, idx, centers, s);
+    if (N <= 16384) return launch_fps_reg<16, 1024>(coords, B, N, M, idx, centers, s);
+    P2PB_CHECK_ARG(scratch != nullptr, "fps: N=%d > 16384 needs a B*N float scratch buffer", N);
+    P2PB_CHECK_ARG(centers == nullptr, "fps: fused centre gather only for N <= 16384");
+    fps_global_kernel<<<B, 1024, 0, s>>>(coords, N, M, scratch, idx);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gather_features: out[b,c,j] = feat[b,c,idx[b,j]]        (pvcnn_sampling_gpu.cu:17-33)
+// grouping:        out[b,c,j,k] = feat[b,c,idx[b,j,k]]    (pvcnn_grouping_gpu.cu:18-39)  == gather with M*U indices
+// channel-first: thread per (c, j) with j fastest (coalesced index reads and writes).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gather_cf_kernel(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
+                                 int C, int N, int M)
+{
+    const int b = blockIdx.z;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const int src = idx[(size_t)b * M + j];
+    const float* f = feat + (size_t)b * C * N;
+    float* o = out + (size_t)b * C * M;
+    for (int c = blockIdx.y; c < C; c += gridDim.y) o[(size_t)c * M + j] = __ldg(f + (size_t)c * N + src);
+}
+
+P2PB_API int p2pb_gather_features(const float* feat, const int* idx, float* out, int B, int C, int N, int M,
+                                  void* stream)
+{
+    P2PB_CHECK_ARG(B >= 0 && C > 0 && N > 0 && M >= 0, "gather: bad sizes");
+    if (B == 0 || M == 0) return P2PB_OK;
+    dim3 grid(p2pb_cdiv(M, 256), C < 64 ? C : 64, B);
+    gather_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, idx, out, C, N, M);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+P2PB_API int p2pb_grouping(const float* feat, const int* idx, float* out, int B, int C, int N, int M, int U,
+                           void* stream)
+{
+    return p2pb_gather_features(feat, idx, out, B, C, N, M * U, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ball query (pvcnn_ball_query_gpu.cu:19-56): first U points (in index order) with d2 < r2, padded with the first
+// hit, all-zero row when the ball is empty.  One WARP per centre: 32 points tested per step, ballot + popc
+// compaction preserves index order, early exit when U are found.  Points staged in shared memory per CTA.
+// ---------------------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) ball_query_kernel(const float* __restrict__ centers,
+                                                                const float* __restrict__ points, int M, int N,
+                                                                float r2, int U, int* __restrict__ out)
+{
+    extern __shared__ float s_pts[];  // [3][N]
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    points += (size_t)b * 3 * N;
+    centers += (size_t)b * 3 * M;
+    for (int i = threadIdx.x; i < 3 * N; i += WARPS * 32) s_pts[i] = points[i];
+    __syncthreads();
+    for (int j = blockIdx.x * WARPS + warp; j < M; j += gridDim.x * WARPS) {
+        const float cx = centers[j], cy = centers[j + M], cz = centers[j + 2 * M];
+        int* o = out + ((size_t)b * M + j) * U;
+        int cnt = 0, first = 0;
+        for (int k0 = 0; k0 < N && cnt < U; k0 += 32) {
+            const int k = k0 + lane;
+            bool hit = false;
+            if (k < N) hit = sqdist3(cx - s_pts[k], cy - s_pts[k + N], cz - s_pts[k + 2 * N]) < r2;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                if (cnt == 0) first = k0 + __ffs(m) - 1;
+                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                if (hit && slot < U) o[slot] = k;
+                cnt += __popc(m);
+            }
+        }
+        if (cnt > U) cnt = U;
+        // pad with the first hit (or zeros when empty: reference output is zero-initialised)
+        for (int v = cnt + lane; v < U; v += 32) o[v] = first;
+    }
+}
+
+P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, int M, int N, float radius, int U,
+                             int* out, void* stream)
+{
+    P2PB_CHECK_ARG(B >= 0 && M >= 0 && N > 0 && U > 0, "ball_query: bad sizes");
+    if (B == 0 || M == 0) return P2PB_OK;
+    const float r2 = radius * radius;  // pvcnn_ball_query.cpp:25 (fp32 product)
+    const size_t smem = (size_t)3 * N * sizeof(float);
+    P2PB_CHECK_ARG(smem <= 200 * 1024, "ball_query: N=%d too large for shared-memory staging", N);
+    constexpr int WARPS = 8;
+    if (smem > 48 * 1024)
+        P2PB_CUDA_OK(cudaFuncSetAttribute(ball_query_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int gx = p2pb_cdiv(M, WARPS);
+    // enough CTAs per patch to fill the chip, but not so many that staging the points dominates
+    const int want = p2pb_cdiv(2 * p2pb_num_sms(), B);
+    if (gx > want) gx = want < 1 ? 1 : want;
+    ball_query_kernel<WARPS><<<dim3(gx, B), WARPS * 32, smem, (cudaStream_t)stream>>>(centers, points, M, N, r2, U, out);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 3-NN search (pvcnn_neighbor_interpolate_gpu.cu:20-81): per point the 3 nearest centres (strict <, first wins),
+// weights from SQUARED distances clamped to [1e-10, 1e10].  The reference keeps the running bests as doubles
+// initialised to 1e40; fp32 with +inf is equivalent (every candidate is an fp32 value, inf and 1e40 both clamp
+// to 1e10, and the double products of two fp32 values round to the fp32 product).  Centres staged in smem.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ points, const float* __restrict__ centers,
+                                                       int N, int M, int* __restrict__ idx, float* __restrict__ w)
+{
+    extern __shared__ float s_c[];  // [3][M]
+    const int b = blockIdx.y;
+    points += (size_t)b * 3 * N;
+    centers += (size_t)b * 3 * M;
+    for (int i = threadIdx.x; i < 3 * M; i += blockDim.x) s_c[i] = centers[i];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const float ux = points[j], uy = points[j + N], uz = points[j + 2 * N];
+    float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY;
+    int i0 = 0, i1 = 0, i2 = 0;
+    for (int k = 0; k < M; ++k) {
+        const float d = sqdist3(ux - s_c[k], uy - s_c[k + M], uz - s_c[k + 2 * M]);
+        if (d < b2) {
+            b2 = d; i2 = k;
+            if (d < b1) {
+                b2 = b1; i2 = i1; b1 = d; i1 = k;
+                if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = k; }
+            }
+        }
+    }
+    b0 = fmaxf(fminf(1e10f, b0), 1e-10f);
+    b1 = fmaxf(fminf(1e10f, b1), 1e-10f);
+    b2 = fmaxf(fminf(1e10f, b2), 1e-10f);
+    const float d0d1 = __fmul_rn(b0, b1), d0d2 = __fmul_rn(b0, b2), d1d2 = __fmul_rn(b1, b2);
+    const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+    int* ix = idx + (size_t)b * 3 * N;
+    float* ww = w + (size_t)b * 3 * N;
+    ww[j] = __fmul_rn(d1d2, inv); ix[j] = i0;
+    ww[j + N] = __fmul_rn(d0d2, inv); ix[j + N] = i1;
+    ww[j + 2 * N] = __fmul_rn(d0d1, inv); ix[j + 2 * N] = i2;
+}
+
+// out[b,c,j] = f[c,i2]*w2 (+fma) f[c,i1]*w1 (+fma) f[c,i3]*w3   (contraction order of the reference build, see oracle)
+__global__ void interp_cf_kernel(const float* __restrict__ cfeat, const int* __restrict__ idx, const float* __restrict__ w,
+                                 float* __restrict__ out, int C, int N, int M)
+{
+    const int b = blockIdx.z;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int* ix = idx + (size_t)b * 3 * N;
+    const float* ww = w + (size_t)b * 3 * N;
+    const int i1 = ix[j], i2 = ix[j + N], i3 = ix[j + 2 * N];
+    const float w1 = ww[j], w2 = ww[j + N], w3 = ww[j + 2 * N];
+    const float* f = cfeat + (size_t)b * C * M;
+    float* o = out + (size_t)b * C * N;
+    for (int c = blockIdx.y; c < C; c += gridDim.y) {
+        const float* fc = f + (size_t)c * M;
+        float acc = __fmul_rn(__ldg(fc + i2), w2);
+        acc = __fmaf_rn(__ldg(fc + i1), w1, acc);
+        acc = __fmaf_rn(__ldg(fc + i3), w3, acc);
+        o[(size_t)c * N + j] = acc;
+    }
+}
+
+P2PB_API int p2pb_three_nn(const float* points, const float* centers, int B, int N, int M, int* idx, float* w,
+                           void* stream)
+{
+    P2PB_CHECK_ARG(B >= 0 && N > 0 && M > 0, "three_nn: bad sizes");
+    if (B == 0) return P2PB_OK;
+    const size_t smem = (size_t)3 * M * sizeof(float);
+    P2PB_CHECK_ARG(smem <= 200 * 1024, "three_nn: M=%d too large for shared-memory staging", M);
+    if (smem > 48 * 1024)
+        P2PB_CUDA_OK(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    three_nn_kernel<<<dim3(p2pb_cdiv(N, 256), B), 256, smem, (cudaStream_t)stream>>>(points, centers, N, M, idx, w);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+P2PB_API int p2pb_three_nn_interpolate(const float* points, const float* centers, const float* cfeat, int B, int C,
+                                       int N, int M, float* out, int* idx, float* w, void* stream)
+{
+    int rc = p2pb_three_nn(points, centers, B, N, M, idx, w, stream);
+    if (rc != P2PB_OK || B == 0) return rc;
+    P2PB_CHECK_ARG(C > 0, "three_nn_interpolate: bad C");
+    dim3 grid(p2pb_cdiv(N, 256), C < 64 ? C : 64, B);
+    interp_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cfeat, idx, w, out, C, N, M);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}

@@ -1,0 +1,184 @@
+"""Torch-tensor front end of the point/voxel kernels in ``libp2pb_b200.so``.
+
+Reference-layout ops (channel-first ``[B,C,N]`` fp32 / int32, contiguous CUDA tensors), one function per native
+op the reference's hot path calls (``third_party/openpoints/cpp/pointnet2_batch/src/pointnet2_api.cpp:31-47``).
+Outputs are fresh torch tensors owned by the caller; kernels are enqueued on torch's CURRENT stream (the
+reference mixes current-stream and legacy-default-stream launches).  CUDA only -- no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import P2PBError, call
+
+_f = ctypes.c_float
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise P2PBError(f"{name} must be a CUDA tensor (no CPU path)")
+    if t.dtype != dtype:
+        raise P2PBError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise P2PBError(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise P2PBError(f"{name} must have {ndim} dims, got {tuple(t.shape)}")
+
+
+def furthest_point_sampling(coords: torch.Tensor, num_samples: int, return_centers: bool = False):
+    """coords [B,3,N] -> idx int32 [B,M] (start index 0, reference tie-break); optionally the gathered centres."""
+    _chk(coords, torch.float32, "coords", 3)
+    B, _, N = coords.shape
+    M = int(num_samples)
+    idx = torch.empty((B, M), dtype=torch.int32, device=coords.device)
+    fuse = return_centers and N <= 16384
+    centers = torch.empty((B, 3, M), dtype=torch.float32, device=coords.device) if fuse else None
+    scratch = torch.empty((B, N), dtype=torch.float32, device=coords.device) if N > 16384 else None
+    with torch.cuda.device(coords.device):
+        call("p2pb_furthest_point_sampling", _ptr(coords), B, N, M, _ptr(idx), _ptr(centers), _ptr(scratch), _stream())
+    if return_centers:
+        if centers is None:
+            centers = gather_features(coords, idx)
+        return idx, centers
+    return idx
+
+
+def gather_features(features: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    _chk(features, torch.float32, "features", 3)
+    _chk(indices, torch.int32, "indices", 2)
+    B, C, N = features.shape
+    M = indices.shape[1]
+    out = torch.empty((B, C, M), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        call("p2pb_gather_features", _ptr(features), _ptr(indices), _ptr(out), B, C, N, M, _stream())
+    return out
+
+
+def grouping(features: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    _chk(features, torch.float32, "features", 3)
+    _chk(indices, torch.int32, "indices", 3)
+    B, C, N = features.shape
+    _, M, U = indices.shape
+    out = torch.empty((B, C, M, U), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        call("p2pb_grouping", _ptr(features), _ptr(indices), _ptr(out), B, C, N, M, U, _stream())
+    return out
+
+
+def ball_query(centers: torch.Tensor, points: torch.Tensor, radius: float, num_neighbors: int) -> torch.Tensor:
+    _chk(centers, torch.float32, "centers_coords", 3)
+    _chk(points, torch.float32, "points_coords", 3)
+    B, _, M = centers.shape
+    N = points.shape[2]
+    out = torch.empty((B, M, int(num_neighbors)), dtype=torch.int32, device=centers.device)
+    with torch.cuda.device(centers.device):
+        call("p2pb_ball_query", _ptr(centers), _ptr(points), B, M, N, _f(radius), int(num_neighbors), _ptr(out), _stream())
+    return out
+
+
+def three_nn_interpolate(points: torch.Tensor, centers: torch.Tensor, centers_features: torch.Tensor):
+    _chk(points, torch.float32, "points_coords", 3)
+    _chk(centers, torch.float32, "centers_coords", 3)
+    _chk(centers_features, torch.float32, "centers_features", 3)
+    B, _, N = points.shape
+    M = centers.shape[2]
+    C = centers_features.shape[1]
+    dev = points.device
+    out = torch.empty((B, C, N), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, 3, N), dtype=torch.int32, device=dev)
+    w = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_three_nn_interpolate", _ptr(points), _ptr(centers), _ptr(centers_features), B, C, N, M,
+             _ptr(out), _ptr(idx), _ptr(w), _stream())
+    return out, idx, w
+
+
+def avg_voxelize(features: torch.Tensor, coords: torch.Tensor, resolution: int):
+    """features [B,C,N], int32 voxel coords [B,3,N] -> (grid [B,C,r^3], ind [B,N], cnt [B,r^3])."""
+    _chk(features, torch.float32, "features", 3)
+    _chk(coords, torch.int32, "coords", 3)
+    B, C, N = features.shape
+    r = int(resolution)
+    dev = features.device
+    out = torch.empty((B, C, r ** 3), dtype=torch.float32, device=dev)
+    ind = torch.empty((B, N), dtype=torch.int32, device=dev)
+    cnt = torch.empty((B, r ** 3), dtype=torch.int32, device=dev)
+    order = torch.empty((B, N), dtype=torch.int32, device=dev)
+    start = torch.empty((B, r ** 3), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_avg_voxelize", _ptr(features), _ptr(coords), B, C, N, r, _ptr(out), _ptr(ind), _ptr(cnt),
+             _ptr(order), _ptr(start), _stream())
+    return out, ind, cnt
+
+
+def voxel_prep(coords: torch.Tensor, resolution: int, normalize: bool = True, eps: float = 0.0):
+    """Fused ``Voxelization.forward`` coordinate prep (models/pvcnn.py:215-231) + CSR build.
+
+    coords [B,3,N] -> dict(norm_coords [B,3,N], ind [B,N], order [B,N], start [B,r^3], cnt [B,r^3])."""
+    _chk(coords, torch.float32, "coords", 3)
+    B, _, N = coords.shape
+    r = int(resolution)
+    dev = coords.device
+    nc = torch.empty_like(coords)
+    ind = torch.empty((B, N), dtype=torch.int32, device=dev)
+    order = torch.empty((B, N), dtype=torch.int32, device=dev)
+    start = torch.empty((B, r ** 3), dtype=torch.int32, device=dev)
+    cnt = torch.empty((B, r ** 3), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_voxel_prep", _ptr(coords), B, N, r, int(bool(normalize)), _f(eps), _ptr(nc), _ptr(ind), _ptr(order),
+             _ptr(start), _ptr(cnt), _stream())
+    return {"norm_coords": nc, "ind": ind, "order": order, "start": start, "cnt": cnt, "r": r}
+
+
+def trilinear_devoxelize(coords: torch.Tensor, grid: torch.Tensor, resolution: int) -> torch.Tensor:
+    """coords [B,3,N] in [0,r-1], grid [B,C,r^3] -> [B,C,N] (inference branch of the reference op)."""
+    _chk(coords, torch.float32, "coords", 3)
+    _chk(grid, torch.float32, "features", 3)
+    B, C, _ = grid.shape
+    N = coords.shape[2]
+    out = torch.empty((B, C, N), dtype=torch.float32, device=grid.device)
+    with torch.cuda.device(grid.device):
+        call("p2pb_trilinear_devoxelize", _ptr(coords), _ptr(grid), B, C, N, int(resolution), _ptr(out), _stream())
+    return out
+
+
+def nm_distance(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """xyz1 [B,n,3], xyz2 [B,m,3] -> (squared NN distance [B,n], index int32 [B,n]); chamfer3D.cu:12-134."""
+    _chk(xyz1, torch.float32, "xyz1", 3)
+    _chk(xyz2, torch.float32, "xyz2", 3)
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    dist = torch.empty((B, n), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, n), dtype=torch.int32, device=dev)
+    scratch = torch.empty((B, n), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_nm_distance", _ptr(xyz1), _ptr(xyz2), B, n, m, _ptr(dist), _ptr(idx), _ptr(scratch), _stream())
+    return dist, idx
+
+
+def chamfer_forward(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """``chamfer_3D.forward`` results: dist1, dist2, idx1, idx2 (metrics/chamfer3D/chamfer_cuda.cpp)."""
+    d1, i1 = nm_distance(xyz1, xyz2)
+    d2, i2 = nm_distance(xyz2, xyz1)
+    return d1, d2, i1, i2
+
+
+def calculate_cd(pred: torch.Tensor, gt: torch.Tensor):
+    """metrics/metrics.py:56-83 ``calculate_cd_cuda``: per-sample mean(d1)+mean(d2) of squared NN distances."""
+    if pred.shape[-1] != 3:
+        pred = pred.transpose(-1, -2)
+        gt = gt.transpose(-1, -2)
+    d1, d2, _, _ = chamfer_forward(pred.contiguous(), gt.contiguous())
+    return (d1.mean(dim=1) + d2.mean(dim=1)).cpu().tolist()

@@ -1,0 +1,208 @@
+"""``P2PB``: the diffusion Schroedinger-bridge wrapper -- schedule tables and the T-step sampling loop -- with the
+reference's constructor, attributes, state-dict layout and ``sample(...)`` contract (``models/p2pb.py:70-363``).
+
+Only the sampling half is implemented (training is out of scope).  ``sample`` drives either
+  * ``backend="engine"`` (default): the fused channels-last CUDA engine, all T steps captured in a CUDA graph, or
+  * ``backend="eager"``: ``PVCNN2Unet.forward`` step by step (reference-shaped path, used for validation).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+
+def space_indices(num_steps: int, count: int) -> List[int]:
+    """``count`` indices spread over ``num_steps`` using Python ``round`` on an accumulated stride (p2pb.py:16-40)."""
+    assert count <= num_steps
+    stride = 1 if count <= 1 else (num_steps - 1) / (count - 1)
+    cur, taken = 0.0, []
+    for _ in range(count):
+        taken.append(round(cur))
+        cur += stride
+    return taken
+
+
+def make_beta_schedule(n_timestep: int = 1000, linear_start: float = 1e-4, linear_end: float = 2e-2) -> np.ndarray:
+    scale = 1000 / n_timestep  # p2pb.py:62-67
+    linear_start *= scale
+    linear_end *= scale
+    return (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2).numpy()
+
+
+def compute_gaussian_product_coef(sigma1, sigma2):
+    denom = sigma1 ** 2 + sigma2 ** 2  # p2pb.py:54-59
+    return sigma2 ** 2 / denom, sigma1 ** 2 / denom, (sigma1 ** 2 * sigma2 ** 2) / denom
+
+
+class EMA(nn.Module):
+    """Minimal stand-in for ``ema_pytorch.EMA`` (not installed; unpinned dependency of the reference):
+    holds ``ema_model`` (the averaged copy evaluated at sampling time) and registers the online model so that
+    ``ema.ema_model.*`` / ``ema.online_model.*`` / ``ema.initted`` / ``ema.step`` keys of a reference checkpoint
+    load.  The copy is kept in eval mode: sampling with active Dropout (SURVEY.md §7 "EMA path semantics") is
+    not reproduced."""
+
+    def __init__(self, model: nn.Module, beta: float = 0.999):
+        super().__init__()
+        self.beta = beta
+        self.online_model = model
+        self.ema_model = copy.deepcopy(model).eval()
+        for p in self.ema_model.parameters():
+            p.requires_grad_(False)
+        self.register_buffer("initted", torch.tensor(False))
+        self.register_buffer("step", torch.tensor(0))
+
+    def forward(self, *a, **k):
+        return self.ema_model(*a, **k)
+
+
+class P2PB(nn.Module):
+    def __init__(self, cfg, model: nn.Module):
+        super().__init__()
+        d = cfg.diffusion
+        device = cfg.gpu if cfg.get("gpu") is not None else torch.device("cuda")
+        self.device = device
+        self.cfg = cfg
+        self.timesteps = d.timesteps
+        self.sampling_timesteps = d.sampling_timesteps
+        self.ot_ode = d.ot_ode
+        self.cond_x1 = d.get("cond_x1", False)
+        self.add_x1_noise = d.get("add_x1_noise", False)
+        self.objective = d.get("objective", "pred_noise")
+        self.symmetric = d.get("symmetric", True)
+        self.model = model.to(device)
+        self.ema = EMA(self.model, beta=0.999) if cfg.model.get("ema") else None
+
+        betas = make_beta_schedule(n_timestep=d.timesteps, linear_start=d.beta_start, linear_end=d.beta_end)
+        if self.symmetric:
+            betas = np.concatenate([betas[: d.timesteps // 2], np.flip(betas[: d.timesteps // 2])])
+        self.noise_levels = torch.linspace(d.t0, d.T, d.timesteps, dtype=torch.float32).to(device) * d.timesteps
+        std_fwd = np.sqrt(np.cumsum(betas))
+        std_bwd = np.sqrt(np.flip(np.cumsum(np.flip(betas))))
+        mu_x0, mu_x1, var = compute_gaussian_product_coef(std_fwd, std_bwd)
+        to_t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32).to(device)
+        self.betas, self.std_fwd, self.std_bwd = to_t(betas), to_t(std_fwd), to_t(std_bwd)
+        self.std_sb, self.mu_x0, self.mu_x1 = to_t(np.sqrt(var)), to_t(mu_x0), to_t(mu_x1)
+        # training-only table kept for state/attribute compatibility (non-persistent, p2pb.py:132-149)
+        alphas_cumprod = np.cumprod(1 - betas)
+        snr = torch.from_numpy(alphas_cumprod / (1 - alphas_cumprod))
+        self.register_buffer("loss_weight", (snr / snr).to(torch.float32).to(device), persistent=False)
+        self._engines: Dict[tuple, object] = {}
+        self.backend = cfg.get("backend", "engine")
+
+    # -- reference API surface -------------------------------------------------------------------------
+    def multi_gpu_wrapper(self, f):
+        self.model = f(self.model)
+
+    def train(self, mode: bool = True):  # only the online model toggles (train_utils.py:37-43)
+        self.model.train(mode)
+        return self
+
+    def eval(self):
+        self.model.eval()
+        return self
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training forward/loss (p2pb.py:373-413) is out of scope of the B200 hot path")
+
+    def get_std_fwd(self, step, xdim: Tuple[int, ...] = None):
+        s = self.std_fwd[step]
+        return s if xdim is None else s[(...,) + (None,) * len(xdim)]
+
+    def compute_pred_x0_from_eps(self, step, xt: Tensor, net_out: Tensor, clip_denoise: bool = False) -> Tensor:
+        std_fwd = self.get_std_fwd(step, xdim=xt.shape[1:])  # p2pb.py:155-165
+        if std_fwd.ndim != net_out.ndim:
+            std_fwd = std_fwd.squeeze(-1)
+        pred_x0 = xt - std_fwd * net_out
+        if clip_denoise:
+            pred_x0.clamp_(-3.0, 3.0)
+        return pred_x0
+
+    def p_posterior(self, nprev: int, n: int, x_n: Tensor, x0: Tensor) -> Tensor:
+        assert nprev < n  # p2pb.py:190-213
+        std_n, std_nprev = self.std_fwd[n], self.std_fwd[nprev]
+        std_delta = (std_n ** 2 - std_nprev ** 2).sqrt()
+        mu_x0, mu_xn, var = compute_gaussian_product_coef(std_nprev, std_delta)
+        xt_prev = mu_x0 * x0 + mu_xn * x_n
+        if not self.ot_ode and nprev > 0:
+            xt_prev = xt_prev + var.sqrt() * torch.randn_like(xt_prev)
+        return xt_prev
+
+    def posterior_coefs(self, nprev: int, n: int) -> Tuple[float, float, float]:
+        """(std_fwd[n], mu_x0, mu_xn) as fp32 scalars computed exactly like ``p_posterior`` does on device."""
+        s = self.std_fwd.detach().cpu()
+        std_n, std_p = s[n], s[nprev]
+        std_delta = (std_n ** 2 - std_p ** 2).sqrt()
+        mu_x0, mu_xn, _ = compute_gaussian_product_coef(std_p, std_delta)
+        return float(std_n), float(mu_x0), float(mu_xn)
+
+    # -- sampling ----------------------------------------------------------------------------------------
+    def _net(self, use_ema: bool):
+        net = self.ema.ema_model if (use_ema and self.ema is not None) else self.model
+        return net.module if hasattr(net, "module") else net
+
+    @torch.no_grad()
+    def ddpm_sampling(self, x1: Tensor, x_cond: Tensor = None, clip_denoise: bool = False, sampling_steps: int = None,
+                      log_count: int = 10, verbose: bool = True, use_ema: bool = False, backend: Optional[str] = None):
+        sampling_steps = sampling_steps or self.timesteps - 1
+        assert 0 < sampling_steps < self.timesteps == len(self.betas)
+        steps = space_indices(self.timesteps, sampling_steps + 1)
+        log_count = min(len(steps) - 1, log_count)
+        log_steps = [steps[i] for i in space_indices(len(steps) - 1, log_count)]
+        assert steps[0] == log_steps[0] == 0
+        if self.add_x1_noise:
+            x1 = x1 + torch.randn_like(x1)
+        if self.cond_x1:
+            x_cond = x1 if x_cond is None else torch.cat([x1, x_cond], dim=1)
+        backend = backend or self.backend
+        net = self._net(use_ema)
+        was_training = self.model.training
+        self.model.eval()
+        rev = steps[::-1]
+        pairs = list(zip(rev[1:], rev[:-1]))
+        if backend == "engine" and self.ot_ode and self.objective == "pred_noise":
+            from .engine import get_engine
+
+            eng = get_engine(self, net, x1.shape, None if x_cond is None else x_cond.shape)
+            xs, x0s = eng.sample(x1, x_cond, pairs, log_steps, clip_denoise)
+        else:
+            xt = x1.detach().to(self.device)
+            xs, x0s = [], []
+            B = xt.shape[0]
+            it = pairs
+            if verbose:
+                try:
+                    from tqdm import tqdm
+                    it = tqdm(pairs, desc="DDPM sampling", total=len(pairs))
+                except ImportError:
+                    pass
+            for prev_step, step in it:
+                st = torch.full((B,), step, device=xt.device, dtype=torch.long)
+                out = net(xt, self.noise_levels[st], x_cond=x_cond)
+                pred_x0 = self.compute_pred_x0_from_eps(st, xt, out, clip_denoise) if self.objective == "pred_noise" else out
+                xt = self.p_posterior(prev_step, step, xt, pred_x0)
+                if prev_step in log_steps:
+                    x0s.append(pred_x0)
+                    xs.append(xt)
+            flip = lambda z: torch.flip(torch.stack(z, dim=1), dims=(1,))
+            xs, x0s = flip(xs), flip(x0s)
+        assert xs.shape == x0s.shape == (x1.shape[0], log_count, *x1.shape[1:])
+        if was_training:
+            self.model.train()
+        return xs, x0s
+
+    @torch.no_grad()
+    def sample(self, x_cond: Optional[Tensor] = None, x_start: Optional[Tensor] = None, clip: bool = False,
+               use_ema: bool = False, verbose: bool = True, log_count: int = 10, steps: int = None,
+               backend: Optional[str] = None) -> Dict:
+        """Same contract as ``P2PB.sample`` (p2pb.py:337-363): {"x_chain" [B,log_count,3,N], "x_pred", "x_start"}."""
+        if self.cfg.diffusion.sampling_strategy != "DDPM":
+            raise NotImplementedError(self.cfg.diffusion.sampling_strategy)
+        xs, x0s = self.ddpm_sampling(x1=x_start, x_cond=x_cond, clip_denoise=clip,
+                                     sampling_steps=self.cfg.diffusion.sampling_timesteps if steps is None else steps,
+                                     verbose=verbose, use_ema=use_ema, log_count=log_count, backend=backend)
+        return {"x_chain": xs, "x_pred": xs[:, 0, ...], "x_start": x_start}

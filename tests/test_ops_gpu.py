@@ -1,0 +1,148 @@
+"""GPU parity tests of the point/voxel kernels, called through the C ABI (ctypes), against the oracle on the same
+seeded inputs.  Bar: bit-exact for indices AND for every fp32 output (same contraction order, deterministic sums)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import cloud
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from oracle import ops as OO
+    from p2pb_b200 import ops, pointnet2_batch_cuda as P
+
+    return OO, ops, P
+
+
+CASES = [(2, 2048, 512, None), (3, 1024, 256, 8.0), (2, 8192, 2048, None), (4, 128, 32, None), (2, 32, 8, 4.0),
+         (1, 1000, 250, None)]
+
+
+@pytest.mark.parametrize("B,N,M,snap", CASES)
+def test_fps_gather_ball_group_bit_exact(mods, B, N, M, snap):
+    OO, ops, P = mods
+    coords = cloud(B, N, seed=N + M, snap=snap)
+    cd = coords.cuda()
+    idx = P.furthest_point_sampling_forward(cd, M)
+    ref_idx = OO.furthest_point_sampling_forward(coords, M)
+    assert torch.equal(idx.cpu(), ref_idx)
+    idx2, centers = ops.furthest_point_sampling(cd, M, return_centers=True)
+    ref_centers = OO.gather_features_forward(coords, ref_idx)
+    assert torch.equal(idx2.cpu(), ref_idx) and torch.equal(centers.cpu(), ref_centers)
+    assert torch.equal(P.gather_features_forward(cd, idx).cpu(), ref_centers)
+    for radius in (0.1, 0.4):
+        nidx = P.ball_query(centers, cd, radius, 32)
+        ref_n = OO.ball_query(ref_centers, coords, radius, 32)
+        assert torch.equal(nidx.cpu(), ref_n), radius
+    feats = torch.randn(B, 7, N, generator=torch.Generator().manual_seed(1))
+    g = P.grouping_forward(feats.cuda(), nidx)
+    assert torch.equal(g.cpu(), OO.grouping_forward(feats, ref_n))
+
+
+@pytest.mark.parametrize("B,N,M,C", [(2, 2048, 512, 16), (3, 512, 128, 5), (2, 32, 8, 64), (1, 8192, 2048, 4)])
+def test_three_nn_interpolate_bit_exact(mods, B, N, M, C):
+    OO, ops, P = mods
+    pts = cloud(B, N, seed=3)
+    ctr = pts[:, :, ::N // M].contiguous()  # centres coincide with points -> zero distances hit the 1e-10 clamp
+    cf = torch.randn(B, C, M, generator=torch.Generator().manual_seed(2))
+    out, idx, w = P.three_nearest_neighbors_interpolate_forward(pts.cuda(), ctr.cuda(), cf.cuda())
+    ro, ri, rw = OO.three_nearest_neighbors_interpolate_forward(pts, ctr, cf)
+    assert torch.equal(idx.cpu(), ri)
+    assert torch.equal(w.cpu(), rw)
+    assert torch.equal(out.cpu(), ro)
+
+
+@pytest.mark.parametrize("B,N,C,r", [(2, 2048, 35, 32), (3, 512, 8, 16), (2, 128, 16, 8), (1, 8192, 4, 32), (2, 100, 3, 4)])
+def test_voxelize_devoxelize_bit_exact(mods, B, N, C, r):
+    OO, ops, P = mods
+    coords = cloud(B, N, seed=7 + r)
+    feats = torch.randn(B, C, N, generator=torch.Generator().manual_seed(4))
+    prep = ops.voxel_prep(coords.cuda(), r)
+    nc, vc = OO.voxel_coords(coords, r)
+    assert torch.equal(prep["norm_coords"].cpu(), nc)
+    ref_out, ref_ind, ref_cnt = OO.avg_voxelize_forward(feats, vc, r)
+    assert torch.equal(prep["ind"].cpu(), ref_ind) and torch.equal(prep["cnt"].cpu(), ref_cnt)
+    # CSR: order is sorted by (voxel, point index) and start/cnt partition it
+    order, start, cnt = prep["order"].cpu(), prep["start"].cpu(), prep["cnt"].cpu()
+    for b in range(B):
+        ind_sorted = ref_ind[b][order[b].long()]
+        assert torch.all(ind_sorted[1:] >= ind_sorted[:-1])
+        assert sorted(order[b].tolist()) == list(range(N))
+        occ = torch.nonzero(cnt[b]).flatten()
+        assert int(cnt[b].sum()) == N
+        v = occ[len(occ) // 2].item()
+        seg = order[b][start[b][v]: start[b][v] + cnt[b][v]]
+        assert torch.all(ref_ind[b][seg.long()] == v) and torch.all(seg[1:] > seg[:-1])
+    out, ind, cnt2 = P.avg_voxelize_forward(feats.cuda(), vc.cuda(), r)
+    assert torch.equal(ind.cpu(), ref_ind) and torch.equal(cnt2.cpu(), ref_cnt)
+    assert torch.equal(out.cpu(), ref_out)  # deterministic index-ordered sums: bit-exact, unlike the reference's atomics
+    grid = torch.randn(B, C, r ** 3, generator=torch.Generator().manual_seed(5))
+    dv = P.trilinear_devoxelize_forward(r, False, prep["norm_coords"], grid.cuda())[0]
+    assert torch.equal(dv.cpu(), OO.trilinear_devoxelize_forward(r, False, nc, grid)[0])
+
+
+def test_voxelize_all_points_in_one_voxel_and_r_minus_1_corner(mods):
+    OO, ops, P = mods
+    B, N, C, r = 1, 64, 4, 8
+    vc = torch.zeros(B, 3, N, dtype=torch.int32)
+    vc[:, :, N // 2:] = r - 1
+    feats = torch.randn(B, C, N, generator=torch.Generator().manual_seed(9))
+    out, ind, cnt = P.avg_voxelize_forward(feats.cuda(), vc.cuda(), r)
+    ro, ri, rc = OO.avg_voxelize_forward(feats, vc, r)
+    assert torch.equal(out.cpu(), ro) and torch.equal(cnt.cpu(), rc)
+    # devox exactly at integer coordinates incl. r-1: hi-corner must not be touched (trilinear_devox_gpu.cu:66-68)
+    coords = torch.tensor([[[0.0, float(r - 1), 3.0], [0.0, float(r - 1), 2.5], [0.0, float(r - 1), 7.0]]])
+    grid = torch.randn(1, C, r ** 3, generator=torch.Generator().manual_seed(3))
+    dv = P.trilinear_devoxelize_forward(r, False, coords.cuda(), grid.cuda())[0]
+    assert torch.equal(dv.cpu(), OO.trilinear_devoxelize_forward(r, False, coords, grid)[0])
+
+
+@pytest.mark.parametrize("B,n,m", [(2, 2048, 2048), (1, 8192, 5000), (3, 100, 1500), (64, 2048, 2048)])
+def test_chamfer_bit_exact(mods, B, n, m):
+    OO, ops, P = mods
+    a = cloud(B, n, seed=1, snap=16.0 if B == 3 else None).transpose(1, 2).contiguous()
+    b = (cloud(B, m, seed=2, snap=16.0 if B == 3 else None) * 1.02).transpose(1, 2).contiguous()
+    if B == 64:  # full bench batch: property checks only (self-distance is zero, symmetric use)
+        d1, d2, i1, i2 = ops.chamfer_forward(a.cuda(), a.cuda())
+        assert float(d1.abs().max()) == 0.0 and torch.equal(i1.cpu(), torch.arange(n, dtype=torch.int32).expand(B, n))
+        return
+    d1, d2, i1, i2 = ops.chamfer_forward(a.cuda(), b.cuda())
+    r1, r2, j1, j2 = OO.chamfer_forward(a, b)
+    assert torch.equal(d1.cpu(), r1) and torch.equal(d2.cpu(), r2)
+    assert torch.equal(i1.cpu(), j1) and torch.equal(i2.cpu(), j2)
+    assert ops.calculate_cd(a.cuda(), b.cuda()) == pytest.approx(OO.calculate_cd(a, b), rel=1e-6)
+
+
+def test_large_cloud_fps_global_path(mods):
+    """N > 16384 takes the global-memory FPS kernel (object-level seed/merge FPS); same selection rule."""
+    OO, ops, P = mods
+    coords = cloud(1, 20000, seed=5)
+    idx = P.furthest_point_sampling_forward(coords.cuda(), 300)
+    assert torch.equal(idx.cpu(), OO.furthest_point_sampling_forward(coords, 300))
+
+
+@pytest.mark.parametrize("tag", ["a", "tie"])
+def test_kernels_match_reference_kernels(mods, ref_ops, tag):
+    """Against outputs of the reference's OWN compiled CUDA kernels (tests/golden/ref_ops.npz)."""
+    OO, ops, P = mods
+    g = lambda k: torch.from_numpy(ref_ops[f"{tag}_{k}"]).cuda()
+    coords, feats = g("coords"), g("feats")
+    idx = P.furthest_point_sampling_forward(coords, 512)
+    assert torch.equal(idx, g("fps_idx"))
+    centers = P.gather_features_forward(coords, idx)
+    nidx = P.ball_query(centers, coords, 0.1, 32)
+    assert torch.equal(nidx, g("ball_idx"))
+    assert torch.equal(P.grouping_forward(feats, nidx), g("grouped"))
+    out, iidx, iw = P.three_nearest_neighbors_interpolate_forward(coords, centers, g("cfeat"))
+    assert torch.equal(iidx, g("interp_idx")) and torch.equal(iw, g("interp_w")) and torch.equal(out, g("interp"))
+    vo, vind, vcnt = P.avg_voxelize_forward(feats, g("vox"), 16)
+    assert torch.equal(vind, g("vox_ind")) and torch.equal(vcnt, g("vox_cnt"))
+    spread = (g("vox_out") - g("vox_out2")).abs().max().item()
+    assert (vo - g("vox_out")).abs().max().item() <= max(2e-6, 4 * spread)
+    dv = P.trilinear_devoxelize_forward(16, False, g("norm_coords"), g("grid"))[0]
+    assert torch.equal(dv, g("devox"))
+    d1, i1 = ops.nm_distance(coords.transpose(1, 2).contiguous(), (coords[:, :, :1024] + 0.01).transpose(1, 2).contiguous())
+    assert torch.equal(d1, g("cd_d1")) and torch.equal(i1, g("cd_i1"))
