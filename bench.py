@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- denoised patches/sec of the P2P-Bridge hot path (BASELINE.json metric) on N B200s of one node.
+
+A "step" = one ``P2PB.sample`` call (T=30 bridge steps of the PVDS PVCNN U-Net) over one batch of 64 synthetic
+2048-point patches per GPU (BASELINE.json configs[1]); weights are seeded random-init in the reference's checkpoint
+layout (no trained weights exist offline).  Patches shard data-parallel over ranks with no data-path collective
+(weak scaling: 64 patches per GPU); timing is CUDA events on the launching stream, max over ranks.
+
+  value  patches/s with the batch already resident in HBM
+  e2e    same metric through the public API with HOST buffers (pinned H2D of the batch + D2H of x_pred per step)
+  roofline      dominant kernel (the implicit-GEMM voxel convolution) timed live with CUDA events after the run
+  cpu_baseline  the CPU restatement (oracle/, checker only) timed on the host cores on a bounded sample (rank 0, N=1)
+
+``--impl reference`` times the reference's CPU path for the same metric/config: the reference's ops are CUDA-only, so
+its CPU implementation is the oracle port (oracle/model.py + oracle/p2pb_oracle.c, pinned against the reference's own
+code and kernels), run with all host threads on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoised patches/sec (PVDS, N=2048, T=30)"
+UNIT = "patches/s"
+WORKLOAD = "PVDS_PUNet N=2048 T=30 batch=64/GPU (BASELINE configs[1])"
+B_PER_GPU, NPTS, TSTEPS = 64, 2048, 30
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--backend", default=os.environ.get("P2PB_BACKEND", "engine"), choices=["engine", "eager"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patches per GPU (default = the named config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def load_cfg_dict():
+    import yaml
+
+    return yaml.safe_load(open(os.path.join(ROOT, "p2pb_b200", "configs", "PVDS_PUNet.yaml")))
+
+
+def synth_patches(B, N, seed):
+    """64 kNN-like surface patches: noisy unit-sphere caps, per-patch centred, one global max-norm scale
+    (denoise_object.py:97-100).  Synthetic (no PU-Net data offline)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    d = torch.randn(B, 3, 1, generator=g)
+    d = d / d.norm(dim=1, keepdim=True)
+    x = d + 0.35 * torch.randn(B, 3, N, generator=g)
+    x = x / x.norm(dim=1, keepdim=True) + 0.02 * torch.randn(B, 3, N, generator=g)
+    x = x - x.mean(dim=2, keepdim=True)
+    return (x / x.norm(dim=1).max()).contiguous()
+
+
+def cpu_port_rate(cfg, seconds_budget=20.0, threads=None):
+    """patches/s of the CPU restatement on a bounded sample: 1 patch x n_eval network evaluations (of T=30)."""
+    import torch
+
+    from oracle import model as OM
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = OM.make_state_dict(cfg, seed=0)
+    x = synth_patches(1, NPTS, seed=123)
+    t0 = time.perf_counter()
+    OM.sample(sd, cfg, x, None, steps=1, log_count=1)      # one evaluation to size the sample (and warm caches)
+    t_eval = time.perf_counter() - t0
+    n_eval = int(max(1, min(TSTEPS, seconds_budget // max(t_eval, 1e-3))))
+    t0 = time.perf_counter()
+    OM.sample(sd, cfg, x, None, steps=n_eval, log_count=1)
+    dt = time.perf_counter() - t0
+    rate = 1.0 / (dt * TSTEPS / n_eval)
+    return rate, threads, f"1 patch N={NPTS}, {n_eval} of T={TSTEPS} network evaluations timed ({dt:.1f} s), scaled to T={TSTEPS}"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: CPU implementation of the path on the host cores (oracle port; see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = load_cfg_dict()
+    import torch
+
+    from oracle import model as OM
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = OM.make_state_dict(cfg, seed=0)
+    x = synth_patches(1, NPTS, seed=123)
+    t0 = time.perf_counter()
+    OM.sample(sd, cfg, x, None, steps=1, log_count=1)
+    t_eval = time.perf_counter() - t0
+    total_steps = args.steps + args.warmup
+    n_eval = int(max(1, min(TSTEPS, (180.0 / max(total_steps, 1)) // max(t_eval, 1e-3))))
+    for _ in range(args.warmup):
+        OM.sample(sd, cfg, x, None, steps=n_eval, log_count=1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        OM.sample(sd, cfg, x, None, steps=n_eval, log_count=1)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    rate = 1.0 / (dt * TSTEPS / n_eval)
+    sample = f"per step: 1 patch N={NPTS}, {n_eval} of T={TSTEPS} network evaluations, scaled to T={TSTEPS}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from p2pb_b200 import _lib
+    from p2pb_b200.config import Config
+    from p2pb_b200.model_loader import seeded_state_dict
+    from p2pb_b200.p2pb import P2PB
+    from p2pb_b200.unet_pvc import PVCNN2Unet
+
+    cfg_dict = load_cfg_dict()
+    cfg = Config.wrap(cfg_dict)
+    cfg.gpu = str(dev)
+    cfg.model.ema = False
+    cfg.backend = args.backend
+    net = PVCNN2Unet(cfg)
+    net.load_state_dict(seeded_state_dict(net, seed=0), strict=True)
+    model = P2PB(cfg, net.to(dev)).eval()
+
+    B = args.batch
+    host_x = synth_patches(B, NPTS, seed=1000 + rank).pin_memory()          # each rank: its own shard of patches
+    host_out = torch.empty((B, 3, NPTS), dtype=torch.float32).pin_memory()
+    x_dev = host_x.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        return model.sample(x_start=x_dev, steps=TSTEPS, log_count=1, verbose=False, use_ema=False)["x_pred"]
+
+    def step_e2e():
+        xd = host_x.to(dev, non_blocking=True)
+        out = model.sample(x_start=xd, steps=TSTEPS, log_count=1, verbose=False, use_ema=False)["x_pred"]
+        host_out.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            flush.zero_()            # L2 flush between timed iterations (working set is >> L2 anyway)
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, _lib.launch_count() - l0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_step, launches = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    eng = getattr(model, "last_engine", None)
+    if eng is not None:
+        launches = eng.kernels_per_sample * args.steps
+    total_patches = B * world
+    value = total_patches / (ms_step / 1e3)
+    e2e = total_patches / (ms_e2e / 1e3)
+
+    roofline = None
+    if rank == 0 and not args.no_roofline:
+        try:
+            from p2pb_b200 import roofline as RL
+
+            roofline = RL.dominant_kernel_roofline(model, B, dev)
+        except Exception as ex:  # keep the bench line even if the micro-timing fails
+            roofline = {"error": repr(ex)}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, cores, sample = cpu_port_rate(cfg_dict)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": getattr(eng, "dtype_name", "tf32") if eng is not None else "tf32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "backend": args.backend, "patches_per_gpu": B, "npoints": NPTS, "T": TSTEPS,
+                       "weights": "seeded random-init, reference checkpoint layout",
+                       "l2": "256 MiB L2 flush between timed iterations; per-step working set >> 126 MB L2",
+                       "parallelism": f"dp{world} over patches, no data-path collective"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": host_x.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

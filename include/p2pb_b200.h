@@ -20,6 +20,8 @@ extern "C" {
 const char* p2pb_last_error(void);
 int p2pb_abi_version(void);
 int p2pb_device_sm_count(void);
+/* kernels launched (or captured into a CUDA graph) through this library since load */
+unsigned long long p2pb_launch_count(void);
 
 /* ---- point ops, reference layout (channel-first [B,C,N]) ------------------------------------------------- */
 

@@ -39,3 +39,10 @@ def check(rc: int, what: str) -> None:
 def call(name: str, *args) -> None:
     fn = getattr(lib(), name)
     check(fn(*args), name)
+
+
+def launch_count() -> int:
+    """Kernels launched (or captured into a graph) through the library so far."""
+    fn = lib().p2pb_launch_count
+    fn.restype = ctypes.c_ulonglong
+    return int(fn())

@@ -19,6 +19,10 @@ P2PB_API const char* p2pb_last_error() { return g_last_error; }
 
 P2PB_API int p2pb_abi_version() { return 1; }
 
+unsigned long long g_p2pb_launches = 0;
+// number of kernels this library has launched (or recorded into a CUDA graph under stream capture) so far
+P2PB_API unsigned long long p2pb_launch_count() { return g_p2pb_launches; }
+
 int p2pb_num_sms()
 {
     static int n = 0;

@@ -33,8 +33,10 @@ void p2pb_set_error(const char* fmt, ...);
     } while (0)
 
 // launch check: never exit() (the reference does, cuda_utils.cuh:30-40); report through the return code
+extern unsigned long long g_p2pb_launches;  // kernels launched through this library (p2pb_launch_count)
 #define P2PB_LAUNCH_OK()                                                                      \
     do {                                                                                      \
+        ++g_p2pb_launches;                                                                    \
         cudaError_t _e = cudaGetLastError();                                                  \
         if (_e != cudaSuccess) {                                                              \
             p2pb_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -73,3 +73,29 @@ def load_diffusion(cfg) -> tuple:
 def save_checkpoint(path: str, model: P2PB, step: int = 0) -> None:
     """Write a checkpoint in the reference's format (train.py:169-174); used to make synthetic seeded checkpoints."""
     torch.save({"step": step, "model_state": model.state_dict(), "optimizer_state": {}}, path)
+
+
+def seeded_state_dict(net: torch.nn.Module, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic weights for ``net`` (no trained checkpoints exist offline): one independent RNG stream per
+    state-dict key, so values do not depend on construction order.  Conv/linear weights ~ U(+-1/sqrt(fan_in))
+    (AdaGN ``emd`` at half scale), norm gains 1+0.1 N(0,1), biases 0.05 N(0,1) with the AdaGN (1, 0) centre."""
+    import math
+    import zlib
+
+    out = {}
+    for key, ref in net.state_dict().items():
+        shp = tuple(ref.shape)
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+        if key.endswith(".weight") and len(shp) >= 2:
+            bound = 1.0 / math.sqrt(float(torch.tensor(shp[1:]).prod()))
+            if ".emd." in key:
+                bound *= 0.5
+            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        elif key.endswith(".weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            t = 0.05 * torch.randn(shp, generator=g)
+            if key.endswith(".emd.bias"):
+                t[: shp[0] // 2] += 1.0
+        out[key] = t.float()
+    return out

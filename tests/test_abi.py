@@ -63,3 +63,18 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|from\s+\.\.?oracle|p2pb_oracle\.so", txt, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_seeded_weights_equal_oracle_weights():
+    """bench/smoke weights come from the product's own generator; it must equal the oracle's (same per-key streams)."""
+    from oracle import model as OM
+    from p2pb_b200.config import load_yaml
+    from p2pb_b200.model_loader import seeded_state_dict
+    from p2pb_b200.unet_pvc import PVCNN2Unet
+
+    cfg = load_yaml(os.path.join(ROOT, "p2pb_b200", "configs", "PVDS_PUNet.yaml"))
+    a = seeded_state_dict(PVCNN2Unet(cfg), seed=0)
+    b = OM.make_state_dict(cfg.to_dict(), seed=0)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
