@@ -1,0 +1,78 @@
+"""Torch-tensor front end of the tcgen05 GEMM / implicit-GEMM conv kernels (``csrc/gemm_tf32.cu``).
+
+Channels-last fp32 activations ("rows": ``[M, C]`` with C padded to a multiple of 32); weights pre-packed K-major
+``[N, K]``.  Kernels run on torch's current stream; CUDA only."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import P2PBError, call
+
+_vp = ctypes.c_void_p
+
+
+def _p(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _s():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def num_m_tiles(M: int) -> int:
+    return (M + 127) // 128
+
+
+def gemm_rows(segs: Sequence[torch.Tensor], W: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              bias2: Optional[torch.Tensor] = None, rows_per_sample: int = 0, out: Optional[torch.Tensor] = None,
+              stats: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """D[M,N] = cat(segs, dim=1)[M,K] @ W[N,K]^T + bias + bias2[m // rows_per_sample].
+
+    ``segs``: 1-3 fp32 2-D tensors with unit inner stride (column slices of wider buffers are fine); ``ks`` optionally
+    restricts the number of leading columns used from each segment."""
+    assert 1 <= len(segs) <= 3
+    M = segs[0].shape[0]
+    N = W.shape[0]
+    a = []
+    for i in range(3):
+        if i < len(segs):
+            t = segs[i]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == M):
+                raise P2PBError(f"gemm_rows: segment {i} must be a CUDA fp32 [M,K] tensor with unit inner stride")
+            k = t.shape[1] if ks is None else ks[i]
+            a += [_p(t), int(k), int(t.stride(0))]
+        else:
+            a += [_vp(0), 0, 0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=W.device)
+    assert out.stride(1) == 1 and W.is_contiguous()
+    with torch.cuda.device(W.device):
+        call("p2pb_gemm_rows", *a, _p(W), _p(bias), _p(bias2), int(rows_per_sample), _p(out), int(out.stride(0)),
+             _p(stats), int(M), int(N), _s())
+    return out
+
+
+def conv3d_cl(grid: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], B: int, r: int, cin: int, cout: int,
+              out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3x3 / stride 1 / pad 1 conv on a channels-last grid [B, r, r, r, cin] -> rows [B*r^3, cout]."""
+    if out is None:
+        out = torch.empty((B * r ** 3, cout), dtype=torch.float32, device=grid.device)
+    assert grid.is_contiguous() and W.is_contiguous() and out.stride(1) == 1
+    with torch.cuda.device(grid.device):
+        call("p2pb_conv3d_cl", _p(grid), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
+             int(cout), _s())
+    return out
+
+
+def pack_conv3d_weight(w: torch.Tensor, cin_pad: int, perm: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """[Cout, Cin, 3, 3, 3] (reference layout) -> [Cout, 27*cin_pad], k = ((kx*3+ky)*3+kz)*cin_pad + c.
+    ``perm[c_new] = c_old`` optionally reorders input channels (the engine stores features before coordinates)."""
+    cout, cin = w.shape[:2]
+    if perm is not None:
+        w = w[:, list(perm)]
+    p = torch.zeros((cout, 27, cin_pad), dtype=torch.float32, device=w.device)
+    p[:, :, :cin] = w.reshape(cout, cin, 27).permute(0, 2, 1)
+    return p.reshape(cout, 27 * cin_pad).contiguous()
