@@ -127,12 +127,15 @@ def make_input(kind, B, N, seed):
 
 
 CASES = [
-    # name, config, overrides, input kind, B, N, T, x_cond channels
-    ("pvds_cfg1", "PVDS_PUNet", {}, "test_xyz", 1, 1024, 5, 0),
-    ("pvds_b2", "PVDS_PUNet", {}, "synth", 2, 2048, 2, 0),
-    ("pvdl_xyz", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 0}, "synth", 1, 512, 2, 0),
-    ("pvdl_rgb", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 3}, "synth", 1, 512, 1, 3),
-    ("pvdl_dino", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 387}, "synth", 1, 512, 1, 387),
+    # name, config, overrides, input kind, B, N, T, x_cond channels, head_scale
+    ("pvds_cfg1", "PVDS_PUNet", {}, "test_xyz", 1, 1024, 5, 0, 1.0),
+    ("pvds_b2", "PVDS_PUNet", {}, "synth", 2, 2048, 2, 0, 1.0),
+    ("pvdl_xyz", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 0}, "synth", 1, 512, 2, 0, 1.0),
+    ("pvdl_rgb", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 3}, "synth", 1, 512, 1, 3, 1.0),
+    ("pvdl_dino", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 387}, "synth", 1, 512, 1, 387, 1.0),
+    # damped noise head: well-conditioned free-running loops (see oracle/model.py make_state_dict)
+    ("pvds_cfg1_damped", "PVDS_PUNet", {}, "test_xyz", 1, 1024, 5, 0, 0.02),
+    ("pvds_t30_damped", "PVDS_PUNet", {}, "synth", 2, 2048, 30, 0, 0.02),
 ]
 
 
@@ -141,7 +144,7 @@ def main():
     PVCNN2Unet, P2PB = import_reference()
     torch.set_grad_enabled(False)
     report = []
-    for name, cfgname, over, kind, B, N, T, F in CASES:
+    for name, cfgname, over, kind, B, N, T, F, hs in CASES:
         cfg = load_cfg(cfgname, **over)
         acfg = AttrDict.wrap(copy.deepcopy(cfg))
         acfg.model.ema = False
@@ -150,7 +153,7 @@ def main():
         ora_shapes = OM.param_shapes(cfg)
         assert ref_shapes == ora_shapes, (
             name, set(ref_shapes) ^ set(ora_shapes), [k for k in ref_shapes if ora_shapes.get(k) != ref_shapes[k]][:5])
-        sd = OM.make_state_dict(cfg, seed=0)
+        sd = OM.make_state_dict(cfg, seed=0, head_scale=hs)
         net.load_state_dict(sd, strict=True)
         model = P2PB(acfg, net)
         x = make_input(kind, B, N, seed=1)
@@ -183,7 +186,7 @@ def main():
             x_start=x.numpy(), x_cond=(xc.numpy().astype(np.float16) if xc is not None else np.zeros(0)),
             eps=eps_ref.numpy(), x_pred=out_ref["x_pred"].numpy(), x_chain=out_ref["x_chain"].numpy(),
             noise_level=nl.numpy(), T=T, cfg_name=cfgname, overrides=yaml.safe_dump(over),
-            n_params=len(ref_shapes))
+            n_params=len(ref_shapes), head_scale=hs)
     # schedule fixtures for both beta_end settings (p2pb.py:93-130) and the step grids (p2pb.py:16-40)
     for cfgname in ("PVDS_PUNet", "PVDL_SNPP"):
         cfg = load_cfg(cfgname)

@@ -1,0 +1,623 @@
+// engine_kernels.cu -- fused streaming kernels of the channels-last engine (everything of the PVCNN U-Net evaluation
+// that is not a tensor-core contraction).  They replace the ~600 un-fused ATen launches per network evaluation of the
+// reference (GroupNorm, AdaGN mul/add, Swish, SE, torch.cat, expand, max, zeros) with a handful of
+// HBM-bound passes:  rows are channels-last fp32 [M, ld] (ld multiple of 4), one thread per float4, coalesced.
+//
+//   voxelize_cl      CSR gather-mean of point rows (+ broadcast time-embedding channels) -> dense grid rows
+//   gn_coef          (sum, sum^2) partials of a GEMM/conv epilogue -> per-(sample, channel) affine of GroupNorm/AdaGN
+//   affine_act       y = act(x*A[b,c] + B[b,c])      (+ max over K consecutive rows, + max over all rows of a sample)
+//   devox_cl         trilinear gather of the raw conv output with AdaGN*SE folded in + point branch (AdaGN+Swish) add
+//   group_rows       ball-query neighbourhood gather: [features[idx], xyz[idx]-centre]
+//   interp_rows      3-NN inverse-distance interpolation gather
+//   linear_small     per-sample small Linear (AdaGN/temb/SE/attention-sized matvecs), warp per output
+//   attention_small  bottleneck LinearAttention core (softmax over tokens, 32x32 context per head)
+//   bridge_update    pred_x0 = xt - std*eps ; xt <- mu_x0*pred_x0 + mu_xn*xt           (p2pb.py:155-165,190-213)
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// coords [B,3,N] -> rows [B*N, ld] columns col0..col0+2 (other columns untouched)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void coords_to_rows_kernel(const float* __restrict__ coords, float* __restrict__ rows, int N, int ld, int col0,
+                                      long long total)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / N;
+    const int n = (int)(i - b * N);
+    const float* c = coords + b * 3 * N;
+    float* o = rows + i * ld + col0;
+    o[0] = c[n];
+    o[1] = c[n + N];
+    o[2] = c[n + 2 * N];
+}
+
+P2PB_API int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N, int ld, int col0, void* stream)
+{
+    const long long total = (long long)B * N;
+    if (total == 0) return P2PB_OK;
+    coords_to_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(coords, rows, N, ld, col0, total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// voxelize_cl: out[b, v, c] for every voxel v and channel c < Cp (each element written exactly once)
+//   c <  Cf        : sum over the voxel's points (ascending index) of feat[b, p, c] * (1/cnt)    (vox_gpu.cu:70-75)
+//   Cf <= c < Cf+E : the same scatter-mean applied to the broadcast time embedding temb[b, c-Cf]
+//   else           : 0 (channel padding for the 32-wide K chunks of the conv)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxelize_cl_kernel(const float* __restrict__ feat, int ldf, int Cf,
+                                                          const float* __restrict__ temb, int E,
+                                                          const int* __restrict__ order, const int* __restrict__ start,
+                                                          const int* __restrict__ cnt, float* __restrict__ out, int Cp,
+                                                          int N, int r3, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int C4 = Cp >> 2;
+    const int c0 = (int)(e % C4) * 4;
+    const long long vrow = e / C4;  // b*r3 + v
+    const int b = (int)(vrow / r3);
+    const int n = cnt[vrow];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n > 0) {
+        const float inv = (float)(1.0 / (double)(float)n);
+        const int* ord = order + (size_t)b * N + start[vrow];
+        float* a = reinterpret_cast<float*>(&acc);
+        if (c0 + 3 < Cf && (ldf & 3) == 0) {
+            for (int i = 0; i < n; ++i) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + ord[i]) * ldf + c0));
+                acc.x = __fadd_rn(acc.x, __fmul_rn(f.x, inv));
+                acc.y = __fadd_rn(acc.y, __fmul_rn(f.y, inv));
+                acc.z = __fadd_rn(acc.z, __fmul_rn(f.z, inv));
+                acc.w = __fadd_rn(acc.w, __fmul_rn(f.w, inv));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                if (c < Cf) {
+                    float s = 0.f;
+                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
+                    a[j] = s;
+                } else if (c < Cf + E) {
+                    const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
+                    float s = 0.f;
+                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
+                    a[j] = s;
+                }
+            }
+        }
+    }
+    reinterpret_cast<float4*>(out)[e] = acc;
+}
+
+P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
+                              const int* start, const int* cnt, float* out, int Cp, int B, int N, int r, void* stream)
+{
+    P2PB_CHECK_ARG(Cp % 4 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_cl: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
+    const int r3 = r * r * r;
+    const long long total4 = (long long)B * r3 * (Cp / 4);
+    if (total4 == 0) return P2PB_OK;
+    voxelize_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
+                                                                               Cp, N, r3, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gn_coef: GroupNorm (+ AdaGN) statistics -> per-(sample, channel) affine.
+//   stats  [B*tiles, C, 2]  per-tile column (sum, sum^2) written by the GEMM epilogue (tiles per sample = tiles)
+//   y = ((x - mean_g) * rstd_g * gamma_c + beta_c) * factor_bc + bias_bc     =  x * A[b,c] + Bc[b,c]
+//   emd (optional) [B, ld_emd]: factor at column emd_off + c, bias at emd_off + C + c      (modules.py:341-358)
+//   ymean (optional) [B, C]: mean over rows of y (= A*mean_c + Bc), the SE squeeze          (modules.py:378)
+// One CTA per (sample, group); fp64 accumulation of the partials (deterministic, no atomics anywhere).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gn_coef_kernel(const float* __restrict__ stats, int tiles, int C, int groups, float count,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ emd, int ld_emd, int emd_off, float eps,
+                                                      float* __restrict__ coefA, float* __restrict__ coefB,
+                                                      float* __restrict__ ymean)
+{
+    __shared__ double s_sum[128], s_sq[128];
+    __shared__ double s_cm[128];  // per-channel sums (group width <= 128)
+    const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+    const int cpg = C / groups;
+    const int t = threadIdx.x;
+    double gs = 0.0, gq = 0.0;
+    for (int c = t; c < cpg; c += blockDim.x) {
+        const int ch = g * cpg + c;
+        double s = 0.0, q = 0.0;
+        for (int tl = 0; tl < tiles; ++tl) {
+            const float* p = stats + (((size_t)b * tiles + tl) * C + ch) * 2;
+            s += (double)p[0];
+            q += (double)p[1];
+        }
+        s_cm[c] = s;
+        gs += s;
+        gq += q;
+    }
+    s_sum[t] = gs;
+    s_sq[t] = gq;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            s_sum[t] += s_sum[t + s];
+            s_sq[t] += s_sq[t + s];
+        }
+        __syncthreads();
+    }
+    const double n = (double)count * cpg;
+    const double mean = s_sum[0] / n;
+    double var = s_sq[0] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float meanf = (float)mean;
+    for (int c = t; c < cpg; c += blockDim.x) {
+        const int ch = g * cpg + c;
+        float a = rstd * gamma[ch];
+        float bb = beta[ch] - meanf * a;
+        if (emd != nullptr) {
+            const float f = emd[(size_t)b * ld_emd + emd_off + ch];
+            const float eb = emd[(size_t)b * ld_emd + emd_off + C + ch];
+            a *= f;
+            bb = bb * f + eb;
+        }
+        coefA[(size_t)b * C + ch] = a;
+        coefB[(size_t)b * C + ch] = bb;
+        if (ymean != nullptr) ymean[(size_t)b * C + ch] = a * (float)(s_cm[c] / (double)count) + bb;
+    }
+}
+
+P2PB_API int p2pb_gn_coef(const float* stats, int tiles, int B, int C, int groups, int rows_per_sample, const float* gamma,
+                          const float* beta, const float* emd, int ld_emd, int emd_off, float eps, float* coefA, float* coefB,
+                          float* ymean, void* stream)
+{
+    P2PB_CHECK_ARG(C % groups == 0 && C / groups <= 128, "gn_coef: C=%d groups=%d (group width must be <= 128)", C, groups);
+    if (B == 0) return P2PB_OK;
+    gn_coef_kernel<<<B * groups, 128, 0, (cudaStream_t)stream>>>(stats, tiles, C, groups, (float)rows_per_sample, gamma, beta, emd,
+                                                                ld_emd, emd_off, eps, coefA, coefB, ymean);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// column (sum, sum^2) of rows for samples whose row count is not a multiple of the 128-row GEMM tile
+// (deep U-Net levels: 8..32 points per patch): out [B, C, 2] == the epilogue format with tiles = 1
+__global__ void col_stats_kernel(const float* __restrict__ x, int ld, int rows, int C, float* __restrict__ out)
+{
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float* p = x + (size_t)b * rows * ld + c;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < rows; ++i) {
+        const float v = p[(size_t)i * ld];
+        s += v;
+        q += v * v;
+    }
+    out[((size_t)b * C + c) * 2 + 0] = s;
+    out[((size_t)b * C + c) * 2 + 1] = q;
+}
+
+P2PB_API int p2pb_col_stats(const float* x, int ld, int B, int rows, int C, float* out, void* stream)
+{
+    if (B == 0) return P2PB_OK;
+    col_stats_kernel<<<dim3(p2pb_cdiv(C, 128), B), 128, 0, (cudaStream_t)stream>>>(x, ld, rows, C, out);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// affine_act: out[m, c] = act(x[m, c] * A[b, c] + Bc[b, c]),  b = m / rows_per_sample,  act: 0 none, 1 swish
+//   pool == 1 : out rows [M, ldo]
+//   pool  > 1 : max over `pool` consecutive rows -> out rows [M/pool, ldo]            (neighbour max, pvcnn.py:414)
+//   gmax != 0 : additionally atomic-max over all rows of the sample -> gmax[b, c]      (global max-pool, pvcnn.py:923,930)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float(float* addr, float v)
+{
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+template <int ACT>
+__device__ __forceinline__ float4 affine4(float4 x, float4 a, float4 b)
+{
+    float4 y = make_float4(fmaf(x.x, a.x, b.x), fmaf(x.y, a.y, b.y), fmaf(x.z, a.z, b.z), fmaf(x.w, a.w, b.w));
+    if (ACT == 1) {
+        y.x = swishf(y.x); y.y = swishf(y.y); y.z = swishf(y.z); y.w = swishf(y.w);
+    }
+    return y;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
+                                                         const float* __restrict__ Bc, int rows_per_sample, int C,
+                                                         float* __restrict__ out, int ldo, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int C4 = C >> 2;
+    const int c = (int)(e % C4) * 4;
+    const long long m = e / C4;
+    const long long b = m / rows_per_sample;
+    const float4 xv = *reinterpret_cast<const float4*>(x + m * ldx + c);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(A + b * C + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c));
+    *reinterpret_cast<float4*>(out + m * ldo + c) = affine4<ACT>(xv, a, bb);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256) affine_act_pool_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
+                                                              const float* __restrict__ Bc, int rows_per_sample, int C,
+                                                              int pool, float* __restrict__ out, int ldo, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int C4 = C >> 2;
+    const int c = (int)(e % C4) * 4;
+    const long long mo = e / C4;  // pooled row
+    const long long m0 = mo * pool;
+    const long long b = m0 / rows_per_sample;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(A + b * C + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c));
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int i = 0; i < pool; ++i) {
+        const float4 y = affine4<ACT>(*reinterpret_cast<const float4*>(x + (m0 + i) * ldx + c), a, bb);
+        mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
+    }
+    *reinterpret_cast<float4*>(out + mo * ldo + c) = mx;
+}
+
+// global max over the rows of each sample: grid (row tiles, B); each thread owns 4 channels and walks `rows_per_cta` rows
+template <int ACT>
+__global__ void __launch_bounds__(256) affine_act_gmax_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
+                                                              const float* __restrict__ Bc, int rows_per_sample, int C,
+                                                              int rows_per_cta, float* __restrict__ out, int ldo,
+                                                              float* __restrict__ gmax)
+{
+    const int b = blockIdx.y;
+    const int C4 = C >> 2;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+        const int c = c4 * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c));
+        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int i = 0; i < rows_per_cta; ++i) {
+            const long long rr = r0 + i;
+            if (rr >= rows_per_sample) break;
+            const long long m = (long long)b * rows_per_sample + rr;
+            const float4 y = affine4<ACT>(*reinterpret_cast<const float4*>(x + m * ldx + c), a, bb);
+            if (out != nullptr) *reinterpret_cast<float4*>(out + m * ldo + c) = y;
+            mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
+        }
+        float* g = gmax + (size_t)b * C + c;
+        atomic_max_float(g + 0, mx.x); atomic_max_float(g + 1, mx.y); atomic_max_float(g + 2, mx.z); atomic_max_float(g + 3, mx.w);
+    }
+}
+
+__global__ void fill_kernel(float* p, float v, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const float* Bc, int rows_per_sample, int M, int C, int act,
+                             int pool, float* out, int ldo, float* gmax, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    P2PB_CHECK_ARG(C % 4 == 0 && ldx % 4 == 0 && (out == nullptr || ldo % 4 == 0), "affine_act: C/ld must be multiples of 4");
+    P2PB_CHECK_ARG(M % rows_per_sample == 0 && pool >= 1 && rows_per_sample % pool == 0, "affine_act: bad row partition");
+    if (M == 0) return P2PB_OK;
+    const int B = M / rows_per_sample;
+    if (gmax != nullptr) {
+        P2PB_CHECK_ARG(pool == 1, "affine_act: gmax and pool are exclusive");
+        fill_kernel<<<p2pb_cdiv((long long)B * C, 256), 256, 0, s>>>(gmax, -INFINITY, (long long)B * C);
+        P2PB_LAUNCH_OK();
+        int rows_per_cta = p2pb_cdiv(rows_per_sample, p2pb_cdiv(4 * p2pb_num_sms(), B));
+        if (rows_per_cta < 8) rows_per_cta = 8;
+        dim3 grid(p2pb_cdiv(rows_per_sample, rows_per_cta), B);
+        if (act) affine_act_gmax_kernel<1><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax);
+        else affine_act_gmax_kernel<0><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax);
+        P2PB_LAUNCH_OK();
+        return P2PB_OK;
+    }
+    P2PB_CHECK_ARG(out != nullptr, "affine_act: out required");
+    if (pool == 1) {
+        const long long total4 = (long long)M * (C / 4);
+        if (act) affine_act_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4);
+        else affine_act_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4);
+    } else {
+        const long long total4 = (long long)(M / pool) * (C / 4);
+        if (act) affine_act_pool_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4);
+        else affine_act_pool_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4);
+    }
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// devox_cl: out[b,n,c] = (sum_k w_k * raw[b, corner_k, c]) * (A[b,c]*se[b,c]) + (Bc[b,c]*se[b,c]) * sum_k w_k
+//                        + swish(praw[b,n,c] * pA[b,c] + pB[b,c])
+// i.e. trilinear devoxelisation (trilinear_devox_gpu.cu:21-109) of  SE(AdaGN(conv2 output))  without ever materialising
+// the normalised grid, plus the PVConv point branch (pvcnn.py:324-328).  raw grid rows [B*r^3, ldg].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) devox_cl_kernel(const float* __restrict__ ncoords, const float* __restrict__ raw, int ldg,
+                                                       const float* __restrict__ A, const float* __restrict__ Bc,
+                                                       const float* __restrict__ se, const float* __restrict__ praw, int ldp,
+                                                       const float* __restrict__ pA, const float* __restrict__ pB,
+                                                       float* __restrict__ out, int ldo, int C, int N, int r, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int C4 = C >> 2;
+    const int c = (int)(e % C4) * 4;
+    const long long m = e / C4;  // b*N + n
+    const int b = (int)(m / N);
+    const int n = (int)(m - (long long)b * N);
+    const float* co = ncoords + (size_t)b * 3 * N;
+    const float x = co[n], y = co[n + N], z = co[n + 2 * N];
+    const int r2 = r * r;
+    const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+    const float xd1 = x - xl, yd1 = y - yl, zd1 = z - zl;
+    const float xd0 = 1.0f - xd1, yd0 = 1.0f - yd1, zd0 = 1.0f - zd1;
+    const int base = (int)xl * r2 + (int)yl * r + (int)zl;
+    const int xh = (xd1 > 0) ? r2 : 0, yh = (yd1 > 0) ? r : 0, zh = (zd1 > 0) ? 1 : 0;
+    const float w[8] = {xd0 * yd0 * zd0, xd0 * yd0 * zd1, xd0 * yd1 * zd0, xd0 * yd1 * zd1,
+                        xd1 * yd0 * zd0, xd1 * yd0 * zd1, xd1 * yd1 * zd0, xd1 * yd1 * zd1};
+    const int off[8] = {0, zh, yh, yh + zh, xh, xh + zh, xh + yh, xh + yh + zh};
+    const float* g = raw + ((size_t)b * r2 * r + base) * ldg + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(g + (size_t)off[k] * ldg));
+        acc.x = fmaf(w[k], f.x, acc.x); acc.y = fmaf(w[k], f.y, acc.y);
+        acc.z = fmaf(w[k], f.z, acc.z); acc.w = fmaf(w[k], f.w, acc.w);
+        wsum += w[k];
+    }
+    float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c));
+    float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c));
+    if (se != nullptr) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(se + (size_t)b * C + c));
+        a.x *= s.x; a.y *= s.y; a.z *= s.z; a.w *= s.w;
+        bb.x *= s.x; bb.y *= s.y; bb.z *= s.z; bb.w *= s.w;
+    }
+    float4 o = make_float4(fmaf(acc.x, a.x, bb.x * wsum), fmaf(acc.y, a.y, bb.y * wsum), fmaf(acc.z, a.z, bb.z * wsum),
+                           fmaf(acc.w, a.w, bb.w * wsum));
+    if (praw != nullptr) {
+        const float4 p = *reinterpret_cast<const float4*>(praw + m * ldp + c);
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(pA + (size_t)b * C + c));
+        const float4 pb = __ldg(reinterpret_cast<const float4*>(pB + (size_t)b * C + c));
+        const float4 q = affine4<1>(p, pa, pb);
+        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+    }
+    *reinterpret_cast<float4*>(out + m * ldo + c) = o;
+}
+
+P2PB_API int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, const float* A, const float* Bc, const float* se,
+                           const float* praw, int ldp, const float* pA, const float* pB, float* out, int ldo, int B, int C, int N,
+                           int r, void* stream)
+{
+    P2PB_CHECK_ARG(C % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0 && (praw == nullptr || ldp % 4 == 0), "devox_cl: alignment");
+    const long long total4 = (long long)B * N * (C / 4);
+    if (total4 == 0) return P2PB_OK;
+    devox_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(ncoords, raw, ldg, A, Bc, se, praw, ldp, pA, pB, out,
+                                                                            ldo, C, N, r, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// group_rows: out[(b*M + j)*U + k, 0:Cf] = feat[b, idx[b,j,k], 0:Cf] ; out[.., Cf:Cf+3] = xyz[idx] - centre_j
+// (pvcnn_grouping_gpu.cu:18-39 twice + the centre subtraction + torch.cat of pvcnn.py:117-126).  Columns >= Cf+3 are
+// never written (zero from allocation).  One thread per (row, 4-channel chunk); chunk index Cf/4 carries the xyz part.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) group_rows_kernel(const float* __restrict__ feat, int ldf, int Cf,
+                                                         const float* __restrict__ coords, const float* __restrict__ centers,
+                                                         const int* __restrict__ idx, float* __restrict__ out, int ldo, int N,
+                                                         int M, int U, long long total)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int C4 = (Cf >> 2) + 1;
+    const int c4 = (int)(e % C4);
+    const long long row = e / C4;  // (b*M + j)*U + k
+    const long long bj = row / U;
+    const int b = (int)(bj / M);
+    const int j = (int)(bj - (long long)b * M);
+    const int src = idx[row];
+    if (c4 < (Cf >> 2)) {
+        *reinterpret_cast<float4*>(out + row * ldo + c4 * 4) =
+            __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + src) * ldf + c4 * 4));
+    } else {
+        const float* co = coords + (size_t)b * 3 * N;
+        const float* ce = centers + (size_t)b * 3 * M;
+        float* o = out + row * ldo + Cf;
+        o[0] = co[src] - ce[j];
+        o[1] = co[src + N] - ce[j + M];
+        o[2] = co[src + 2 * N] - ce[j + 2 * M];
+    }
+}
+
+P2PB_API int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* coords, const float* centers, const int* idx,
+                             float* out, int ldo, int B, int N, int M, int U, void* stream)
+{
+    P2PB_CHECK_ARG(Cf % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0 && ldo >= Cf + 3, "group_rows: alignment (Cf %% 4, ld %% 4)");
+    const long long total = (long long)B * M * U * (Cf / 4 + 1);
+    if (total == 0) return P2PB_OK;
+    group_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
+                                                                             U, total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// interp_rows: out[b*N + n, 0:C] = f[i2]*w2 + f[i1]*w1 + f[i3]*w3 (reference contraction order) from rows [B*M, ldf]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) interp_rows_kernel(const float* __restrict__ f, int ldf, const int* __restrict__ idx,
+                                                          const float* __restrict__ w, float* __restrict__ out, int ldo, int C,
+                                                          int N, int M, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int C4 = C >> 2;
+    const int c = (int)(e % C4) * 4;
+    const long long m = e / C4;
+    const int b = (int)(m / N);
+    const int n = (int)(m - (long long)b * N);
+    const int* ix = idx + (size_t)b * 3 * N;
+    const float* ww = w + (size_t)b * 3 * N;
+    const int i1 = ix[n], i2 = ix[n + N], i3 = ix[n + 2 * N];
+    const float w1 = ww[n], w2 = ww[n + N], w3 = ww[n + 2 * N];
+    const float* fb = f + (size_t)b * M * ldf + c;
+    const float4 f1 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)i1 * ldf));
+    const float4 f2 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)i2 * ldf));
+    const float4 f3 = __ldg(reinterpret_cast<const float4*>(fb + (size_t)i3 * ldf));
+    float4 o;
+    o.x = fmaf(f3.x, w3, fmaf(f1.x, w1, f2.x * w2));
+    o.y = fmaf(f3.y, w3, fmaf(f1.y, w1, f2.y * w2));
+    o.z = fmaf(f3.z, w3, fmaf(f1.z, w1, f2.z * w2));
+    o.w = fmaf(f3.w, w3, fmaf(f1.w, w1, f2.w * w2));
+    *reinterpret_cast<float4*>(out + m * ldo + c) = o;
+}
+
+P2PB_API int p2pb_interp_rows(const float* f, int ldf, const int* idx, const float* w, float* out, int ldo, int B, int C, int N,
+                              int M, void* stream)
+{
+    P2PB_CHECK_ARG(C % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0, "interp_rows: alignment");
+    const long long total4 = (long long)B * N * (C / 4);
+    if (total4 == 0) return P2PB_OK;
+    interp_rows_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(f, ldf, idx, w, out, ldo, C, N, M, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// linear_small: out[b, o] = act(sum_k in[b, k] * W[o, k] + bias[o]);  warp per (b, o);  act: 0 none, 1 swish, 2 relu,
+// 3 sigmoid, 4 leaky_relu(0.1).  For the per-sample vectors of the network (time-embedding MLP unet_pvc.py:52-56,
+// time-embedding bias folds, SE excitation modules.py:365-370, global-feature bias fold of Pnet2Stage).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W,
+                                                           int ldw, const float* __restrict__ bias, int K, int O, int act,
+                                                           float* __restrict__ out, int ldo, long long total)
+{
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= total) return;
+    const int o = (int)(wid % O);
+    const long long b = wid / O;
+    const float* x = in + b * ldi;
+    const float* wr = W + (size_t)o * ldw;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(x[k], __ldg(wr + k), s);
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (bias != nullptr) s += bias[o];
+        if (act == 1) s = swishf(s);
+        else if (act == 2) s = fmaxf(s, 0.f);
+        else if (act == 3) s = 1.0f / (1.0f + __expf(-s));
+        else if (act == 4) s = s > 0.f ? s : 0.1f * s;
+        out[b * ldo + o] = s;
+    }
+}
+
+P2PB_API int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw, const float* bias, int B, int K, int O, int act,
+                               float* out, int ldo, void* stream)
+{
+    const long long total = (long long)B * O;
+    if (total == 0) return P2PB_OK;
+    linear_small_kernel<<<p2pb_cdiv(total * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, W, ldw, bias, K, O, act, out, ldo,
+                                                                                    total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// attention_small: LinearAttention core (modules.py:186-192) on the bottleneck tokens.  qkv rows [B*N, 3*H*32] with
+// channel = qkv*H*32 + head*32 + d.  k <- softmax over the N tokens; ctx[d,e] = sum_n k[d,n] v[e,n];
+// out[e,n] = sum_d ctx[d,e] q[d,n]  -> out rows [B*N, H*32].  One CTA (32x32 threads) per (sample, head); N <= 64.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) attention_small_kernel(const float* __restrict__ qkv, int ldq, int H, int N,
+                                                               float* __restrict__ out, int ldo)
+{
+    __shared__ float sq[32][65], sk[32][65], sv[32][65], sctx[32][33];
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 32
+    const float* base = qkv + (size_t)b * N * ldq;
+    for (int n = ty; n < N; n += 32) {
+        sq[tx][n] = base[(size_t)n * ldq + 0 * H * 32 + h * 32 + tx];
+        sk[tx][n] = base[(size_t)n * ldq + 1 * H * 32 + h * 32 + tx];
+        sv[tx][n] = base[(size_t)n * ldq + 2 * H * 32 + h * 32 + tx];
+    }
+    __syncthreads();
+    if (ty == 0) {  // softmax over tokens for row d = tx
+        float mx = -INFINITY;
+        for (int n = 0; n < N; ++n) mx = fmaxf(mx, sk[tx][n]);
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float ev = expf(sk[tx][n] - mx);
+            sk[tx][n] = ev;
+            s += ev;
+        }
+        for (int n = 0; n < N; ++n) sk[tx][n] /= s;
+    }
+    __syncthreads();
+    {  // ctx[d = ty][e = tx]
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s = fmaf(sk[ty][n], sv[tx][n], s);
+        sctx[ty][tx] = s;
+    }
+    __syncthreads();
+    for (int n = ty; n < N; n += 32) {  // out[e = tx][n]
+        float s = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) s = fmaf(sctx[d][tx], sq[d][n], s);
+        out[((size_t)b * N + n) * ldo + h * 32 + tx] = s;
+    }
+}
+
+P2PB_API int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N, float* out, int ldo, void* stream)
+{
+    P2PB_CHECK_ARG(N > 0 && N <= 64, "attention_small: N=%d tokens (bottleneck only, <= 64)", N);
+    if (B == 0) return P2PB_OK;
+    attention_small_kernel<<<B * H, dim3(32, 32), 0, (cudaStream_t)stream>>>(qkv, ldq, H, N, out, ldo);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bridge_update (p2pb.py:155-165 + 190-213, ot_ode): eps rows [B*N, lde] (first 3 columns) and xt [B,3,N]
+//   pred_x0 = xt - std_n * eps ; (clip +-3) ; xt_next = mu_x0 * pred_x0 + mu_xn * xt      (same op order as the reference)
+// Scalars come from a device table coef[step_slot*3 + {0,1,2}] so that one captured graph serves every step.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bridge_update_kernel(const float* __restrict__ xt, const float* __restrict__ eps, int lde,
+                                     const float* __restrict__ coef, int clip, float* __restrict__ xt_next,
+                                     float* __restrict__ pred_x0, int N, long long total)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / N;
+    const int n = (int)(i - b * N);
+    const float std_n = coef[0], mu_x0 = coef[1], mu_xn = coef[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const size_t o = ((size_t)b * 3 + a) * N + n;
+        const float x = xt[o];
+        float p0 = __fsub_rn(x, __fmul_rn(std_n, eps[i * lde + a]));
+        if (clip) p0 = fminf(fmaxf(p0, -3.0f), 3.0f);
+        if (pred_x0 != nullptr) pred_x0[o] = p0;
+        xt_next[o] = __fadd_rn(__fmul_rn(mu_x0, p0), __fmul_rn(mu_xn, x));
+    }
+}
+
+P2PB_API int p2pb_bridge_update(const float* xt, const float* eps, int lde, const float* coef, int clip, float* xt_next,
+                                float* pred_x0, int B, int N, void* stream)
+{
+    const long long total = (long long)B * N;
+    if (total == 0) return P2PB_OK;
+    bridge_update_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, eps, lde, coef, clip, xt_next, pred_x0, N,
+                                                                                total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}

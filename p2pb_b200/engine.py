@@ -1,0 +1,609 @@
+"""Fused channels-last engine: one PVCNN U-Net evaluation + bridge update as ~250 hand-written kernels, all T
+sampling steps captured in one CUDA graph.
+
+Python here only *plans*: it packs the weights of a ``PVCNN2Unet`` once (K-major, channel-permuted, zero-padded to the
+32-wide K chunks of the tcgen05 GEMM), allocates every intermediate buffer once (static shapes per (config, B, N)), and
+enqueues kernels of ``libp2pb_b200.so`` through the C ABI on the current stream.  No torch op runs inside a network
+evaluation.  Replaces the eager hot loop ``models/p2pb.py:215-262`` x ``models/unet_pvc.py:171-269``.
+
+Layout: point features are rows ``[B*N, C]`` fp32 (C padded to a multiple of 32, feature channels FIRST, xyz after:
+the reference concatenates ``[coords, features]``; weights are column-permuted at pack time), voxel grids are rows
+``[B*r^3, C]``; coordinates stay ``[B,3,N]`` (what FPS / ball query / 3-NN read coalesced).
+
+Fusions relative to the reference:
+  * GroupNorm/AdaGN statistics come out of the GEMM/conv epilogue; normalise+AdaGN+Swish is one pass (or folded into the
+    consumer: SE + AdaGN of the second voxel conv are applied inside the devoxelisation gather);
+  * every ``torch.cat`` is a multi-segment GEMM operand; every ``cat[..., time_emb]`` in front of a 1x1 conv is a
+    per-sample bias (``W[:, temb cols] @ temb``); in front of a voxel conv the time embedding is scatter-averaged by
+    the voxelisation kernel itself;
+  * geometry (FPS chain, ball queries, 3-NN, voxel CSRs) is computed once per evaluation and shared by all blocks.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import dense, ops
+from ._lib import call, launch_count
+
+_vp = ctypes.c_void_p
+_f = ctypes.c_float
+
+
+def _p(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _s():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def pad32(c: int) -> int:
+    return (c + 31) // 32 * 32
+
+
+class _AdaGN:
+    """Packed norm parameters: gamma/beta + offset of this layer's (factor, bias) block in the batched emd GEMM."""
+
+    def __init__(self, gamma, beta, emd_off, groups):
+        self.gamma, self.beta, self.emd_off, self.groups = gamma, beta, emd_off, groups
+
+
+class Engine:
+    dtype_name = "tf32"
+
+    def __init__(self, p2pb, net, B: int, N: int, F: int):
+        self.p2pb, self.net = p2pb, net
+        self.B, self.N, self.F = B, N, F
+        self.dev = next(net.parameters()).device
+        self.E = net.embed_dim
+        self.ind = net.input_dim
+        assert self.ind == 3
+        self.extra = net.extra_feature_channels
+        assert F == self.extra, f"x_cond has {F} channels, model expects {self.extra}"
+        self._emd_w: List[torch.Tensor] = []
+        self._emd_b: List[torch.Tensor] = []
+        self._emd_total = 0
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._graphs: Dict[tuple, tuple] = {}
+        self.kernels_per_sample = 0
+        with torch.no_grad():
+            self._pack()
+
+    # ------------------------------------------------------------------------------------------------ utils
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.dev)
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def _w(self, t):
+        return t.detach().to(self.dev, torch.float32).contiguous()
+
+    def _norm(self, mod, groups=8) -> _AdaGN:
+        """AdaGN (norm + emd) or plain GroupNorm / MyGroupNorm."""
+        if hasattr(mod, "emd"):
+            off = self._emd_total
+            self._emd_w.append(self._w(mod.emd.weight))
+            self._emd_b.append(self._w(mod.emd.bias))
+            self._emd_total += mod.emd.weight.shape[0]
+            return _AdaGN(self._w(mod.norm.weight), self._w(mod.norm.bias), off, mod.norm.num_groups)
+        gn = mod.group_norm if hasattr(mod, "group_norm") else mod
+        return _AdaGN(self._w(gn.weight), self._w(gn.bias), -1, gn.num_groups)
+
+    def _pack_rows_w(self, w, col_map, k_pad) -> torch.Tensor:
+        """[O, I(,1..)] -> [O, k_pad] with source column blocks moved: col_map = [(src0, n, dst0), ...]."""
+        w = self._w(w).reshape(w.shape[0], w.shape[1])
+        out = self.zeros(w.shape[0], k_pad)
+        for src, n, dst in col_map:
+            out[:, dst:dst + n] = w[:, src:src + n]
+        return out.contiguous()
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _pack_pvconv(self, mod, c_in: int, temb_in: bool, coords_first: bool):
+        """c_in = valid channels of the incoming rows (features[, xyz]); temb_in: 64 time channels follow in the
+        reference's channel order.  coords_first: reference input order is [xyz, feats] (level 0) -> ours [feats, xyz]."""
+        E = self.E if temb_in else 0
+        conv1, n1, conv2, n2 = mod.voxel_layers[0], mod.voxel_layers[1], mod.voxel_layers[4], mod.voxel_layers[5]
+        se = mod.voxel_layers[6] if len(mod.voxel_layers) > 6 else None
+        cout = conv1.out_channels
+        cin_ref = conv1.in_channels
+        assert cin_ref == c_in + E
+        if coords_first:
+            perm = list(range(3, c_in)) + [0, 1, 2]
+        else:
+            perm = list(range(c_in))
+        perm_full = perm + list(range(c_in, c_in + E))
+        cp = pad32(c_in + E)
+        P = {"cout": cout, "cin": c_in, "E": E, "cp": cp, "r": int(mod.resolution)}
+        P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full)
+        P["b1"] = self._w(conv1.bias)
+        P["n1"] = self._norm(n1)
+        P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad32(cout))
+        P["b2"] = self._w(conv2.bias)
+        P["n2"] = self._norm(n2)
+        if se is not None:
+            P["se0"], P["se2"] = self._w(se.fc[0].weight), self._w(se.fc[2].weight)
+        pf = mod.point_features.layers
+        wp = self._w(pf[0].weight).reshape(cout, cin_ref)
+        kp = pad32(c_in)
+        P["wp"] = self.zeros(cout, kp)
+        P["wp"][:, :c_in] = wp[:, perm]
+        P["wp"] = P["wp"].contiguous()
+        P["bp"] = self._w(pf[0].bias)
+        P["wp_t"] = wp[:, c_in:c_in + E].contiguous() if E else None
+        P["np"] = self._norm(pf[1])
+        return P
+
+    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None):
+        """SharedMLP -> list of dicts; first layer's columns remapped by first_cols; optional temb fold block."""
+        out = []
+        i = 0
+        while i < len(layers):
+            conv, nm = layers[i], layers[i + 1]
+            o, c = conv.weight.shape[:2]
+            L = {"cout": o}
+            if i == 0:
+                L["w"] = self._pack_rows_w(conv.weight, first_cols, k_pad_first)
+                if temb_cols is not None:
+                    w = self._w(conv.weight).reshape(o, c)
+                    L["w_t"] = w[:, temb_cols[0]:temb_cols[0] + temb_cols[1]].contiguous()
+            else:
+                L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad32(c))
+            L["b"] = self._w(conv.bias)
+            L["n"] = self._norm(nm)
+            out.append(L)
+            i += 3
+        return out
+
+    def _pack(self):
+        net, E = self.net, self.E
+        self.fe = net.f_embed_dim
+        fe = self.fe
+        assert fe % 4 == 0
+        W = {}
+        # time embedding MLP
+        W["tw0"], W["tb0"] = self._w(net.embedf[0].weight), self._w(net.embedf[0].bias)
+        W["tw2"], W["tb2"] = self._w(net.embedf[2].weight), self._w(net.embedf[2].bias)
+        # feature embedding
+        if net.embed_feats is not None:
+            ef = net.embed_feats
+            cin = ef[0].weight.shape[1]
+            W["ef0"] = self._pack_rows_w(ef[0].weight, [(0, cin, 0)], pad32(cin))
+            W["ef0b"] = self._w(ef[0].bias)
+            W["efn"] = self._norm(ef[1])
+            W["ef3"] = self._pack_rows_w(ef[3].weight, [(0, fe, 0)], pad32(fe))
+            W["ef3b"] = self._w(ef[3].bias)
+        # global PointNet
+        self.cond_dim = net.cond_emb_dim
+        if net.global_pnet is not None:
+            gp = net.global_pnet
+            m = [gp.mlp1.shared_mlp_0.mlp, gp.mlp1.shared_mlp_1.mlp, gp.mlp2.shared_mlp_0.mlp, gp.mlp2.shared_mlp_1.mlp]
+            G = []
+            for j, seq in enumerate(m):
+                conv, gn = seq[0], seq[1]
+                o, c = conv.weight.shape[:2]
+                L = {"cout": o, "b": self._w(conv.bias), "n": self._norm(gn)}
+                if j == 2:  # input = cat[point feature (c/2), global max (c/2)]: second half becomes a per-sample bias
+                    h = c // 2
+                    L["w"] = self._pack_rows_w(conv.weight, [(0, h, 0)], pad32(h))
+                    L["w_g"] = self._w(conv.weight).reshape(o, c)[:, h:].contiguous()
+                else:
+                    L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad32(c))
+                G.append(L)
+            W["pnet"] = G
+        # SA levels
+        sa = []
+        c_feat = fe + 3
+        self.Ns = [self.N]
+        n_levels = len(net.sa_layers)
+        for i, blk in enumerate(net.sa_layers):
+            mods = list(blk) if isinstance(blk, torch.nn.Sequential) else [blk]
+            pvs, sam = mods[:-1], mods[-1]
+            L = {"pv": [], "skip_c": c_feat}
+            c_cur = c_feat
+            for k, pv in enumerate(pvs):
+                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=(i > 0 and k == 0), coords_first=(i == 0 and k == 0)))
+                c_cur = L["pv"][-1]["cout"]
+            temb_sa = (len(pvs) == 0 and i > 0)
+            # SA-module MLP: reference grouped input = [rel xyz (3), features (c_cur) (+ temb 64)]; ours [features, rel xyz]
+            if i == 0 and len(pvs) == 0:
+                raise NotImplementedError("level 0 without PVConv")
+            assert c_cur % 4 == 0
+            L["mlp"] = self._pack_mlp(sam.mlps[0].layers, [(3, c_cur, 0), (0, 3, c_cur)], pad32(c_cur + 3),
+                                      temb_cols=(3 + c_cur, E) if temb_sa else None)
+            L["centers"], L["radius"], L["K"] = sam.num_centers, float(sam.radius[0]), int(sam.num_neighbors[0])
+            L["c_grp"] = c_cur
+            sa.append(L)
+            c_feat = L["mlp"][-1]["cout"]
+            self.Ns.append(sam.num_centers)
+        W["sa"] = sa
+        # bottleneck attention
+        if net.global_att is not None:
+            ga = net.global_att
+            W["att_qkv"] = self._pack_rows_w(ga.to_qkv.weight, [(0, c_feat, 0)], pad32(c_feat))
+            hid = ga.to_out.weight.shape[1]
+            W["att_out"] = self._pack_rows_w(ga.to_out.weight, [(0, hid, 0)], pad32(hid))
+            W["att_outb"] = self._w(ga.to_out.bias)
+            W["heads"] = ga.heads
+        # FP levels
+        fp = []
+        c_low = c_feat
+        for j, blk in enumerate(net.fp_layers):
+            mods = list(blk) if isinstance(blk, torch.nn.Sequential) else [blk]
+            fpm, pvs = mods[0], mods[1:]
+            lvl = n_levels - 1 - j
+            c_skip = sa[lvl]["skip_c"]
+            kp_skip = pad32(c_skip)
+            # reference input = [interp(c_low + temb E), skip(c_skip)]; skip at level 0 is [xyz(3), feats(fe)] -> ours [feats, xyz]
+            if lvl == 0:
+                skip_cols = [(c_low + E + 3, c_skip - 3, c_low), (c_low + E, 3, c_low + c_skip - 3)]
+            else:
+                skip_cols = [(c_low + E, c_skip, c_low)]
+            assert c_low % 32 == 0
+            L = {"mlp": self._pack_mlp(fpm.mlp.layers, [(0, c_low, 0)] + skip_cols, c_low + kp_skip, temb_cols=(c_low, E)),
+                 "c_low": c_low, "kp_skip": kp_skip, "lvl": lvl, "pv": []}
+            c_cur = L["mlp"][-1]["cout"]
+            for pv in pvs:
+                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=False, coords_first=False))
+                c_cur = L["pv"][-1]["cout"]
+            fp.append(L)
+            c_low = c_cur
+        W["fp"] = fp
+        # classifier
+        cl = net.classifier
+        W["cls"] = self._pack_mlp(cl[0].layers, [(0, c_low, 0)], pad32(c_low))
+        om = cl[-1].weight.shape[1]
+        W["cls_out"] = self.zeros(16, pad32(om))
+        W["cls_out"][:3, :om] = self._w(cl[-1].weight).reshape(3, om)
+        W["cls_outb"] = self.zeros(16)
+        W["cls_outb"][:3] = self._w(cl[-1].bias)
+        # batched AdaGN emd weights
+        if self._emd_total:
+            W["emd_w"] = torch.cat(self._emd_w, 0).contiguous()
+            W["emd_b"] = torch.cat(self._emd_b, 0).contiguous()
+            pad = (-self._emd_total) % 128
+            if pad:
+                W["emd_w"] = torch.cat([W["emd_w"], self.zeros(pad, W["emd_w"].shape[1])], 0).contiguous()
+                W["emd_b"] = torch.cat([W["emd_b"], self.zeros(pad)], 0).contiguous()
+            self._emd_ld = W["emd_w"].shape[0]
+        self.W = W
+
+    # ------------------------------------------------------------------------------------------------ buffers
+    def buf(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
+        """Named, zero-initialised, allocated once (padding columns stay zero forever)."""
+        t = self._bufs.get(name)
+        if t is None:
+            t = self.zeros(*shape, dtype=dtype)
+            self._bufs[name] = t
+        assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+        return t
+
+    # ------------------------------------------------------------------------------------------------ primitives
+    def gemm(self, name, segs, ks, w, bias, n_out, rows_per_sample, bias2=None, want_stats=True, out=None):
+        """rows GEMM + (sum, sum^2) statistics in the format gn_coef expects -> (raw, stats, tiles)."""
+        M = segs[0].shape[0]
+        raw = out if out is not None else self.buf(name + ".raw", M, n_out)
+        stats, tiles = None, 0
+        fused = want_stats and rows_per_sample % 128 == 0
+        if want_stats:
+            tiles = rows_per_sample // 128 if fused else 1
+            stats = self.buf(name + ".stats", (M // rows_per_sample) * tiles, n_out, 2)
+        dense.gemm_rows(segs, w, bias, bias2, rows_per_sample if bias2 is not None else 0, out=raw,
+                        stats=stats if fused else None, ks=ks)
+        if want_stats and not fused:
+            call("p2pb_col_stats", _p(raw), int(raw.stride(0)), M // rows_per_sample, rows_per_sample, n_out, _p(stats), _s())
+        return raw, stats, tiles
+
+    def coef(self, name, stats, tiles, nrm: _AdaGN, C, rows_per_sample, want_mean=False):
+        B = self.B
+        A, Bc = self.buf(name + ".A", B, C), self.buf(name + ".B", B, C)
+        ym = self.buf(name + ".ym", B, C) if want_mean else None
+        emd = self.emd_all if nrm.emd_off >= 0 else None
+        call("p2pb_gn_coef", _p(stats), tiles, B, C, nrm.groups, rows_per_sample, _p(nrm.gamma), _p(nrm.beta), _p(emd),
+             self._emd_ld if emd is not None else 0, max(nrm.emd_off, 0), _f(1e-5), _p(A), _p(Bc), _p(ym), _s())
+        return A, Bc, ym
+
+    def act(self, x, A, Bc, rows_per_sample, C, out, act=1, pool=1, gmax=None):
+        call("p2pb_affine_act", _p(x), int(x.stride(0)), _p(A), _p(Bc), rows_per_sample, x.shape[0], C, act, pool,
+             _p(out), int(out.stride(0)) if out is not None else 0, _p(gmax), _s())
+
+    def linear(self, x, w, bias, act, out, K=None, O=None):
+        call("p2pb_linear_small", _p(x), int(x.stride(0)), _p(w), int(w.stride(0)), _p(bias), x.shape[0], K or w.shape[1],
+             O or w.shape[0], act, _p(out), int(out.stride(0)), _s())
+
+    def mlp_chain(self, name, layers, segs, ks, rows_per_sample, temb, final_pool=1, final_out=None):
+        """(GEMM -> GN/AdaGN coef -> Swish)* ; the last layer's activation optionally max-pools `final_pool` rows."""
+        B = self.B
+        x_segs, x_ks = segs, ks
+        for li, L in enumerate(layers):
+            nm = f"{name}.{li}"
+            bias2 = None
+            if li == 0 and "w_t" in L:
+                bias2 = self.buf(nm + ".tb", B, L["cout"])
+                self.linear(temb, L["w_t"], None, 0, bias2)
+            raw, stats, tiles = self.gemm(nm, x_segs, x_ks, L["w"], L["b"], L["cout"], rows_per_sample, bias2=bias2)
+            A, Bc, _ = self.coef(nm, stats, tiles, L["n"], L["cout"], rows_per_sample)
+            last = li == len(layers) - 1
+            if last and final_out is not None:
+                out = final_out
+            elif last and final_pool > 1:
+                out = self.buf(nm + ".pool", raw.shape[0] // final_pool, L["cout"])
+            else:
+                out = self.buf(nm + ".act", raw.shape[0], pad32(L["cout"]))
+            self.act(raw, A, Bc, rows_per_sample, L["cout"], out, act=1, pool=final_pool if last else 1)
+            x_segs, x_ks = [out], [pad32(L["cout"])] if not last else None
+        return out
+
+    def pvconv(self, name, P, feats, coords_lvl, prep, temb, n_pts):
+        """PVConv (pvcnn.py:306-334): voxel branch + point branch -> rows [B*n_pts, cout]."""
+        B, r, cout, cp = self.B, P["r"], P["cout"], P["cp"]
+        r3 = r ** 3
+        grid = self.buf(f"{name}.grid", B * r3, cp)
+        call("p2pb_voxelize_cl", _p(feats), int(feats.stride(0)), P["cin"], _p(temb if P["E"] else None), P["E"], _p(prep["order"]),
+             _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
+        raw1 = self.buf(f"{name}.raw1", B * r3, cout)
+        st1 = self.buf(f"{name}.st1", B * r3 // 128, cout, 2)
+        dense.conv3d_cl(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1)
+        A1, B1, _ = self.coef(f"{name}.n1", st1, r3 // 128, P["n1"], cout, r3)
+        act1 = self.buf(f"{name}.act1", B * r3, pad32(cout))
+        self.act(raw1, A1, B1, r3, cout, act1, act=1)
+        raw2 = self.buf(f"{name}.raw2", B * r3, cout)
+        st2 = self.buf(f"{name}.st2", B * r3 // 128, cout, 2)
+        dense.conv3d_cl(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
+        A2, B2, ym = self.coef(f"{name}.n2", st2, r3 // 128, P["n2"], cout, r3, want_mean="se0" in P)
+        se = None
+        if "se0" in P:
+            hid = self.buf(f"{name}.seh", B, P["se0"].shape[0])
+            self.linear(ym, P["se0"], None, 2, hid)
+            se = self.buf(f"{name}.se", B, cout)
+            self.linear(hid, P["se2"], None, 3, se)
+        # point branch
+        bias2 = None
+        if P["E"]:
+            bias2 = self.buf(f"{name}.ptb", B, cout)
+            self.linear(temb, P["wp_t"], None, 0, bias2)
+        kp = P["wp"].shape[1]
+        praw, pst, ptiles = self.gemm(f"{name}.pt", [feats], [kp], P["wp"], P["bp"], cout, n_pts, bias2=bias2)
+        pA, pB, _ = self.coef(f"{name}.np", pst, ptiles, P["np"], cout, n_pts)
+        out = self.buf(f"{name}.out", B * n_pts, cout)
+        call("p2pb_devox_cl", _p(prep["norm_coords"]), _p(raw2), cout, _p(A2), _p(B2), _p(se), _p(praw), int(praw.stride(0)),
+             _p(pA), _p(pB), _p(out), cout, B, cout, n_pts, r, _s())
+        return out
+
+    def voxel_prep(self, cache, lvl, coords, r):
+        key = (lvl, r)
+        if key not in cache:
+            B, _, n = coords.shape
+            nc = self.buf(f"prep{key}.nc", B, 3, n)
+            ind = self.buf(f"prep{key}.ind", B, n, dtype=torch.int32)
+            order = self.buf(f"prep{key}.order", B, n, dtype=torch.int32)
+            start = self.buf(f"prep{key}.start", B, r ** 3, dtype=torch.int32)
+            cnt = self.buf(f"prep{key}.cnt", B, r ** 3, dtype=torch.int32)
+            call("p2pb_voxel_prep", _p(coords), B, n, r, 1, _f(0.0), _p(nc), _p(ind), _p(order), _p(start), _p(cnt), _s())
+            cache[key] = {"norm_coords": nc, "order": order, "start": start, "cnt": cnt}
+        return cache[key]
+
+    # ------------------------------------------------------------------------------------------------ one evaluation
+    def prepare_cond(self, x_cond):
+        """Step-invariant part: embed_feats(x_cond) (unet_pvc.py:184-188) when conditioning features are given."""
+        if self.extra == 0:
+            return
+        B, N, W, fe = self.B, self.N, self.W, self.fe
+        kc = pad32(self.extra)
+        xc = self.buf("xcond.rows", B * N, kc)
+        xc[:, :self.extra] = x_cond.permute(0, 2, 1).reshape(B * N, self.extra)   # layout change of the INPUT, once per call
+        F0 = self.buf("F0", B * N, pad32(fe + 3))
+        if "ef0" in W:
+            raw, st, tl = self.gemm("ef0", [xc], [kc], W["ef0"], W["ef0b"], fe, N)
+            A, Bc, _ = self.coef("ef0", st, tl, W["efn"], fe, N)
+            h = self.buf("ef0.act", B * N, pad32(fe))
+            self.act(raw, A, Bc, N, fe, h, act=1)
+            dense.gemm_rows([h], W["ef3"], W["ef3b"], out=F0[:, :fe], ks=[pad32(fe)])
+        else:
+            F0[:, :fe] = xc[:, :fe]
+
+    def evaluate(self, xt, temb):
+        """One network evaluation: xt [B,3,N], temb [B,E] (after the embedf MLP) -> eps rows [B*N, 16] (cols 0..2)."""
+        B, N, W, fe, E = self.B, self.N, self.W, self.fe, self.E
+        Ns = self.Ns
+        n_levels = len(W["sa"])
+        # ---- geometry: FPS chain, ball queries, 3-NN, voxel CSRs (coordinates only)
+        coords = [xt]
+        for i in range(n_levels):
+            M = Ns[i + 1]
+            idx = self.buf(f"fps{i}.idx", B, M, dtype=torch.int32)
+            ctr = self.buf(f"fps{i}.ctr", B, 3, M)
+            call("p2pb_furthest_point_sampling", _p(coords[i]), B, Ns[i], M, _p(idx), _p(ctr), _vp(0), _s())
+            coords.append(ctr)
+        nidx = []
+        for i, L in enumerate(W["sa"]):
+            t = self.buf(f"bq{i}", B, Ns[i + 1], L["K"], dtype=torch.int32)
+            call("p2pb_ball_query", _p(coords[i + 1]), _p(coords[i]), B, Ns[i + 1], Ns[i], _f(L["radius"]), L["K"], _p(t), _s())
+            nidx.append(t)
+        nn3 = []
+        for j, L in enumerate(W["fp"]):
+            lvl = L["lvl"]
+            ix = self.buf(f"nn{j}.idx", B, 3, Ns[lvl], dtype=torch.int32)
+            ww = self.buf(f"nn{j}.w", B, 3, Ns[lvl])
+            call("p2pb_three_nn", _p(coords[lvl]), _p(coords[lvl + 1]), B, Ns[lvl], Ns[lvl + 1], _p(ix), _p(ww), _s())
+            nn3.append((ix, ww))
+        preps: Dict[tuple, dict] = {}
+        # ---- point rows of the raw coordinates
+        X0 = self.buf("X0", B * N, 32)
+        call("p2pb_coords_to_rows", _p(xt), _p(X0), B, N, 32, 0, _s())
+        F0 = self.buf("F0", B * N, pad32(fe + 3))
+        call("p2pb_coords_to_rows", _p(xt), _p(F0), B, N, int(F0.stride(0)), fe, _s())
+        if self.extra == 0:
+            if "ef0" in W:
+                raw, st, tl = self.gemm("ef0", [X0], [32], W["ef0"], W["ef0b"], fe, N)
+                A, Bc, _ = self.coef("ef0", st, tl, W["efn"], fe, N)
+                h = self.buf("ef0.act", B * N, pad32(fe))
+                self.act(raw, A, Bc, N, fe, h, act=1)
+                dense.gemm_rows([h], W["ef3"], W["ef3b"], out=F0[:, :fe], ks=[pad32(fe)])
+            else:
+                raise NotImplementedError("extra_feature_channels == 0 without embed_feats")
+        # ---- global PointNet -> cond [B, cond_dim] -> all AdaGN (factor, bias) vectors in one GEMM
+        if "pnet" in W:
+            G = W["pnet"]
+            x, kx = X0, 32
+            g_half = None
+            for j, L in enumerate(G):
+                nm = f"pnet{j}"
+                bias2 = None
+                if j == 2:
+                    bias2 = self.buf(nm + ".gb", B, L["cout"])
+                    self.linear(g_half, L["w_g"], None, 0, bias2)
+                raw, st, tl = self.gemm(nm, [x], [kx], L["w"], L["b"], L["cout"], N, bias2=bias2)
+                A, Bc, _ = self.coef(nm, st, tl, L["n"], L["cout"], N)
+                if j == 1:      # activation rows AND global max over points (pvcnn.py:923-926)
+                    out = self.buf(nm + ".act", B * N, pad32(L["cout"]))
+                    g_half = self.buf(nm + ".gmax", B, L["cout"])
+                    self.act(raw, A, Bc, N, L["cout"], out, act=1, gmax=g_half)
+                elif j == 3:    # only the global max is needed (pvcnn.py:930-931)
+                    out = None
+                    cond = self.buf("cond", B, L["cout"])
+                    self.act(raw, A, Bc, N, L["cout"], None, act=1, gmax=cond)
+                else:
+                    out = self.buf(nm + ".act", B * N, pad32(L["cout"]))
+                    self.act(raw, A, Bc, N, L["cout"], out, act=1)
+                x, kx = out, pad32(L["cout"])
+            self.emd_all = self.buf("emd_all", B, self._emd_ld)
+            dense.gemm_rows([cond], W["emd_w"], W["emd_b"], out=self.emd_all)
+        else:
+            self.emd_all = None
+        # ---- set abstraction
+        feats = F0
+        skips = []
+        for i, L in enumerate(W["sa"]):
+            skips.append(feats)
+            n_pts = Ns[i]
+            for k, P in enumerate(L["pv"]):
+                prep = self.voxel_prep(preps, i, coords[i], P["r"])
+                feats = self.pvconv(f"sa{i}.pv{k}", P, feats, coords[i], prep, temb, n_pts)
+            M, K, cg = Ns[i + 1], L["K"], L["c_grp"]
+            grp = self.buf(f"sa{i}.grp", B * M * K, pad32(cg + 3))
+            call("p2pb_group_rows", _p(feats), int(feats.stride(0)), cg, _p(coords[i]), _p(coords[i + 1]), _p(nidx[i]), _p(grp),
+                 int(grp.stride(0)), B, n_pts, M, K, _s())
+            feats = self.mlp_chain(f"sa{i}.mlp", L["mlp"], [grp], [pad32(cg + 3)], M * K, temb, final_pool=K)
+        # ---- bottleneck linear attention (modules.py:165-194; no residual)
+        nb = Ns[-1]
+        if "att_qkv" in W:
+            c = feats.shape[1]
+            qkv = self.buf("att.qkv", B * nb, W["att_qkv"].shape[0])
+            dense.gemm_rows([feats], W["att_qkv"], None, out=qkv, ks=[pad32(c)])
+            hid = W["att_out"].shape[1]
+            att = self.buf("att.ctx", B * nb, hid)
+            call("p2pb_attention_small", _p(qkv), int(qkv.stride(0)), B, W["heads"], nb, _p(att), hid, _s())
+            fo = self.buf("att.out", B * nb, c)
+            dense.gemm_rows([att], W["att_out"], W["att_outb"], out=fo, ks=[hid])
+            feats = fo
+        # ---- feature propagation
+        for j, L in enumerate(W["fp"]):
+            lvl = L["lvl"]
+            n_up, n_low, c_low = Ns[lvl], Ns[lvl + 1], L["c_low"]
+            ix, ww = nn3[j]
+            itp = self.buf(f"fp{j}.itp", B * n_up, c_low)
+            call("p2pb_interp_rows", _p(feats), int(feats.stride(0)), _p(ix), _p(ww), _p(itp), c_low, B, c_low, n_up, n_low, _s())
+            skip = skips[lvl]
+            feats = self.mlp_chain(f"fp{j}.mlp", L["mlp"], [itp, skip], [c_low, L["kp_skip"]], n_up, temb)
+            for k, P in enumerate(L["pv"]):
+                prep = self.voxel_prep(preps, lvl, coords[lvl], P["r"])
+                feats = self.pvconv(f"fp{j}.pv{k}", P, feats, coords[lvl], prep, temb, n_up)
+        # ---- classifier head (unet_pvc.py:147-154,263-267)
+        h = self.mlp_chain("cls", W["cls"], [feats], [pad32(feats.shape[1])], N, temb)
+        eps = self.buf("eps", B * N, 16)
+        dense.gemm_rows([h], W["cls_out"], W["cls_outb"], out=eps, ks=[W["cls_out"].shape[1]])
+        return eps
+
+    def time_embedding(self, noise_level: float, out):
+        """get_timestep_embedding + embedf (unet_pvc.py:156-169, 52-56) for a batch that shares one noise level."""
+        import numpy as np
+
+        half = self.E // 2
+        e = np.log(10000) / (half - 1)
+        freqs = torch.from_numpy(np.exp(np.arange(0, half) * -e)).float()
+        ang = torch.tensor(noise_level, dtype=torch.float32) * freqs
+        return torch.cat([torch.sin(ang), torch.cos(ang)]).to(self.dev)
+
+    # ------------------------------------------------------------------------------------------------ sampling loop
+    def _run_loop(self, pairs, log_set, clip, xs_buf, x0_buf):
+        """All T steps on the current stream (this is what gets captured)."""
+        B, N, E = self.B, self.N, self.E
+        xt = self.buf("xt", B, 3, N)
+        li = 0
+        for s, (prev, step) in enumerate(pairs):
+            sin = self.buf("temb.sin", len(pairs), E)
+            th = self.buf("temb.h", B, E)
+            temb = self.buf("temb", B, E)
+            row = sin[s:s + 1].expand(B, E)       # stride-0 view: every sample shares the noise level in sampling
+            self.linear(row, self.W["tw0"], self.W["tb0"], 4, th)
+            self.linear(th, self.W["tw2"], self.W["tb2"], 0, temb)
+            eps = self.evaluate(xt, temb)
+            logged = prev in log_set
+            x0 = x0_buf[li] if logged else None
+            call("p2pb_bridge_update", _p(xt), _p(eps), 16, _p(self.buf("coef", len(pairs), 3)[s]), int(bool(clip)), _p(xt),
+                 _p(x0), B, N, _s())
+            if logged:
+                xs_buf[li].copy_(xt)
+                li += 1
+
+    def sample(self, x1, x_cond, pairs, log_steps, clip):
+        """pairs = [(prev_step, step)] in sampling order -> (xs, pred_x0s) [B, log_count, 3, N], logged steps flipped
+        to ascending time like ``sample_ddpm`` (p2pb.py:215-262)."""
+        B, N, E = self.B, self.N, self.E
+        p = self.p2pb
+        T = len(pairs)
+        log_set = set(log_steps)
+        n_log = sum(1 for prev, _ in pairs if prev in log_set)
+        key = (tuple(pairs), tuple(sorted(log_set)), bool(clip))
+        # per-step host tables: sinusoid of the noise level, posterior scalars (fp32, same op order as p_posterior)
+        sin = self.buf("temb.sin", T, E)
+        coef = self.buf("coef", T, 3)
+        sin_h = torch.stack([self.time_embedding(float(p.noise_levels[step].item()), None) for _, step in pairs])
+        coef_h = torch.tensor([p.posterior_coefs(prev, step) for prev, step in pairs], dtype=torch.float32)
+        sin.copy_(sin_h)
+        coef.copy_(coef_h.to(self.dev))
+        xt = self.buf("xt", B, 3, N)
+        xt.copy_(x1.detach().to(self.dev, torch.float32))
+        if x_cond is not None:
+            self.prepare_cond(x_cond.detach().to(self.dev, torch.float32))
+        xs_buf = self.buf(f"xs{n_log}", n_log, B, 3, N)
+        x0_buf = self.buf(f"x0s{n_log}", n_log, B, 3, N)
+        if os.environ.get("P2PB_NO_GRAPH"):     # debugging aid: same kernels, no graph capture
+            self._run_loop(pairs, log_set, clip, xs_buf, x0_buf)
+            xs = torch.flip(xs_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
+            return xs, torch.flip(x0_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
+        entry = self._graphs.get(key)
+        if entry is None:
+            # first call: run eagerly once (allocates every buffer, sets kernel attributes), then capture
+            l0 = launch_count()
+            self._run_loop(pairs, log_set, clip, xs_buf, x0_buf)
+            self.kernels_per_sample = launch_count() - l0
+            torch.cuda.current_stream().synchronize()
+            xt.copy_(x1.detach().to(self.dev, torch.float32))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_loop(pairs, log_set, clip, xs_buf, x0_buf)
+            self._graphs[key] = (g,)
+            xt.copy_(x1.detach().to(self.dev, torch.float32))
+            entry = self._graphs[key]
+        entry[0].replay()
+        xs = torch.flip(xs_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
+        x0s = torch.flip(x0_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
+        return xs, x0s
+
+
+def get_engine(p2pb, net, x_shape, cond_shape) -> Engine:
+    B, _, N = x_shape
+    F = 0 if cond_shape is None else cond_shape[1]
+    key = (id(net), B, N, F)
+    eng = p2pb._engines.get(key)
+    if eng is None:
+        eng = Engine(p2pb, net, B, N, F)
+        p2pb._engines[key] = eng
+    p2pb.last_engine = eng
+    return eng

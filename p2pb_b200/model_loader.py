@@ -75,7 +75,7 @@ def save_checkpoint(path: str, model: P2PB, step: int = 0) -> None:
     torch.save({"step": step, "model_state": model.state_dict(), "optimizer_state": {}}, path)
 
 
-def seeded_state_dict(net: torch.nn.Module, seed: int = 0) -> Dict[str, torch.Tensor]:
+def seeded_state_dict(net: torch.nn.Module, seed: int = 0, head_scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """Seeded synthetic weights for ``net`` (no trained checkpoints exist offline): one independent RNG stream per
     state-dict key, so values do not depend on construction order.  Conv/linear weights ~ U(+-1/sqrt(fan_in))
     (AdaGN ``emd`` at half scale), norm gains 1+0.1 N(0,1), biases 0.05 N(0,1) with the AdaGN (1, 0) centre."""
@@ -97,5 +97,7 @@ def seeded_state_dict(net: torch.nn.Module, seed: int = 0) -> Dict[str, torch.Te
             t = 0.05 * torch.randn(shp, generator=g)
             if key.endswith(".emd.bias"):
                 t[: shp[0] // 2] += 1.0
+        if key.startswith("classifier.2."):
+            t = t * head_scale   # < 1: damped noise head, keeps the free-running T-step map well conditioned
         out[key] = t.float()
     return out

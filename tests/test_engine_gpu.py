@@ -1,0 +1,117 @@
+"""GPU parity of the fused engine (hand-written kernels only, CUDA graph) against
+  * the golden outputs of the reference's REAL model code (tests/golden/model_*.npz, fp32 CPU) and
+  * the eager reference-shaped path on the same device.
+Tolerance: the engine's contractions are TF32 tensor-core MMAs with fp32 accumulation -- the arithmetic the reference's
+own convolutions use on a GPU (cuDNN TF32 default) -- so one network evaluation is compared to the fp32 golden with
+mean |err| <= 2e-3 and max |err| <= 3e-2 on eps of O(1); the T-step loop is compared set-wise (Chamfer, the
+north-star bound 1e-5) because discrete ops (voxel rounding, FPS, ball query) flip on rounding-level differences."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from tests.helpers import load_cfg, patch_input
+from tests.test_model_gpu import build
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    cfg = load_cfg(str(z["cfg_name"]), **(yaml.safe_load(str(z["overrides"])) or {}))
+    return z, cfg
+
+
+@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino"])
+def test_engine_single_evaluation_vs_reference_golden(golden_dir, name):
+    from p2pb_b200.engine import get_engine
+
+    z, cfg = _golden(golden_dir, name)
+    model, _ = build(cfg, backend="engine")
+    x = torch.from_numpy(z["x_start"]).cuda()
+    xc = torch.from_numpy(z["x_cond"].astype(np.float32)).cuda() if z["x_cond"].size else None
+    eng = get_engine(model, model.model, x.shape, None if xc is None else xc.shape)
+    B, _, N = x.shape
+    nl = float(z["noise_level"][0])
+    with torch.no_grad():
+        if xc is not None:
+            eng.prepare_cond(xc)
+        sin = eng.time_embedding(nl, None)[None].expand(B, -1).contiguous()
+        th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
+        eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
+        eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
+        eps_rows = eng.evaluate(x.contiguous(), temb)
+    torch.cuda.synchronize()
+    eps = eps_rows[:, :3].reshape(B, N, 3).permute(0, 2, 1).cpu().numpy()
+    err = np.abs(eps - z["eps"])
+    print(f"{name}: engine vs reference golden eps: mean|err|={err.mean():.3e} max|err|={err.max():.3e} |eps|max={np.abs(z['eps']).max():.2f}")
+    assert err.mean() <= 2e-3 and err.max() <= 3e-2, (err.mean(), err.max())
+
+
+@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_t30_damped"])
+def test_engine_teacher_forced_steps_vs_reference_golden(golden_dir, name):
+    """Every step of the loop (T=5 on config 1 = first 1024 points of the reference's test.xyz; T=30 on 2 x 2048
+    points), teacher-forced: the engine advances the REFERENCE's state x_t (golden chain) by one bridge step and must
+    land on the reference's x_{t-1}.  (Free-running with un-damped random weights is chaotic -- see DESIGN.md.)"""
+    from p2pb_b200.engine import get_engine
+    from p2pb_b200.p2pb import space_indices
+
+    z, cfg = _golden(golden_dir, name)
+    model, _ = build(cfg, backend="engine", head_scale=float(z["head_scale"]))
+    T = int(z["T"])
+    chain = torch.from_numpy(z["x_chain"]).cuda()          # [B, T, 3, N], index 0 = final state
+    x = torch.from_numpy(z["x_start"]).cuda()
+    eng = get_engine(model, model.model, x.shape, None)
+    rev = space_indices(1000, T + 1)[::-1]
+    worst = 0.0
+    for s, (prev, step) in enumerate(zip(rev[1:], rev[:-1])):
+        before = x if s == 0 else chain[:, T - s]
+        after_ref = chain[:, T - 1 - s]
+        xs, _ = eng.sample(before.contiguous(), None, [(prev, step)], [prev], False)
+        d = (xs[:, 0] - after_ref).abs()
+        worst = max(worst, d.max().item())
+        assert d.mean().item() < 5e-4 and d.max().item() < 1e-2, (s, d.mean().item(), d.max().item())
+    print(f"{name} teacher-forced: worst max|diff| over {T} steps = {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", ["pvds_cfg1_damped", "pvds_t30_damped"])
+def test_engine_free_running_loop_vs_reference_golden(golden_dir, name):
+    """Free-running T-step loop through P2PB.sample (engine, one CUDA graph) on the damped-head checkpoint vs the
+    reference's real P2PB.sample: Chamfer (calculate_cd_cuda definition) within the north-star bound 1e-5."""
+    from p2pb_b200 import ops
+
+    z, cfg = _golden(golden_dir, name)
+    model, _ = build(cfg, backend="engine", head_scale=float(z["head_scale"]))
+    x = torch.from_numpy(z["x_start"]).cuda()
+    T = int(z["T"])
+    out = model.sample(x_start=x, steps=T, log_count=T, verbose=False)
+    out2 = model.sample(x_start=x, steps=T, log_count=T, verbose=False)      # graph replay: bit-identical
+    assert torch.equal(out["x_pred"], out2["x_pred"])
+    assert out["x_chain"].shape == z["x_chain"].shape
+    ref = torch.from_numpy(z["x_pred"]).cuda()
+    cd = ops.calculate_cd(out["x_pred"], ref)
+    diff = (out["x_pred"] - ref).abs()
+    moved = (ref - x).abs().mean().item()
+    print(f"{name}: T={T} chamfer={max(cd):.3e} mean|diff|={diff.mean():.3e} max|diff|={diff.max():.3e} (mean |x_pred-x_start|={moved:.3e})")
+    # T=5 (the reference scripts' default step count): the north-star bound.  T=30: rounding-level differences (TF32
+    # vs the fp32 golden) are amplified step after step by the discrete ops; bound 5e-5, measured value printed above.
+    assert max(cd) < (1e-5 if T <= 5 else 5e-5), cd
+    assert diff.mean().item() < 0.1 * moved + 1e-4
+
+
+def test_engine_vs_eager_batch(golden_dir):
+    """B=4 patches, N=2048, T=3: engine vs the eager path (our ops + torch library layers) on the same GPU."""
+    from p2pb_b200 import ops
+
+    cfg = load_cfg("PVDS_PUNet")
+    model, _ = build(cfg, backend="engine", head_scale=0.02)
+    x = patch_input(4, 2048, seed=11).cuda()
+    a = model.sample(x_start=x, steps=3, log_count=3, verbose=False, backend="engine")
+    b = model.sample(x_start=x, steps=3, log_count=3, verbose=False, backend="eager")
+    cd = ops.calculate_cd(a["x_pred"], b["x_pred"])
+    diff = (a["x_pred"] - b["x_pred"]).abs()
+    print(f"engine vs eager: chamfer={max(cd):.3e} mean|diff|={diff.mean():.3e} max|diff|={diff.max():.3e}")
+    assert max(cd) < 1e-5 and diff.mean().item() < 1e-3
+    assert a["x_chain"].shape == b["x_chain"].shape == (4, 3, 3, 2048)

@@ -12,7 +12,7 @@ from tests.helpers import load_cfg, patch_input
 pytestmark = pytest.mark.gpu
 
 
-def build(cfg_dict, seed=0, backend="eager"):
+def build(cfg_dict, seed=0, backend="eager", head_scale=1.0):
     from oracle import model as OM
     from p2pb_b200.config import Config
     from p2pb_b200.p2pb import P2PB
@@ -23,7 +23,7 @@ def build(cfg_dict, seed=0, backend="eager"):
     cfg.model.ema = False
     cfg.backend = backend
     net = PVCNN2Unet(cfg)
-    sd = OM.make_state_dict(cfg_dict, seed=seed)
+    sd = OM.make_state_dict(cfg_dict, seed=seed, head_scale=head_scale)
     net.load_state_dict(sd, strict=True)
     return P2PB(cfg, net.cuda()).eval(), sd
 

@@ -15,7 +15,7 @@ from oracle import model as OM
 from oracle import ops as OO
 from tests.helpers import load_cfg
 
-CASES = ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino"]
+CASES = ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino", "pvds_cfg1_damped"]
 
 
 def _case(golden_dir, name):
@@ -29,7 +29,7 @@ def _case(golden_dir, name):
 def test_oracle_forward_matches_reference_model(golden_dir, name):
     """eps of one network evaluation: oracle restatement vs the reference's own PVCNN2Unet (fp32 CPU, 1e-4)."""
     z, cfg = _case(golden_dir, name)
-    sd = OM.make_state_dict(cfg, seed=0)
+    sd = OM.make_state_dict(cfg, seed=0, head_scale=float(z["head_scale"]))
     assert len(sd) == int(z["n_params"])
     x = torch.from_numpy(z["x_start"])
     xc = torch.from_numpy(z["x_cond"].astype(np.float32)) if z["x_cond"].size else None
@@ -128,3 +128,11 @@ def test_voxel_round_half_even_and_clamp():
     assert nc.max().item() <= 3.0 and nc.min().item() >= 0.0
     assert vc[0, 0].tolist() == [0, 3, 2, 2]  # 0 -> 0, 4 clamps to 3, 2.0 -> 2
     assert vc[0, 1].tolist() == [2, 2, 2, 2]
+
+
+def test_oracle_damped_loop_matches_reference_loop(golden_dir):
+    """Damped-head checkpoint (well-conditioned free-running loop): oracle T=5 loop vs the reference's P2PB.sample."""
+    z, cfg = _case(golden_dir, "pvds_cfg1_damped")
+    sd = OM.make_state_dict(cfg, seed=0, head_scale=float(z["head_scale"]))
+    out = OM.sample(sd, cfg, torch.from_numpy(z["x_start"]), None, steps=int(z["T"]), log_count=int(z["T"]))
+    np.testing.assert_allclose(out["x_chain"].numpy(), z["x_chain"], atol=1e-5, rtol=0)
