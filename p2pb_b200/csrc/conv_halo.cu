@@ -1,0 +1,411 @@
+// conv_halo.cu -- 3x3x3 voxel convolution as a halo-reuse implicit GEMM on tcgen05 (TF32), for the large-grid / small-
+// channel layers (r = 32, 16) where the plain per-tap TMA kernel (gemm_tf32.cu, conv mode) is bound by L2->SM traffic:
+// it re-reads the activation tile once per tap (27x).  Measured on B200 (tools/bench_conv.py): 85-155 TFLOP/s at
+// C<=64 vs 530 TFLOP/s at C=256 for the same kernel.
+//
+// Idea: store the conv INPUT as a zero-bordered row-major grid  X[b][(r+2)^3][Cin]  indexed by the padded-linear voxel
+// index q = (x+1)P^2 + (y+1)P + (z+1), P = r+2.  In padded-linear space every tap is a CONSTANT row shift
+// d = dx*P^2 + dy*P + dz, so for one dx the 9 taps (dy,dz) of a 128-row output tile read nine overlapping 128-row
+// windows of ONE contiguous run of W = 128 + 2P + 2 rows.  That run is brought into shared memory ONCE per 32-channel
+// chunk by a single TMA box load {32 ch, W rows} (128B swizzle) and the 9 taps are 9 UMMA descriptors into the same
+// buffer: start address advanced by whole 128-byte rows, with the descriptor's base-offset field carrying the swizzle
+// phase ((addr >> 7) & 7) of the un-aligned start.  Activation traffic drops from 27 to 3*(W/128) tile reads (5.8x less
+// at r=32).  Weights are stationary per (dx, 32-channel chunk) slab [9 taps][Cout][32] and shared by G = 512/Cout
+// output tiles whose accumulators all live in TMEM at once.
+//
+// Why 128B-swizzled A and not the un-swizzled core-matrix layout (which takes any 16-byte start): measured with
+// tools/ubench/mma_rate.cu on B200, one tcgen05.mma (M=128, K=32 bytes) costs max(64, N/2) cycles with a SWIZZLE_128B
+// A operand but ~115-125 cycles with an INTERLEAVE (no-swizzle) A operand, independent of the B layout.
+//
+// Outputs for border positions inside the tile's linear range are computed but masked (not stored, not counted in the
+// GroupNorm statistics); the result is written in the dense [B*r^3, Cout] row layout the rest of the engine uses.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int HBM = 128;
+constexpr int HBK = 32;
+constexpr int HALO_THREADS = 192;
+
+struct HaloArgs {
+    int B, r, P, P2, P3;      // P = r+2
+    int cin_chunks;           // Cin_p / 32
+    int cout;
+    int W;                    // window rows (odd, >= 128 + 2P + 2)
+    int G;                    // tiles per CTA
+    int tiles_per_sample, total_tiles;
+    int q_first, q_last;
+    int ldd;
+    int a_stages, slab_bufs;
+    const float* X;           // padded row-major input (only used for documentation; loads go through mapX)
+    const float* bias;
+    float* D;                 // dense rows [B*r^3, ldd]
+    float* stats;             // [total_tiles, cout, 2] or null
+};
+
+__device__ __forceinline__ uint32_t h_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one elected lane of a converged warp: ptxas then feeds tcgen05/TMA instructions from uniform registers directly
+// (with `if (lane == 0)` it emits an ELECT + R2UR "waterfall" loop around every tcgen05.mma, ~100 cycles each)
+__device__ __forceinline__ bool h_elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void h_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void h_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void h_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void h_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// B: K-major SWIZZLE_128B (as gemm_tf32.cu)
+__device__ __forceinline__ uint64_t h_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// A uses the same descriptor with a start address advanced by whole 128-byte rows inside the window (the row shift of
+// a tap): the tensor core applies the 128B swizzle to absolute shared-memory address bits, exactly as the TMA unit did
+// when it wrote the window, so no base-offset correction is needed (verified against fp64 convolutions on B200;
+// setting base_offset = (addr >> 7) & 7 gives wrong results).
+__device__ __forceinline__ void h_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void h_umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_tmem_ld32(uint32_t taddr, float* v)
+{
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float h_colsum32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            const float send = up ? v[j] : v[j + n / 2];
+            const float keep = up ? v[j + n / 2] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const HaloArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int slab_tap_bytes = a.cout * HBK * 4;        // one tap: [Cout][32] fp32, 128B-swizzled rows
+    const int slab_bytes = 9 * slab_tap_bytes;
+    const int a_stage_bytes = a.W * 128;                // W rows x 32 channels (one 128-byte swizzle span per row)
+    const int a_stage_stride = (a_stage_bytes + 1023) & ~1023;
+    uint8_t* sSlab = smem;
+    uint8_t* sA = sSlab + (size_t)a.slab_bufs * slab_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.a_stages * a_stage_stride);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + a.a_stages;
+    uint64_t* s_full = a_empty + a.a_stages;
+    uint64_t* s_empty = s_full + a.slab_bufs;
+    uint64_t* tmem_full = s_empty + a.slab_bufs;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][cout][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile0 = blockIdx.x * a.G;
+    int ntiles = a.total_tiles - tile0;
+    if (ntiles > a.G) ntiles = a.G;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+        for (int s = 0; s < a.a_stages; ++s) {
+            h_mbar_init(h_smem_u32(&a_full[s]), 1);
+            h_mbar_init(h_smem_u32(&a_empty[s]), 1);
+        }
+        for (int s = 0; s < a.slab_bufs; ++s) {
+            h_mbar_init(h_smem_u32(&s_full[s]), 1);
+            h_mbar_init(h_smem_u32(&s_empty[s]), 1);
+        }
+        h_mbar_init(h_smem_u32(tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_ptr_smem)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int nslabs = 3 * a.cin_chunks;
+
+    if (warp == 0) {
+        // ===================== producer: weight slabs (TMA) + activation windows (bulk copies) =====================
+        if (h_elect_one()) {
+            int ait = 0;
+            for (int sl = 0; sl < nslabs; ++sl) {
+                const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
+                const int sb = sl % a.slab_bufs;
+                const uint32_t sph = (uint32_t)(sl / a.slab_bufs) & 1u;
+                h_mbar_wait(h_smem_u32(&s_empty[sb]), sph ^ 1u);
+                const uint32_t sfb = h_smem_u32(&s_full[sb]);
+                h_mbar_expect_tx(sfb, (uint32_t)slab_bytes);
+                for (int t9 = 0; t9 < 9; ++t9)
+                    h_tma_load_2d(h_smem_u32(sSlab + (size_t)sb * slab_bytes + (size_t)t9 * slab_tap_bytes), &mapW, sfb,
+                                  ((dx * 9 + t9) * a.cin_chunks + kc) * HBK, 0);
+                for (int g = 0; g < ntiles; ++g, ++ait) {
+                    const int tile = tile0 + g;
+                    const int b = tile / a.tiles_per_sample;
+                    const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * HBM;
+                    const long long qs = (long long)q0 + (long long)(dx - 1) * a.P2 - (a.P + 1);  // window start row (>= 0)
+                    const int st = ait % a.a_stages;
+                    const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
+                    h_mbar_wait(h_smem_u32(&a_empty[st]), ph ^ 1u);
+                    const uint32_t fb = h_smem_u32(&a_full[st]);
+                    h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
+                    h_tma_load_2d(h_smem_u32(sA + (size_t)st * a_stage_stride), &mapX, fb, kc * HBK, (int)((long long)b * a.P3 + qs));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)(HBM >> 4) << 24);
+        int ait = 0;
+        for (int sl = 0; sl < nslabs; ++sl) {
+            const int sb = sl % a.slab_bufs;
+            const uint32_t sph = (uint32_t)(sl / a.slab_bufs) & 1u;
+            h_mbar_wait(h_smem_u32(&s_full[sb]), sph);
+            for (int g = 0; g < ntiles; ++g, ++ait) {
+                const int st = ait % a.a_stages;
+                const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
+                h_mbar_wait(h_smem_u32(&a_full[st]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (h_elect_one()) {
+                    const uint64_t abase_d = h_desc_sw128(h_smem_u32(sA + (size_t)st * a_stage_stride));
+                    const uint64_t bbase_d = h_desc_sw128(h_smem_u32(sSlab + (size_t)sb * slab_bytes));
+                    const uint32_t dcol = tmem_base + (uint32_t)(g * a.cout);
+                    const uint32_t tap_step = (uint32_t)(slab_tap_bytes >> 4);
+#pragma unroll
+                    for (int t9 = 0; t9 < 9; ++t9) {
+                        const int dy = t9 / 3 - 1, dz = t9 % 3 - 1;
+                        // row offset of this tap inside the window, in 16-byte descriptor units (128 B per row)
+                        const uint64_t ad = abase_d + (uint64_t)(((a.P + 1) + dy * a.P + dz) * 8);
+                        const uint64_t bd = bbase_d + (uint64_t)(t9 * tap_step);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            h_umma_tf32(dcol, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (uint32_t)((sl | t9 | j) != 0));
+                    }
+                    h_umma_commit(h_smem_u32(&a_empty[st]));
+                    if (g == ntiles - 1) h_umma_commit(h_smem_u32(&s_empty[sb]));
+                    if (sl == nslabs - 1 && g == ntiles - 1) h_umma_commit(h_smem_u32(tmem_full));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int qd = warp & 3;
+        h_mbar_wait(h_smem_u32(tmem_full), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r = a.r, r3 = r * r * r;
+        for (int g = 0; g < ntiles; ++g) {
+            const int tile = tile0 + g;
+            const int b = tile / a.tiles_per_sample;
+            const int q = a.q_first + (tile - b * a.tiles_per_sample) * HBM + qd * 32 + lane;
+            const int x = q / a.P2, rem = q - x * a.P2, y = rem / a.P, z = rem - y * a.P;
+            const bool ok = q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
+            const size_t v = (size_t)b * r3 + (size_t)(x - 1) * r * r + (size_t)(y - 1) * r + (size_t)(z - 1);
+            float* drow = a.D + v * a.ldd;
+            for (int c = 0; c < a.cout / 32; ++c) {
+                float vv[32];
+                h_tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * a.cout + c * 32), vv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = vv[j];
+                    if (a.bias != nullptr) t += __ldg(a.bias + c * 32 + j);
+                    vv[j] = ok ? t : 0.f;
+                }
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(drow + c * 32 + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+                }
+                if (a.stats != nullptr) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = vv[j] * vv[j];
+                    const float s1 = h_colsum32(vv, lane);
+                    const float s2 = h_colsum32(sq, lane);
+                    s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
+                    s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
+                }
+            }
+            if (a.stats != nullptr) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int t = threadIdx.x - 64;
+                for (int n = t; n < a.cout; n += 128) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        s1 += s_stats[((w * a.cout) + n) * 2 + 0];
+                        s2 += s_stats[((w * a.cout) + n) * 2 + 1];
+                    }
+                    float* o = a.stats + ((size_t)tile * a.cout + n) * 2;
+                    o[0] = s1;
+                    o[1] = s2;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled_h)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+// geometry of the padded row-major layout for resolution r: rows per sample, slack rows needed after the last sample
+P2PB_API int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int* tiles_per_sample_out)
+{
+    const int P = r + 2, P2 = P * P, P3 = P2 * P;
+    const int q_first = P2 + P + 1, q_last = P3 - P2 - P - 2;
+    if (P3_out) *P3_out = P3;
+    if (slack_rows_out) *slack_rows_out = 128 + 2 * P + 8;
+    if (tiles_per_sample_out) *tiles_per_sample_out = (q_last - q_first + 1 + HBM - 1) / HBM;
+    return P2PB_OK;
+}
+
+// X: zero-bordered row-major grid [B*(r+2)^3 + slack rows, Cin]; W: [Cout, 27*Cin] (k = tap*Cin + c);
+// D: dense rows [B*r^3, ldd]; stats (optional): [B*tiles_per_sample, Cout, 2]
+P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                              int Cin, int Cout, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    P2PB_CHECK_ARG(B > 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cout <= 256, "conv3d_halo: Cin=%d Cout=%d (multiples of 32, Cout<=256)", Cin, Cout);
+    P2PB_CHECK_ARG(r >= 8 && r <= 62, "conv3d_halo: r=%d out of range (TMA box rows 128+2(r+2)+2 <= 256)", r);
+    P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= Cout, "conv3d_halo: bad ldd");
+    HaloArgs a = {};
+    a.B = B; a.r = r; a.P = r + 2; a.P2 = a.P * a.P; a.P3 = a.P2 * a.P;
+    a.cin_chunks = Cin / 32; a.cout = Cout;
+    a.W = 128 + 2 * a.P + 2;
+    a.q_first = a.P2 + a.P + 1;
+    a.q_last = a.P3 - a.P2 - a.P - 2;
+    a.tiles_per_sample = (a.q_last - a.q_first + 1 + HBM - 1) / HBM;
+    a.total_tiles = B * a.tiles_per_sample;
+    a.G = 512 / Cout;
+    if (a.G > 8) a.G = 8;
+    a.ldd = ldd;
+    a.X = X; a.bias = bias; a.D = D; a.stats = stats;
+    const int slab_bytes = 9 * Cout * HBK * 4;
+    const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
+    const int budget = 225 * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
+    a.slab_bufs = (2 * slab_bytes + 3 * a_stage_stride <= budget) ? 2 : 1;
+    a.a_stages = (budget - a.slab_bufs * slab_bytes) / a_stage_stride;
+    if (a.a_stages > 6) a.a_stages = 6;
+    P2PB_CHECK_ARG(a.a_stages >= 2, "conv3d_halo: shared memory budget exceeded (Cout=%d r=%d)", Cout, r);
+    const size_t smem = 1024 + (size_t)a.slab_bufs * slab_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)4 * Cout * 2 * 4;
+    CUtensorMap mapW, mapX;
+    {
+        static PFN_encodeTiled_h enc = nullptr;
+        if (enc == nullptr) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+                qres == cudaDriverEntryPointSuccess)
+                enc = reinterpret_cast<PFN_encodeTiled_h>(p);
+        }
+        P2PB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+        cuuint64_t dims[2] = {(cuuint64_t)27 * Cin, (cuuint64_t)Cout};
+        cuuint64_t str[1] = {(cuuint64_t)27 * Cin * 4};
+        cuuint32_t box[2] = {HBK, (cuuint32_t)Cout};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult rc = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), dims, str, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) {
+            p2pb_set_error("conv3d_halo: cuTensorMapEncodeTiled(W) failed (%d)", (int)rc);
+            return P2PB_ERR_CUDA;
+        }
+        int slack = 0;
+        p2pb_conv_halo_layout(r, nullptr, &slack, nullptr);
+        cuuint64_t xdims[2] = {(cuuint64_t)Cin, (cuuint64_t)B * a.P3 + (cuuint64_t)slack};
+        cuuint64_t xstr[1] = {(cuuint64_t)Cin * 4};
+        cuuint32_t xbox[2] = {HBK, (cuuint32_t)a.W};
+        rc = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), xdims, xstr, xbox, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) {
+            p2pb_set_error("conv3d_halo: cuTensorMapEncodeTiled(X) failed (%d)", (int)rc);
+            return P2PB_ERR_CUDA;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = (a.total_tiles + a.G - 1) / a.G;
+    conv_halo_kernel<<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}

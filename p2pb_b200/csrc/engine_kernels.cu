@@ -621,3 +621,94 @@ P2PB_API int p2pb_bridge_update(const float* xt, const float* eps, int lde, cons
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Producers of the zero-bordered row-major conv input  X[b][(r+2)^3][Cp]  (padded-linear voxel index, see
+// conv_halo.cu).  Same thread mapping as the dense kernels (one thread per float4, channel chunk fastest: coalesced
+// reads and writes); only interior rows are ever written, so the border rows stay zero from allocation.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t padded_row(int b, int v, int r)
+{
+    const int P = r + 2;
+    const int x = v / (r * r), y = (v / r) % r, z = v % r;
+    return (size_t)b * P * P * P + (size_t)(x + 1) * P * P + (size_t)(y + 1) * P + (z + 1);
+}
+
+__global__ void __launch_bounds__(256) voxelize_padded_kernel(const float* __restrict__ feat, int ldf, int Cf,
+                                                              const float* __restrict__ temb, int E,
+                                                              const int* __restrict__ order, const int* __restrict__ start,
+                                                              const int* __restrict__ cnt, float* __restrict__ out, int Cp,
+                                                              int N, int r, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int r3 = r * r * r;
+    const int C4 = Cp >> 2;
+    const int c0 = (int)(e % C4) * 4;
+    const long long vrow = e / C4;
+    const int b = (int)(vrow / r3);
+    const int v = (int)(vrow - (long long)b * r3);
+    const int n = cnt[vrow];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n > 0) {
+        const float inv = (float)(1.0 / (double)(float)n);
+        const int* ord = order + (size_t)b * N + start[vrow];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            if (c < Cf) {
+                float s = 0.f;
+                for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
+                a[j] = s;
+            } else if (c < Cf + E) {
+                const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
+                float s = 0.f;
+                for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
+                a[j] = s;
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * Cp + c0) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
+                                  const int* start, const int* cnt, float* out, int Cp, int B, int N, int r, void* stream)
+{
+    P2PB_CHECK_ARG(Cp % 32 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_padded: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
+    const long long total4 = (long long)B * r * r * r * (Cp / 4);
+    if (total4 == 0) return P2PB_OK;
+    voxelize_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
+                                                                                   Cp, N, r, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// y = swish(x*A + B) of dense conv-output rows [B*r^3, ldx] -> zero-bordered padded input rows of the next conv
+__global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
+                                                                const float* __restrict__ Bc, int C, float* __restrict__ out,
+                                                                int r, long long total4)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const int r3 = r * r * r;
+    const int C4 = C >> 2;
+    const int c = (int)(e % C4) * 4;
+    const long long vrow = e / C4;
+    const int b = (int)(vrow / r3);
+    const int v = (int)(vrow - (long long)b * r3);
+    const float4 xv = *reinterpret_cast<const float4*>(x + vrow * ldx + c);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c));
+    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * C + c) = affine4<1>(xv, a, bb);
+}
+
+P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, float* out,
+                                    void* stream)
+{
+    P2PB_CHECK_ARG(C % 32 == 0 && ldx % 4 == 0, "affine_act_padded: C %% 32, ldx %% 4");
+    const long long total4 = (long long)B * r * r * r * (C / 4);
+    if (total4 == 0) return P2PB_OK;
+    affine_act_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, r, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}

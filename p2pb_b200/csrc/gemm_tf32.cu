@@ -42,6 +42,19 @@ struct GemmArgs {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a converged warp (ptxas then knows a single thread issues the tcgen05/TMA instructions and
+// feeds them from uniform registers directly instead of emitting a per-operand R2UR "waterfall" loop)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -205,7 +218,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int cb = 0, cx = 0, cy = 0;
             if (args.conv) {
                 cb = m_tile / args.tiles_per_sample;
@@ -246,7 +259,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             const uint32_t ph = (uint32_t)(it / stages) & 1u;
             mbar_wait(smem_u32(&full_bar[st]), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint64_t ad = umma_desc_sw128(smem_u32(sA + (size_t)st * A_STAGE_BYTES));
                 const uint64_t bd = umma_desc_sw128(smem_u32(sB + (size_t)st * B_STAGE_BYTES));
 #pragma unroll

@@ -76,3 +76,37 @@ def pack_conv3d_weight(w: torch.Tensor, cin_pad: int, perm: Optional[Sequence[in
     p = torch.zeros((cout, 27, cin_pad), dtype=torch.float32, device=w.device)
     p[:, :, :cin] = w.reshape(cout, cin, 27).permute(0, 2, 1)
     return p.reshape(cout, 27 * cin_pad).contiguous()
+
+
+# ---- halo-reuse conv (csrc/conv_halo.cu): zero-bordered row-major input -------------------------------------------
+def halo_layout(r: int):
+    """(rows per sample P^3, slack rows after the last sample, tiles per sample) of the padded layout."""
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    call("p2pb_conv_halo_layout", int(r), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return a.value, b.value, c.value
+
+
+def alloc_padded(B: int, C: int, r: int, device) -> torch.Tensor:
+    """Zero-initialised X[B*(r+2)^3 + slack, C]; border rows stay zero forever (kernels only write interior rows)."""
+    P3, slack, _ = halo_layout(r)
+    return torch.zeros(B * P3 + slack, C, dtype=torch.float32, device=device)
+
+
+def dense_to_padded(grid: torch.Tensor, r: int) -> torch.Tensor:
+    """Test helper (torch ops): channels-last dense grid [B, r, r, r, C] -> padded row-major layout."""
+    B, C = grid.shape[0], grid.shape[-1]
+    P = r + 2
+    X = alloc_padded(B, C, r, grid.device)
+    X[: B * P ** 3].view(B, P, P, P, C)[:, 1:-1, 1:-1, 1:-1, :] = grid
+    return X
+
+
+def conv3d_halo(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], B: int, r: int, cin: int, cout: int,
+                out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((B * r ** 3, cout), dtype=torch.float32, device=X.device)
+    assert X.is_contiguous() and X.shape[1] == cin
+    with torch.cuda.device(X.device):
+        call("p2pb_conv3d_halo", _p(X), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
+             int(cout), _s())
+    return out

@@ -282,6 +282,14 @@ class Engine:
         assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
         return t
 
+    def padded(self, name: str, B: int, C: int, r: int) -> torch.Tensor:
+        """Zero-bordered padded-linear conv input [B*(r+2)^3 + slack, C] (conv_halo.cu); borders stay zero forever."""
+        t = self._bufs.get(name)
+        if t is None:
+            t = dense.alloc_padded(B, C, r, self.dev)
+            self._bufs[name] = t
+        return t
+
     # ------------------------------------------------------------------------------------------------ primitives
     def gemm(self, name, segs, ks, w, bias, n_out, rows_per_sample, bias2=None, want_stats=True, out=None):
         """rows GEMM + (sum, sum^2) statistics in the format gn_coef expects -> (raw, stats, tiles)."""
@@ -342,19 +350,35 @@ class Engine:
         """PVConv (pvcnn.py:306-334): voxel branch + point branch -> rows [B*n_pts, cout]."""
         B, r, cout, cp = self.B, P["r"], P["cout"], P["cp"]
         r3 = r ** 3
-        grid = self.buf(f"{name}.grid", B * r3, cp)
-        call("p2pb_voxelize_cl", _p(feats), int(feats.stride(0)), P["cin"], _p(temb if P["E"] else None), P["E"], _p(prep["order"]),
-             _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
+        halo = r >= 16 and cout <= 128 and cout % 32 == 0        # large grid / few channels: halo-reuse conv (conv_halo.cu)
         raw1 = self.buf(f"{name}.raw1", B * r3, cout)
-        st1 = self.buf(f"{name}.st1", B * r3 // 128, cout, 2)
-        dense.conv3d_cl(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1)
-        A1, B1, _ = self.coef(f"{name}.n1", st1, r3 // 128, P["n1"], cout, r3)
-        act1 = self.buf(f"{name}.act1", B * r3, pad32(cout))
-        self.act(raw1, A1, B1, r3, cout, act1, act=1)
         raw2 = self.buf(f"{name}.raw2", B * r3, cout)
-        st2 = self.buf(f"{name}.st2", B * r3 // 128, cout, 2)
-        dense.conv3d_cl(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
-        A2, B2, ym = self.coef(f"{name}.n2", st2, r3 // 128, P["n2"], cout, r3, want_mean="se0" in P)
+        tvox = _p(temb if P["E"] else None)
+        if halo:
+            _, _, tiles = dense.halo_layout(r)
+            grid = self.padded(f"{name}.grid", B, cp, r)
+            call("p2pb_voxelize_padded", _p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]),
+                 _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
+            st1 = self.buf(f"{name}.st1", B * tiles, cout, 2)
+            dense.conv3d_halo(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1)
+            A1, B1, _ = self.coef(f"{name}.n1", st1, tiles, P["n1"], cout, r3)
+            act1 = self.padded(f"{name}.act1", B, pad32(cout), r)
+            call("p2pb_affine_act_padded", _p(raw1), cout, _p(A1), _p(B1), B, cout, r, _p(act1), _s())
+            st2 = self.buf(f"{name}.st2", B * tiles, cout, 2)
+            dense.conv3d_halo(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
+        else:
+            tiles = r3 // 128
+            grid = self.buf(f"{name}.grid", B * r3, cp)
+            call("p2pb_voxelize_cl", _p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]),
+                 _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
+            st1 = self.buf(f"{name}.st1", B * tiles, cout, 2)
+            dense.conv3d_cl(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1)
+            A1, B1, _ = self.coef(f"{name}.n1", st1, tiles, P["n1"], cout, r3)
+            act1 = self.buf(f"{name}.act1", B * r3, pad32(cout))
+            self.act(raw1, A1, B1, r3, cout, act1, act=1)
+            st2 = self.buf(f"{name}.st2", B * tiles, cout, 2)
+            dense.conv3d_cl(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
+        A2, B2, ym = self.coef(f"{name}.n2", st2, tiles, P["n2"], cout, r3, want_mean="se0" in P)
         se = None
         if "se0" in P:
             hid = self.buf(f"{name}.seh", B, P["se0"].shape[0])

@@ -1,6 +1,8 @@
 """GPU tests of the tcgen05 GEMM / implicit-GEMM conv kernels against fp64 torch references.
 TF32 tolerance (10-bit mantissa operands, fp32 accumulate): max |err| <= 2e-3 * max |ref| -- the arithmetic class of
 the reference's own cuDNN-TF32 convolutions."""
+import os
+
 import pytest
 import torch
 
@@ -89,3 +91,28 @@ def test_conv3d_padded_channels_and_permutation():
     out = dense.conv3d_cl(grid, dense.pack_conv3d_weight(w, cp, perm), None, B, r, cp, cout)
     ref = F.conv3d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 4, 1).reshape(-1, cout)
     _close(out, ref)
+
+
+@pytest.mark.parametrize("B,r,cin,cout", [(1, 8, 32, 32), (2, 16, 64, 64), (1, 32, 32, 32), (2, 32, 64, 64), (1, 16, 128, 128),
+                                          (3, 16, 128, 64), (1, 32, 64, 32)])
+def test_conv3d_halo_vs_fp64(B, r, cin, cout):
+    """Halo-reuse conv (chunk-planar padded input, un-swizzled A descriptors, stationary weight slabs)."""
+    import torch.nn.functional as F
+
+    from p2pb_b200 import dense
+
+    g = torch.Generator(device="cuda").manual_seed(r + cin + cout)
+    x = torch.randn(B, cin, r, r, r, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    X = dense.dense_to_padded(x.permute(0, 2, 3, 4, 1).contiguous(), r)
+    _, _, tps = dense.halo_layout(r)
+    stats = torch.zeros(B * tps, cout, 2, device="cuda")
+    out = torch.full((B * r ** 3, cout), float("nan"), device="cuda")
+    dense.conv3d_halo(X, dense.pack_conv3d_weight(w, cin), bias, B, r, cin, cout, out=out, stats=stats)
+    ref = F.conv3d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(B * r ** 3, cout)
+    _close(out, ref)
+    s = stats.double().view(B, tps, cout, 2).sum(1)
+    o = out.double().view(B, -1, cout)
+    assert torch.allclose(s[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)

@@ -31,7 +31,13 @@ for r, cin, cout in shapes:
     tc = timeit(lambda: F.conv3d(x, w, bias, padding=1))
     xc = x.contiguous()
     tcc = timeit(lambda: F.conv3d(xc, w, bias, padding=1))
+    th = float("nan")
+    if r >= 16 and cout <= 128:
+        X = dense.dense_to_padded(grid, r)
+        _, _, tps = dense.halo_layout(r)
+        hst = torch.zeros(B * tps, cout, 2, device="cuda")
+        th = timeit(lambda: dense.conv3d_halo(X, wp, bias, B, r, cin, cout, out=out, stats=hst))
     fl = 2.0 * B * r ** 3 * 27 * cin * cout
     tot_m += t; tot_c += min(tc, tcc)
-    print(f"r={r:3d} cin={cin:4d} cout={cout:4d}: ours {t:7.3f} ms {fl / t / 1e9:7.1f} TF/s | cudnn CL {tc:7.3f} ms {fl / tc / 1e9:7.1f} | cudnn NCDHW {tcc:7.3f} ms {fl / tcc / 1e9:7.1f}")
+    print(f"r={r:3d} cin={cin:4d} cout={cout:4d}: ours {t:7.3f} ms {fl / t / 1e9:7.1f} TF/s | halo {th:7.3f} ms {fl / th / 1e9:7.1f} | cudnn CL {tc:7.3f} ms {fl / tc / 1e9:7.1f} | cudnn NCDHW {tcc:7.3f} ms {fl / tcc / 1e9:7.1f}")
 print("sum ours", tot_m, "sum cudnn best", tot_c)
