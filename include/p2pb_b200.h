@@ -71,6 +71,77 @@ int p2pb_trilinear_devoxelize(const float* coords, const float* grid, int B, int
 int p2pb_nm_distance(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist, int* idx,
                      unsigned long long* scratch, void* stream);
 
+/* ==== fused channels-last engine (rows [M, ld] fp32, ld multiple of 4) ====================== */
+
+/* The dense contractions: replaces cuDNN Conv1d/Conv2d(1x1) and cuBLAS Linear behind
+ * /root/reference/models/pvcnn.py:174-192 and models/modules.py:337,365-370 (tcgen05 TF32 tiles fed by TMA).
+ * D[M,N] = sum_i A_i[M,K_i] * W[N, sum K_i]^T + bias[N] + bias2[m / rows_per_sample, N]; up to 3 A segments replace
+ * torch.cat; stats (optional) [ceil(M/128), N, 2] = per-tile column (sum, sum of squares) for the following GroupNorm. */
+int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2, int lda2,
+                   const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D, int ldd,
+                   float* stats, int M, int N, void* stream);
+
+/* replaces nn.Conv3d 3x3x3 pad 1 (/root/reference/models/pvcnn.py:265-284): per-tap 5-D TMA implicit GEMM (any r = 2^k >= 8)
+ * grid [B,r,r,r,Cin] channels-last, W [Cout, 27*Cin] (k = ((kx*3+ky)*3+kz)*Cin + c), D [B*r^3, ldd] */
+int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                   int Cin, int Cout, void* stream);
+
+/* same convolution, halo-reuse kernel for large grids / few channels (r in [8,62], Cout <= 128):
+ * X = zero-bordered padded-linear rows [B*(r+2)^3 + slack, Cin] (p2pb_conv_halo_layout gives rows/slack/tiles) */
+int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int* tiles_per_sample_out);
+int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                     int Cin, int Cout, void* stream);
+
+/* coords [B,3,N] -> columns col0..col0+2 of rows [B*N, ld] */
+int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N, int ld, int col0, void* stream);
+
+/* CSR gather-mean of point rows (+ broadcast time-embedding channels) into a dense grid: replaces avg_voxelize_kernel
+ * (vox_gpu.cu:50-78) + torch::zeros; _cl writes rows [B*r^3, Cp], _padded writes the zero-bordered padded-linear layout */
+int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* start,
+                     const int* cnt, float* out, int Cp, int B, int N, int r, void* stream);
+int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* start,
+                         const int* cnt, float* out, int Cp, int B, int N, int r, void* stream);
+
+/* GroupNorm / AdaGN statistics -> per-(sample, channel) affine (and the SE squeeze): replaces nn.GroupNorm's reduction,
+ * AdaGN.forward (/root/reference/models/modules.py:341-358) and SE3d's mean (modules.py:378) */
+int p2pb_gn_coef(const float* stats, int tiles, int B, int C, int groups, int rows_per_sample, const float* gamma,
+                 const float* beta, const float* emd, int ld_emd, int emd_off, float eps, float* coefA, float* coefB,
+                 float* ymean, void* stream);
+int p2pb_col_stats(const float* x, int ld, int B, int rows, int C, float* out, void* stream);
+
+/* y = act(x*A[b,c] + B[b,c]) (act 0 none / 1 swish), optional max over `pool` consecutive rows (pvcnn.py:414) or global
+ * max over the sample's rows into gmax[B,C] (pvcnn.py:923,930); _padded writes the next conv's padded-linear input */
+int p2pb_affine_act(const float* x, int ldx, const float* A, const float* Bc, int rows_per_sample, int M, int C, int act,
+                    int pool, float* out, int ldo, float* gmax, void* stream);
+int p2pb_affine_act_padded(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, float* out,
+                           void* stream);
+
+/* trilinear devoxelize of the raw conv output with AdaGN*SE folded in + Swish(AdaGN(point branch)) add
+ * (trilinear_devox_gpu.cu:21-109 + /root/reference/models/pvcnn.py:318-328) */
+int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, const float* A, const float* Bc, const float* se,
+                  const float* praw, int ldp, const float* pA, const float* pB, float* out, int ldo, int B, int C, int N,
+                  int r, void* stream);
+
+/* [features[idx], xyz[idx]-centre] rows for the SA-module MLP (pvcnn_grouping_gpu.cu:18-39 x2 + pvcnn.py:117-126) */
+int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* coords, const float* centers, const int* idx,
+                    float* out, int ldo, int B, int N, int M, int U, void* stream);
+
+/* 3-NN weighted gather (pvcnn_neighbor_interpolate_gpu.cu:96-124) on rows */
+int p2pb_interp_rows(const float* f, int ldf, const int* idx, const float* w, float* out, int ldo, int B, int C, int N,
+                     int M, void* stream);
+
+/* per-sample small Linear, act: 0 none 1 swish 2 relu 3 sigmoid 4 leaky_relu(0.1) */
+int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw, const float* bias, int B, int K, int O, int act,
+                      float* out, int ldo, void* stream);
+
+/* LinearAttention core on the bottleneck tokens (/root/reference/models/modules.py:186-192) */
+int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N, float* out, int ldo, void* stream);
+
+/* pred_x0 = xt - std*eps ; xt_next = mu_x0*pred_x0 + mu_xn*xt  (/root/reference/models/p2pb.py:155-165, 190-213);
+ * coef = device pointer to {std_fwd[n], mu_x0, mu_xn} */
+int p2pb_bridge_update(const float* xt, const float* eps, int lde, const float* coef, int clip, float* xt_next,
+                       float* pred_x0, int B, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,71 @@
+"""Live roofline measurement of the dominant kernel for bench.py.
+
+Dominant kernel of the PVDS N=2048 hot path = the 3x3x3 voxel convolution at r=32 (conv_halo_kernel): per network
+evaluation it accounts for ~45 % of the GPU time (profiles/launches_engine_r1*.csv).  Measured here on its largest
+instance (fp_layers.3.1 voxel_layers.0/.4: 64 -> 64 channels on a 32^3 grid, one launch per batch of B patches) with
+CUDA events on the launching stream, inputs larger than L2 (B=64: 644 MB input + 537 MB output per launch).
+
+achieved = algorithmic FLOPs per launch / mean launch time, algorithmic FLOPs = 2 * B * r^3 * 27 * Cin * Cout
+(SURVEY.md §8d counts 7.2478 GFLOP per patch for this layer).  Bound: tensor.  peak = measured dense TF32 rate =
+half of the measured cuBLAS bf16 rate in MEASURED_PEAKS.json (TF32 runs at half the bf16 MMA rate: K=8 vs K=16 per
+instruction at equal issue cost; confirmed by tools/ubench/mma_rate.cu: 1151 vs 2302 TFLOP/s at N>=128)."""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+
+from . import dense
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops"]), float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json, burst)"
+        except Exception:
+            pass
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
+    r, cin, cout = 32, 64, 64
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = dense.alloc_padded(B, cin, r, dev)
+    P = r + 2
+    X[: B * P ** 3].view(B, P, P, P, cin)[:, 1:-1, 1:-1, 1:-1, :] = torch.randn(B, r, r, r, cin, device=dev, generator=g)
+    w = torch.randn(cout, 27 * cin, device=dev, generator=g) / (27 * cin) ** 0.5
+    bias = torch.zeros(cout, device=dev)
+    out = torch.empty(B * r ** 3, cout, device=dev)
+    _, _, tps = dense.halo_layout(r)
+    stats = torch.zeros(B * tps, cout, 2, device=dev)
+    for _ in range(3):
+        dense.conv3d_halo(X, w, bias, B, r, cin, cout, out=out, stats=stats)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        dense.conv3d_halo(X, w, bias, B, r, cin, cout, out=out, stats=stats)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * B * r ** 3 * 27 * cin * cout
+    achieved = flops / (ms * 1e-3) / 1e12
+    bf16_peak, _, how = measured_peaks()
+    peak = bf16_peak / 2.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("conv_halo_64x64_r32_B64_dram_bytes")
+        except Exception:
+            traffic = None
+    return {"bound": "tensor", "kernel": "conv_halo_kernel (3x3x3 conv, 64->64 ch, 32^3 grid, TF32 tcgen05)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic, "ms_per_launch": ms, "flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": 4.0 * B * ((r + 2) ** 3 * cin + r ** 3 * cout),
+            "peak_source": f"{how}: bf16 {bf16_peak:.1f} TFLOP/s / 2 for TF32"}

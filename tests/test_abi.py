@@ -78,3 +78,13 @@ def test_seeded_weights_equal_oracle_weights():
     assert a.keys() == b.keys()
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_header_declares_every_exported_symbol():
+    """include/p2pb_b200.h is the complete boundary: every P2PB_API function in csrc/ is declared there."""
+    import glob
+
+    exported = set()
+    for f in glob.glob(os.path.join(ROOT, "p2pb_b200", "csrc", "*.cu")):
+        exported |= set(re.findall(r"P2PB_API\s+[\w\s\*]+?\b(p2pb_\w+)\s*\(", open(f).read()))
+    assert exported == set(declared_symbols()), exported ^ set(declared_symbols())
