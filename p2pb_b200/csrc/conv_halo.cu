@@ -34,7 +34,9 @@ struct HaloArgs {
     int cin_chunks;           // Cin_p / 32
     int cout;
     int W;                    // window rows (odd, >= 128 + 2P + 2)
-    int G;                    // tiles per CTA
+    int G;                    // tiles per work unit (their accumulators share one TMEM half)
+    int halves;               // 2: units ping-pong between two 256-column TMEM halves; 1: one unit owns all 512 columns
+    int total_units;
     int tiles_per_sample, total_tiles;
     int q_first, q_last;
     int ldd;
@@ -157,14 +159,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     uint64_t* a_empty = a_full + a.a_stages;
     uint64_t* s_full = a_empty + a.a_stages;
     uint64_t* s_empty = s_full + a.slab_bufs;
-    uint64_t* tmem_full = s_empty + a.slab_bufs;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = s_empty + a.slab_bufs;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][cout][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile0 = blockIdx.x * a.G;
-    int ntiles = a.total_tiles - tile0;
-    if (ntiles > a.G) ntiles = a.G;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -177,7 +177,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             h_mbar_init(h_smem_u32(&s_full[s]), 1);
             h_mbar_init(h_smem_u32(&s_empty[s]), 1);
         }
-        h_mbar_init(h_smem_u32(tmem_full), 1);
+        for (int h = 0; h < 2; ++h) {
+            h_mbar_init(h_smem_u32(&tmem_full[h]), 1);
+            h_mbar_init(h_smem_u32(&tmem_empty[h]), 4);   // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -190,124 +193,149 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_ptr_smem;
     const int nslabs = 3 * a.cin_chunks;
+    // Persistent CTA: work units of G tiles, unit u of this CTA accumulates in TMEM half (u & 1) so that the epilogue of
+    // one unit overlaps the mainloop of the next (tmem_full / tmem_empty hand-off per half).
+    const int half_cols = a.halves == 2 ? 256 : 0;
 
     if (warp == 0) {
-        // ===================== producer: weight slabs (TMA) + activation windows (bulk copies) =====================
+        // ===================== producer: weight slabs + activation windows (TMA) =====================
         if (h_elect_one()) {
-            int ait = 0;
-            for (int sl = 0; sl < nslabs; ++sl) {
-                const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
-                const int sb = sl % a.slab_bufs;
-                const uint32_t sph = (uint32_t)(sl / a.slab_bufs) & 1u;
-                h_mbar_wait(h_smem_u32(&s_empty[sb]), sph ^ 1u);
-                const uint32_t sfb = h_smem_u32(&s_full[sb]);
-                h_mbar_expect_tx(sfb, (uint32_t)slab_bytes);
-                for (int t9 = 0; t9 < 9; ++t9)
-                    h_tma_load_2d(h_smem_u32(sSlab + (size_t)sb * slab_bytes + (size_t)t9 * slab_tap_bytes), &mapW, sfb,
-                                  ((dx * 9 + t9) * a.cin_chunks + kc) * HBK, 0);
-                for (int g = 0; g < ntiles; ++g, ++ait) {
-                    const int tile = tile0 + g;
-                    const int b = tile / a.tiles_per_sample;
-                    const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * HBM;
-                    const long long qs = (long long)q0 + (long long)(dx - 1) * a.P2 - (a.P + 1);  // window start row (>= 0)
-                    const int st = ait % a.a_stages;
-                    const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
-                    h_mbar_wait(h_smem_u32(&a_empty[st]), ph ^ 1u);
-                    const uint32_t fb = h_smem_u32(&a_full[st]);
-                    h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
-                    h_tma_load_2d(h_smem_u32(sA + (size_t)st * a_stage_stride), &mapX, fb, kc * HBK, (int)((long long)b * a.P3 + qs));
+            int ait = 0, sit = 0;
+            for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
+                const int tile0 = unit * a.G;
+                const int ntiles = min(a.G, a.total_tiles - tile0);
+                for (int sl = 0; sl < nslabs; ++sl, ++sit) {
+                    const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
+                    const int sb = sit % a.slab_bufs;
+                    const uint32_t sph = (uint32_t)(sit / a.slab_bufs) & 1u;
+                    h_mbar_wait(h_smem_u32(&s_empty[sb]), sph ^ 1u);
+                    const uint32_t sfb = h_smem_u32(&s_full[sb]);
+                    h_mbar_expect_tx(sfb, (uint32_t)slab_bytes);
+                    for (int t9 = 0; t9 < 9; ++t9)
+                        h_tma_load_2d(h_smem_u32(sSlab + (size_t)sb * slab_bytes + (size_t)t9 * slab_tap_bytes), &mapW, sfb,
+                                      ((dx * 9 + t9) * a.cin_chunks + kc) * HBK, 0);
+                    for (int g = 0; g < ntiles; ++g, ++ait) {
+                        const int tile = tile0 + g;
+                        const int b = tile / a.tiles_per_sample;
+                        const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * HBM;
+                        const long long qs = (long long)q0 + (long long)(dx - 1) * a.P2 - (a.P + 1);  // window start row (>= 0)
+                        const int st = ait % a.a_stages;
+                        const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
+                        h_mbar_wait(h_smem_u32(&a_empty[st]), ph ^ 1u);
+                        const uint32_t fb = h_smem_u32(&a_full[st]);
+                        h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
+                        h_tma_load_2d(h_smem_u32(sA + (size_t)st * a_stage_stride), &mapX, fb, kc * HBK,
+                                      (int)((long long)b * a.P3 + qs));
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)(HBM >> 4) << 24);
-        int ait = 0;
-        for (int sl = 0; sl < nslabs; ++sl) {
-            const int sb = sl % a.slab_bufs;
-            const uint32_t sph = (uint32_t)(sl / a.slab_bufs) & 1u;
-            h_mbar_wait(h_smem_u32(&s_full[sb]), sph);
-            for (int g = 0; g < ntiles; ++g, ++ait) {
-                const int st = ait % a.a_stages;
-                const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
-                h_mbar_wait(h_smem_u32(&a_full[st]), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (h_elect_one()) {
-                    const uint64_t abase_d = h_desc_sw128(h_smem_u32(sA + (size_t)st * a_stage_stride));
-                    const uint64_t bbase_d = h_desc_sw128(h_smem_u32(sSlab + (size_t)sb * slab_bytes));
-                    const uint32_t dcol = tmem_base + (uint32_t)(g * a.cout);
-                    const uint32_t tap_step = (uint32_t)(slab_tap_bytes >> 4);
+        int ait = 0, sit = 0, it_unit = 0;
+        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x, ++it_unit) {
+            const int ntiles = min(a.G, a.total_tiles - unit * a.G);
+            const int h = a.halves == 2 ? (it_unit & 1) : 0;
+            const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
+            h_mbar_wait(h_smem_u32(&tmem_empty[h]), (use & 1u) ^ 1u);     // epilogue has drained this half
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int sl = 0; sl < nslabs; ++sl, ++sit) {
+                const int sb = sit % a.slab_bufs;
+                const uint32_t sph = (uint32_t)(sit / a.slab_bufs) & 1u;
+                h_mbar_wait(h_smem_u32(&s_full[sb]), sph);
+                for (int g = 0; g < ntiles; ++g, ++ait) {
+                    const int st = ait % a.a_stages;
+                    const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
+                    h_mbar_wait(h_smem_u32(&a_full[st]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (h_elect_one()) {
+                        const uint64_t abase_d = h_desc_sw128(h_smem_u32(sA + (size_t)st * a_stage_stride));
+                        const uint64_t bbase_d = h_desc_sw128(h_smem_u32(sSlab + (size_t)sb * slab_bytes));
+                        const uint32_t dcol = tmem_base + (uint32_t)(h * half_cols + g * a.cout);
+                        const uint32_t tap_step = (uint32_t)(slab_tap_bytes >> 4);
 #pragma unroll
-                    for (int t9 = 0; t9 < 9; ++t9) {
-                        const int dy = t9 / 3 - 1, dz = t9 % 3 - 1;
-                        // row offset of this tap inside the window, in 16-byte descriptor units (128 B per row)
-                        const uint64_t ad = abase_d + (uint64_t)(((a.P + 1) + dy * a.P + dz) * 8);
-                        const uint64_t bd = bbase_d + (uint64_t)(t9 * tap_step);
+                        for (int t9 = 0; t9 < 9; ++t9) {
+                            const int dy = t9 / 3 - 1, dz = t9 % 3 - 1;
+                            // row offset of this tap inside the window, in 16-byte descriptor units (128 B per row)
+                            const uint64_t ad = abase_d + (uint64_t)(((a.P + 1) + dy * a.P + dz) * 8);
+                            const uint64_t bd = bbase_d + (uint64_t)(t9 * tap_step);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            h_umma_tf32(dcol, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (uint32_t)((sl | t9 | j) != 0));
+                            for (int j = 0; j < 4; ++j)
+                                h_umma_tf32(dcol, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (uint32_t)((sl | t9 | j) != 0));
+                        }
+                        h_umma_commit(h_smem_u32(&a_empty[st]));
+                        if (g == ntiles - 1) h_umma_commit(h_smem_u32(&s_empty[sb]));
+                        if (sl == nslabs - 1 && g == ntiles - 1) h_umma_commit(h_smem_u32(&tmem_full[h]));
                     }
-                    h_umma_commit(h_smem_u32(&a_empty[st]));
-                    if (g == ntiles - 1) h_umma_commit(h_smem_u32(&s_empty[sb]));
-                    if (sl == nslabs - 1 && g == ntiles - 1) h_umma_commit(h_smem_u32(tmem_full));
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
         // ===================== epilogue =====================
         const int qd = warp & 3;
-        h_mbar_wait(h_smem_u32(tmem_full), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int r = a.r, r3 = r * r * r;
-        for (int g = 0; g < ntiles; ++g) {
-            const int tile = tile0 + g;
-            const int b = tile / a.tiles_per_sample;
-            const int q = a.q_first + (tile - b * a.tiles_per_sample) * HBM + qd * 32 + lane;
-            const int x = q / a.P2, rem = q - x * a.P2, y = rem / a.P, z = rem - y * a.P;
-            const bool ok = q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
-            const size_t v = (size_t)b * r3 + (size_t)(x - 1) * r * r + (size_t)(y - 1) * r + (size_t)(z - 1);
-            float* drow = a.D + v * a.ldd;
-            for (int c = 0; c < a.cout / 32; ++c) {
-                float vv[32];
-                h_tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(g * a.cout + c * 32), vv);
+        int it_unit = 0;
+        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x, ++it_unit) {
+            const int tile0 = unit * a.G;
+            const int ntiles = min(a.G, a.total_tiles - tile0);
+            const int h = a.halves == 2 ? (it_unit & 1) : 0;
+            const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
+            h_mbar_wait(h_smem_u32(&tmem_full[h]), use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int g = 0; g < ntiles; ++g) {
+                const int tile = tile0 + g;
+                const int b = tile / a.tiles_per_sample;
+                const int q = a.q_first + (tile - b * a.tiles_per_sample) * HBM + qd * 32 + lane;
+                const int x = q / a.P2, rem = q - x * a.P2, y = rem / a.P, z = rem - y * a.P;
+                const bool ok = q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
+                const size_t v = (size_t)b * r3 + (size_t)(x - 1) * r * r + (size_t)(y - 1) * r + (size_t)(z - 1);
+                float* drow = a.D + v * a.ldd;
+                for (int c = 0; c < a.cout / 32; ++c) {
+                    float vv[32];
+                    h_tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * half_cols + g * a.cout + c * 32), vv);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = vv[j];
-                    if (a.bias != nullptr) t += __ldg(a.bias + c * 32 + j);
-                    vv[j] = ok ? t : 0.f;
-                }
-                if (ok) {
+                    for (int j = 0; j < 32; ++j) {
+                        float t = vv[j];
+                        if (a.bias != nullptr) t += __ldg(a.bias + c * 32 + j);
+                        vv[j] = ok ? t : 0.f;
+                    }
+                    if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(drow + c * 32 + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(drow + c * 32 + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+                    }
+                    if (a.stats != nullptr) {
+                        float sq[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sq[j] = vv[j] * vv[j];
+                        const float s1 = h_colsum32(vv, lane);
+                        const float s2 = h_colsum32(sq, lane);
+                        s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
+                        s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
+                    }
                 }
                 if (a.stats != nullptr) {
-                    float sq[32];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int t = threadIdx.x - 64;
+                    for (int n = t; n < a.cout; n += 128) {
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sq[j] = vv[j] * vv[j];
-                    const float s1 = h_colsum32(vv, lane);
-                    const float s2 = h_colsum32(sq, lane);
-                    s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
-                    s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
-                }
-            }
-            if (a.stats != nullptr) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int t = threadIdx.x - 64;
-                for (int n = t; n < a.cout; n += 128) {
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        s1 += s_stats[((w * a.cout) + n) * 2 + 0];
-                        s2 += s_stats[((w * a.cout) + n) * 2 + 1];
+                        for (int w = 0; w < 4; ++w) {
+                            s1 += s_stats[((w * a.cout) + n) * 2 + 0];
+                            s2 += s_stats[((w * a.cout) + n) * 2 + 1];
+                        }
+                        float* o = a.stats + ((size_t)tile * a.cout + n) * 2;
+                        o[0] = s1;
+                        o[1] = s2;
                     }
-                    float* o = a.stats + ((size_t)tile * a.cout + n) * 2;
-                    o[0] = s1;
-                    o[1] = s2;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            // this half of TMEM may be overwritten by the MMA warp again
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_smem_u32(&tmem_empty[h])) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -352,8 +380,10 @@ P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias,
     a.q_last = a.P3 - a.P2 - a.P - 2;
     a.tiles_per_sample = (a.q_last - a.q_first + 1 + HBM - 1) / HBM;
     a.total_tiles = B * a.tiles_per_sample;
-    a.G = 512 / Cout;
+    a.halves = Cout <= 128 ? 2 : 1;
+    a.G = (a.halves == 2 ? 256 : 512) / Cout;
     if (a.G > 8) a.G = 8;
+    a.total_units = (a.total_tiles + a.G - 1) / a.G;
     a.ldd = ldd;
     a.X = X; a.bias = bias; a.D = D; a.stats = stats;
     const int slab_bytes = 9 * Cout * HBK * 4;
@@ -404,7 +434,8 @@ P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias,
         P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int grid = (a.total_tiles + a.G - 1) / a.G;
+    int grid = p2pb_num_sms();
+    if (grid > a.total_units) grid = a.total_units;
     conv_halo_kernel<<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
