@@ -19,6 +19,8 @@ extern "C" {
 
 const char* p2pb_last_error(void);
 int p2pb_abi_version(void);
+/* development aid for tools/: bit 0 = rows-GEMM epilogue skips its global stores (timing experiments only) */
+int p2pb_debug_set(int flags);
 int p2pb_device_sm_count(void);
 /* kernels launched (or captured into a CUDA graph) through this library since load */
 unsigned long long p2pb_launch_count(void);

@@ -14,6 +14,10 @@
 //   bridge_update    pred_x0 = xt - std*eps ; xt <- mu_x0*pred_x0 + mu_xn*xt           (p2pb.py:155-165,190-213)
 #include "common.cuh"
 
+// Flat element indices are split with 32-bit unsigned divisions (a 64-bit division costs ~10x more ALU work than the
+// 16 bytes each thread moves); every launcher checks that the element count fits.
+#define P2PB_CHECK_U32(total, what) P2PB_CHECK_ARG((total) < 4294967296LL, what ": %lld elements exceed the 32-bit index range, split the batch", (long long)(total))
+
 // ---------------------------------------------------------------------------------------------------------
 // coords [B,3,N] -> rows [B*N, ld] columns col0..col0+2 (other columns untouched)
 // ---------------------------------------------------------------------------------------------------------
@@ -50,14 +54,14 @@ __global__ void __launch_bounds__(256) voxelize_cl_kernel(const float* __restric
                                                           const float* __restrict__ temb, int E,
                                                           const int* __restrict__ order, const int* __restrict__ start,
                                                           const int* __restrict__ cnt, float* __restrict__ out, int Cp,
-                                                          int N, int r3, long long total4)
+                                                          int N, int r3, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int C4 = Cp >> 2;
-    const int c0 = (int)(e % C4) * 4;
-    const long long vrow = e / C4;  // b*r3 + v
-    const int b = (int)(vrow / r3);
+    const unsigned C4 = Cp >> 2;
+    const unsigned vrow = e / C4;  // b*r3 + v
+    const int c0 = (int)(e - vrow * C4) * 4;
+    const int b = (int)(vrow / (unsigned)r3);
     const int n = cnt[vrow];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n > 0) {
@@ -98,6 +102,7 @@ P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* t
     P2PB_CHECK_ARG(Cp % 4 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_cl: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
     const int r3 = r * r * r;
     const long long total4 = (long long)B * r3 * (Cp / 4);
+    P2PB_CHECK_U32(total4, "voxelize_cl");
     if (total4 == 0) return P2PB_OK;
     voxelize_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
                                                                                Cp, N, r3, total4);
@@ -113,59 +118,73 @@ P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* t
 //   ymean (optional) [B, C]: mean over rows of y (= A*mean_c + Bc), the SE squeeze          (modules.py:378)
 // One CTA per (sample, group); fp64 accumulation of the partials (deterministic, no atomics anywhere).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gn_coef_kernel(const float* __restrict__ stats, int tiles, int C, int groups, float count,
+__global__ void __launch_bounds__(256) gn_coef_kernel(const float* __restrict__ stats, int tiles, int C, int groups, float count,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ emd, int ld_emd, int emd_off, float eps,
                                                       float* __restrict__ coefA, float* __restrict__ coefB,
                                                       float* __restrict__ ymean)
 {
-    __shared__ double s_sum[128], s_sq[128];
-    __shared__ double s_cm[128];  // per-channel sums (group width <= 128)
+    // threads = (channel within group) x (tile slice): every thread sums a strided slice of the tiles for one channel in
+    // fp64, slices are combined in a fixed order -> deterministic; the group moments come from the channel sums.
+    __shared__ double s_part[256][2];
+    __shared__ double s_ch[128][2];
+    __shared__ double s_g[2];
     const int b = blockIdx.x / groups, g = blockIdx.x % groups;
     const int cpg = C / groups;
     const int t = threadIdx.x;
-    double gs = 0.0, gq = 0.0;
-    for (int c = t; c < cpg; c += blockDim.x) {
-        const int ch = g * cpg + c;
-        double s = 0.0, q = 0.0;
-        for (int tl = 0; tl < tiles; ++tl) {
-            const float* p = stats + (((size_t)b * tiles + tl) * C + ch) * 2;
-            s += (double)p[0];
-            q += (double)p[1];
+    const int slices = 256 / cpg;              // cpg is a power of two <= 128 for every layer of the network
+    const int c = t % cpg, sl = t / cpg;
+    const int ch = g * cpg + c;
+    double s = 0.0, q = 0.0;
+    if (sl < slices) {
+        for (int tl = sl; tl < tiles; tl += slices) {
+            const float2 p = *reinterpret_cast<const float2*>(stats + (((size_t)b * tiles + tl) * C + ch) * 2);
+            s += (double)p.x;
+            q += (double)p.y;
         }
-        s_cm[c] = s;
-        gs += s;
-        gq += q;
     }
-    s_sum[t] = gs;
-    s_sq[t] = gq;
+    s_part[t][0] = s;
+    s_part[t][1] = q;
     __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (t < s) {
-            s_sum[t] += s_sum[t + s];
-            s_sq[t] += s_sq[t + s];
+    if (t < cpg) {
+        double cs = 0.0, cq = 0.0;
+        for (int k = 0; k < slices; ++k) {
+            cs += s_part[k * cpg + t][0];
+            cq += s_part[k * cpg + t][1];
         }
-        __syncthreads();
+        s_ch[t][0] = cs;
+        s_ch[t][1] = cq;
     }
-    const double n = (double)count * cpg;
-    const double mean = s_sum[0] / n;
-    double var = s_sq[0] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float meanf = (float)mean;
-    for (int c = t; c < cpg; c += blockDim.x) {
-        const int ch = g * cpg + c;
-        float a = rstd * gamma[ch];
-        float bb = beta[ch] - meanf * a;
+    __syncthreads();
+    if (t == 0) {
+        double gs = 0.0, gq = 0.0;
+        for (int k = 0; k < cpg; ++k) {
+            gs += s_ch[k][0];
+            gq += s_ch[k][1];
+        }
+        s_g[0] = gs;
+        s_g[1] = gq;
+    }
+    __syncthreads();
+    if (t < cpg) {
+        const double n = (double)count * cpg;
+        const double mean = s_g[0] / n;
+        double var = s_g[1] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float meanf = (float)mean;
+        const int chn = g * cpg + t;
+        float a = rstd * gamma[chn];
+        float bb = beta[chn] - meanf * a;
         if (emd != nullptr) {
-            const float f = emd[(size_t)b * ld_emd + emd_off + ch];
-            const float eb = emd[(size_t)b * ld_emd + emd_off + C + ch];
+            const float f = emd[(size_t)b * ld_emd + emd_off + chn];
+            const float eb = emd[(size_t)b * ld_emd + emd_off + C + chn];
             a *= f;
             bb = bb * f + eb;
         }
-        coefA[(size_t)b * C + ch] = a;
-        coefB[(size_t)b * C + ch] = bb;
-        if (ymean != nullptr) ymean[(size_t)b * C + ch] = a * (float)(s_cm[c] / (double)count) + bb;
+        coefA[(size_t)b * C + chn] = a;
+        coefB[(size_t)b * C + chn] = bb;
+        if (ymean != nullptr) ymean[(size_t)b * C + chn] = a * (float)(s_ch[t][0] / (double)count) + bb;
     }
 }
 
@@ -173,9 +192,11 @@ P2PB_API int p2pb_gn_coef(const float* stats, int tiles, int B, int C, int group
                           const float* beta, const float* emd, int ld_emd, int emd_off, float eps, float* coefA, float* coefB,
                           float* ymean, void* stream)
 {
-    P2PB_CHECK_ARG(C % groups == 0 && C / groups <= 128, "gn_coef: C=%d groups=%d (group width must be <= 128)", C, groups);
+    const int cpg = groups > 0 ? C / groups : 0;
+    P2PB_CHECK_ARG(groups > 0 && C % groups == 0 && cpg <= 128 && (cpg & (cpg - 1)) == 0,
+                   "gn_coef: C=%d groups=%d (group width must be a power of two <= 128)", C, groups);
     if (B == 0) return P2PB_OK;
-    gn_coef_kernel<<<B * groups, 128, 0, (cudaStream_t)stream>>>(stats, tiles, C, groups, (float)rows_per_sample, gamma, beta, emd,
+    gn_coef_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(stats, tiles, C, groups, (float)rows_per_sample, gamma, beta, emd,
                                                                 ld_emd, emd_off, eps, coefA, coefB, ymean);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -232,14 +253,15 @@ __device__ __forceinline__ float4 affine4(float4 x, float4 a, float4 b)
 template <int ACT>
 __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                          const float* __restrict__ Bc, int rows_per_sample, int C,
-                                                         float* __restrict__ out, int ldo, long long total4)
+                                                         float* __restrict__ out, int ldo, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int C4 = C >> 2;
-    const int c = (int)(e % C4) * 4;
-    const long long m = e / C4;
-    const long long b = m / rows_per_sample;
+    const unsigned C4 = C >> 2;
+    const unsigned mu = e / C4;
+    const int c = (int)(e - mu * C4) * 4;
+    const size_t m = mu;
+    const size_t b = mu / (unsigned)rows_per_sample;
     const float4 xv = *reinterpret_cast<const float4*>(x + m * ldx + c);
     const float4 a = __ldg(reinterpret_cast<const float4*>(A + b * C + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c));
@@ -249,15 +271,16 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
 template <int ACT>
 __global__ void __launch_bounds__(256) affine_act_pool_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                               const float* __restrict__ Bc, int rows_per_sample, int C,
-                                                              int pool, float* __restrict__ out, int ldo, long long total4)
+                                                              int pool, float* __restrict__ out, int ldo, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int C4 = C >> 2;
-    const int c = (int)(e % C4) * 4;
-    const long long mo = e / C4;  // pooled row
-    const long long m0 = mo * pool;
-    const long long b = m0 / rows_per_sample;
+    const unsigned C4 = C >> 2;
+    const unsigned mou = e / C4;  // pooled row
+    const int c = (int)(e - mou * C4) * 4;
+    const size_t mo = mou;
+    const size_t m0 = mo * pool;
+    const size_t b = (mou * (unsigned)pool) / (unsigned)rows_per_sample;
     const float4 a = __ldg(reinterpret_cast<const float4*>(A + b * C + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c));
     float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -325,10 +348,12 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     P2PB_CHECK_ARG(out != nullptr, "affine_act: out required");
     if (pool == 1) {
         const long long total4 = (long long)M * (C / 4);
+        P2PB_CHECK_U32(total4, "affine_act");
         if (act) affine_act_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4);
         else affine_act_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4);
     } else {
         const long long total4 = (long long)(M / pool) * (C / 4);
+        P2PB_CHECK_U32(total4, "affine_act(pool)");
         if (act) affine_act_pool_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4);
         else affine_act_pool_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4);
     }
@@ -346,15 +371,16 @@ __global__ void __launch_bounds__(256) devox_cl_kernel(const float* __restrict__
                                                        const float* __restrict__ A, const float* __restrict__ Bc,
                                                        const float* __restrict__ se, const float* __restrict__ praw, int ldp,
                                                        const float* __restrict__ pA, const float* __restrict__ pB,
-                                                       float* __restrict__ out, int ldo, int C, int N, int r, long long total4)
+                                                       float* __restrict__ out, int ldo, int C, int N, int r, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int C4 = C >> 2;
-    const int c = (int)(e % C4) * 4;
-    const long long m = e / C4;  // b*N + n
-    const int b = (int)(m / N);
-    const int n = (int)(m - (long long)b * N);
+    const unsigned C4 = C >> 2;
+    const unsigned mu = e / C4;  // b*N + n
+    const int c = (int)(e - mu * C4) * 4;
+    const size_t m = mu;
+    const int b = (int)(mu / (unsigned)N);
+    const int n = (int)(mu - (unsigned)b * (unsigned)N);
     const float* co = ncoords + (size_t)b * 3 * N;
     const float x = co[n], y = co[n + N], z = co[n + 2 * N];
     const int r2 = r * r;
@@ -401,6 +427,7 @@ P2PB_API int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, cons
 {
     P2PB_CHECK_ARG(C % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0 && (praw == nullptr || ldp % 4 == 0), "devox_cl: alignment");
     const long long total4 = (long long)B * N * (C / 4);
+    P2PB_CHECK_U32(total4, "devox_cl");
     if (total4 == 0) return P2PB_OK;
     devox_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(ncoords, raw, ldg, A, Bc, se, praw, ldp, pA, pB, out,
                                                                             ldo, C, N, r, total4);
@@ -416,16 +443,17 @@ P2PB_API int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, cons
 __global__ void __launch_bounds__(256) group_rows_kernel(const float* __restrict__ feat, int ldf, int Cf,
                                                          const float* __restrict__ coords, const float* __restrict__ centers,
                                                          const int* __restrict__ idx, float* __restrict__ out, int ldo, int N,
-                                                         int M, int U, long long total)
+                                                         int M, int U, unsigned total)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    const int C4 = (Cf >> 2) + 1;
-    const int c4 = (int)(e % C4);
-    const long long row = e / C4;  // (b*M + j)*U + k
-    const long long bj = row / U;
-    const int b = (int)(bj / M);
-    const int j = (int)(bj - (long long)b * M);
+    const unsigned C4 = (Cf >> 2) + 1;
+    const unsigned rowu = e / C4;  // (b*M + j)*U + k
+    const int c4 = (int)(e - rowu * C4);
+    const size_t row = rowu;
+    const unsigned bj = rowu / (unsigned)U;
+    const int b = (int)(bj / (unsigned)M);
+    const int j = (int)(bj - (unsigned)b * (unsigned)M);
     const int src = idx[row];
     if (c4 < (Cf >> 2)) {
         *reinterpret_cast<float4*>(out + row * ldo + c4 * 4) =
@@ -445,6 +473,7 @@ P2PB_API int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* co
 {
     P2PB_CHECK_ARG(Cf % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0 && ldo >= Cf + 3, "group_rows: alignment (Cf %% 4, ld %% 4)");
     const long long total = (long long)B * M * U * (Cf / 4 + 1);
+    P2PB_CHECK_U32(total, "group_rows");
     if (total == 0) return P2PB_OK;
     group_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
                                                                              U, total);
@@ -457,15 +486,16 @@ P2PB_API int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* co
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) interp_rows_kernel(const float* __restrict__ f, int ldf, const int* __restrict__ idx,
                                                           const float* __restrict__ w, float* __restrict__ out, int ldo, int C,
-                                                          int N, int M, long long total4)
+                                                          int N, int M, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int C4 = C >> 2;
-    const int c = (int)(e % C4) * 4;
-    const long long m = e / C4;
-    const int b = (int)(m / N);
-    const int n = (int)(m - (long long)b * N);
+    const unsigned C4 = C >> 2;
+    const unsigned mu = e / C4;
+    const int c = (int)(e - mu * C4) * 4;
+    const size_t m = mu;
+    const int b = (int)(mu / (unsigned)N);
+    const int n = (int)(mu - (unsigned)b * (unsigned)N);
     const int* ix = idx + (size_t)b * 3 * N;
     const float* ww = w + (size_t)b * 3 * N;
     const int i1 = ix[n], i2 = ix[n + N], i3 = ix[n + 2 * N];
@@ -487,6 +517,7 @@ P2PB_API int p2pb_interp_rows(const float* f, int ldf, const int* idx, const flo
 {
     P2PB_CHECK_ARG(C % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0, "interp_rows: alignment");
     const long long total4 = (long long)B * N * (C / 4);
+    P2PB_CHECK_U32(total4, "interp_rows");
     if (total4 == 0) return P2PB_OK;
     interp_rows_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(f, ldf, idx, w, out, ldo, C, N, M, total4);
     P2PB_LAUNCH_OK();
@@ -638,33 +669,43 @@ __global__ void __launch_bounds__(256) voxelize_padded_kernel(const float* __res
                                                               const float* __restrict__ temb, int E,
                                                               const int* __restrict__ order, const int* __restrict__ start,
                                                               const int* __restrict__ cnt, float* __restrict__ out, int Cp,
-                                                              int N, int r, long long total4)
+                                                              int N, int r, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int r3 = r * r * r;
-    const int C4 = Cp >> 2;
-    const int c0 = (int)(e % C4) * 4;
-    const long long vrow = e / C4;
+    const unsigned r3 = r * r * r;
+    const unsigned C4 = Cp >> 2;
+    const unsigned vrow = e / C4;
+    const int c0 = (int)(e - vrow * C4) * 4;
     const int b = (int)(vrow / r3);
-    const int v = (int)(vrow - (long long)b * r3);
+    const int v = (int)(vrow - (unsigned)b * r3);
     const int n = cnt[vrow];
     float a[4] = {0.f, 0.f, 0.f, 0.f};
     if (n > 0) {
         const float inv = (float)(1.0 / (double)(float)n);
         const int* ord = order + (size_t)b * N + start[vrow];
+        if (c0 + 3 < Cf && (ldf & 3) == 0) {
+            for (int i = 0; i < n; ++i) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + ord[i]) * ldf + c0));
+                a[0] = __fadd_rn(a[0], __fmul_rn(f.x, inv));
+                a[1] = __fadd_rn(a[1], __fmul_rn(f.y, inv));
+                a[2] = __fadd_rn(a[2], __fmul_rn(f.z, inv));
+                a[3] = __fadd_rn(a[3], __fmul_rn(f.w, inv));
+            }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c0 + j;
-            if (c < Cf) {
-                float s = 0.f;
-                for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
-                a[j] = s;
-            } else if (c < Cf + E) {
-                const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
-                float s = 0.f;
-                for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
-                a[j] = s;
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                if (c < Cf) {
+                    float s = 0.f;
+                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
+                    a[j] = s;
+                } else if (c < Cf + E) {
+                    const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
+                    float s = 0.f;
+                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
+                    a[j] = s;
+                }
             }
         }
     }
@@ -676,6 +717,7 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
 {
     P2PB_CHECK_ARG(Cp % 32 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_padded: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
     const long long total4 = (long long)B * r * r * r * (Cp / 4);
+    P2PB_CHECK_U32(total4, "voxelize_padded");
     if (total4 == 0) return P2PB_OK;
     voxelize_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
                                                                                    Cp, N, r, total4);
@@ -686,17 +728,17 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
 // y = swish(x*A + B) of dense conv-output rows [B*r^3, ldx] -> zero-bordered padded input rows of the next conv
 __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                                 const float* __restrict__ Bc, int C, float* __restrict__ out,
-                                                                int r, long long total4)
+                                                                int r, unsigned total4)
 {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
-    const int r3 = r * r * r;
-    const int C4 = C >> 2;
-    const int c = (int)(e % C4) * 4;
-    const long long vrow = e / C4;
+    const unsigned r3 = r * r * r;
+    const unsigned C4 = C >> 2;
+    const unsigned vrow = e / C4;
+    const int c = (int)(e - vrow * C4) * 4;
     const int b = (int)(vrow / r3);
-    const int v = (int)(vrow - (long long)b * r3);
-    const float4 xv = *reinterpret_cast<const float4*>(x + vrow * ldx + c);
+    const int v = (int)(vrow - (unsigned)b * r3);
+    const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)vrow * ldx + c);
     const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c));
     *reinterpret_cast<float4*>(out + padded_row(b, v, r) * C + c) = affine4<1>(xv, a, bb);
@@ -707,6 +749,7 @@ P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, con
 {
     P2PB_CHECK_ARG(C % 32 == 0 && ldx % 4 == 0, "affine_act_padded: C %% 32, ldx %% 4");
     const long long total4 = (long long)B * r * r * r * (C / 4);
+    P2PB_CHECK_U32(total4, "affine_act_padded");
     if (total4 == 0) return P2PB_OK;
     affine_act_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, r, total4);
     P2PB_LAUNCH_OK();

@@ -29,6 +29,7 @@ constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 4;  // 16 KiB
 
 struct GemmArgs {
+    int dbg;
     int M, ldd, n_total;
     int nseg;
     int seg_chunks[3];
@@ -186,9 +187,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][BN][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x;
+    // blockIdx.x = N tile (fastest varying): the CTAs that share one A tile are scheduled together, so A is read from HBM
+    // once and served to the others from L2
+    const int m_tile = blockIdx.y;
     const int m0 = m_tile * BM;
-    const int n0 = blockIdx.y * BN;
+    const int n0 = blockIdx.x * BN;
 
     int total_chunks = 0;
     if (args.conv) total_chunks = 27 * args.cin_chunks;
@@ -300,7 +303,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 if (bias2_row != nullptr) x += __ldg(bias2_row + nb + j);
                 v[j] = row_ok ? x : 0.f;
             }
-            if (row_ok) {
+            if (row_ok && !(args.dbg & 1)) {
 #pragma unroll
                 for (int j = 0; j < CW; j += 4)
                     *reinterpret_cast<float4*>(drow + c * CW + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -381,6 +384,8 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
     return P2PB_OK;
 }
 
+int g_gemm_dbg = 0;
+
 int pick_bn(int n_total)
 {
     const int cands[5] = {256, 128, 64, 32, 16};
@@ -395,6 +400,10 @@ int launch_gemm(const CUtensorMap* maps, const GemmArgs& a, cudaStream_t s)
     const int b_stage = BN * BK * 4;
     int stages = (200 * 1024) / (A_STAGE_BYTES + b_stage);
     if (stages > 8) stages = 8;
+    // short-K GEMMs (1x1 convs on 32..128 channels) need no deep ring: a small footprint lets several CTAs share an SM
+    // (TMEM: BN columns each) so that one CTA's epilogue overlaps another's loads/MMAs
+    int total_chunks = a.conv ? 27 * a.cin_chunks : a.seg_chunks[0] + a.seg_chunks[1] + a.seg_chunks[2];
+    if (stages > total_chunks) stages = total_chunks;
     if (stages < 2) stages = 2;
     const size_t smem = 1024 + (size_t)stages * (A_STAGE_BYTES + b_stage) + (2 * stages + 1) * 8 + 16 + (size_t)4 * BN * 2 * 4;
     static bool attr_set = false;
@@ -402,7 +411,8 @@ int launch_gemm(const CUtensorMap* maps, const GemmArgs& a, cudaStream_t s)
         P2PB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid(p2pb_cdiv(a.M, BM), a.n_total / BN);
+    dim3 grid(a.n_total / BN, p2pb_cdiv(a.M, BM));
+    P2PB_CHECK_ARG(grid.y <= 65535u, "gemm: M=%d needs %u row tiles (> 65535): split the batch", a.M, grid.y);
     gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], a, stages);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -427,6 +437,13 @@ int dispatch_gemm(const CUtensorMap* maps, const GemmArgs& a, int bn, cudaStream
 // C ABI
 // ---------------------------------------------------------------------------------------------------------
 
+// development aid (tools/): bit 0 = skip the epilogue's global stores
+P2PB_API int p2pb_debug_set(int flags)
+{
+    g_gemm_dbg = flags;
+    return P2PB_OK;
+}
+
 // rows-mode GEMM:  D[M, N] = sum_i A_i[M, K_i] * W[N, sum K_i]^T + bias + bias2[m / rows_per_sample]
 //   A_i : row-major, row pitch lda_i floats (K_i, lda_i multiples of 32 resp. 4), i < nseg <= 3 (replaces torch.cat)
 //   W   : [N, Ktot] row-major, Ktot = sum K_i;  N multiple of 16
@@ -442,7 +459,7 @@ P2PB_API int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, 
     P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= N, "gemm_rows: ldd=%d must be >= N and a multiple of 4", ldd);
     P2PB_CHECK_ARG(bias2 == nullptr || rows_per_sample > 0, "gemm_rows: bias2 needs rows_per_sample");
     GemmArgs a = {};
-    a.M = M; a.ldd = ldd; a.n_total = N; a.conv = 0;
+    a.M = M; a.ldd = ldd; a.n_total = N; a.conv = 0; a.dbg = g_gemm_dbg;
     a.bias = bias; a.bias2 = bias2; a.rows_per_sample = rows_per_sample; a.D = D; a.stats = stats;
     CUtensorMap maps[4];
     int ktot = 0, nseg = 0;

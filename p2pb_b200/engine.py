@@ -411,6 +411,44 @@ class Engine:
             cache[key] = {"norm_coords": nc, "order": order, "start": start, "cnt": cnt}
         return cache[key]
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
+
+    def _geometry(self, xt):
+        """FPS chain, ball-query indices, 3-NN indices/weights and the voxel CSR of every (level, resolution)."""
+        B, N, W = self.B, self.N, self.W
+        Ns = self.Ns
+        n_levels = len(W["sa"])
+        coords = [xt]
+        for i in range(n_levels):
+            M = Ns[i + 1]
+            idx = self.buf(f"fps{i}.idx", B, M, dtype=torch.int32)
+            ctr = self.buf(f"fps{i}.ctr", B, 3, M)
+            call("p2pb_furthest_point_sampling", _p(coords[i]), B, Ns[i], M, _p(idx), _p(ctr), _vp(0), _s())
+            coords.append(ctr)
+        nidx = []
+        for i, L in enumerate(W["sa"]):
+            t = self.buf(f"bq{i}", B, Ns[i + 1], L["K"], dtype=torch.int32)
+            call("p2pb_ball_query", _p(coords[i + 1]), _p(coords[i]), B, Ns[i + 1], Ns[i], _f(L["radius"]), L["K"], _p(t), _s())
+            nidx.append(t)
+        nn3 = []
+        for j, L in enumerate(W["fp"]):
+            lvl = L["lvl"]
+            ix = self.buf(f"nn{j}.idx", B, 3, Ns[lvl], dtype=torch.int32)
+            ww = self.buf(f"nn{j}.w", B, 3, Ns[lvl])
+            call("p2pb_three_nn", _p(coords[lvl]), _p(coords[lvl + 1]), B, Ns[lvl], Ns[lvl + 1], _p(ix), _p(ww), _s())
+            nn3.append((ix, ww))
+        preps: Dict[tuple, dict] = {}
+        for i, L in enumerate(W["sa"]):
+            for P in L["pv"]:
+                self.voxel_prep(preps, i, coords[i], P["r"])
+        for L in W["fp"]:
+            for P in L["pv"]:
+                self.voxel_prep(preps, L["lvl"], coords[L["lvl"]], P["r"])
+        return coords, nidx, nn3, preps
+
     # ------------------------------------------------------------------------------------------------ one evaluation
     def prepare_cond(self, x_cond):
         """Step-invariant part: embed_feats(x_cond) (unet_pvc.py:184-188) when conditioning features are given."""
@@ -435,27 +473,18 @@ class Engine:
         B, N, W, fe, E = self.B, self.N, self.W, self.fe, self.E
         Ns = self.Ns
         n_levels = len(W["sa"])
-        # ---- geometry: FPS chain, ball queries, 3-NN, voxel CSRs (coordinates only)
-        coords = [xt]
-        for i in range(n_levels):
-            M = Ns[i + 1]
-            idx = self.buf(f"fps{i}.idx", B, M, dtype=torch.int32)
-            ctr = self.buf(f"fps{i}.ctr", B, 3, M)
-            call("p2pb_furthest_point_sampling", _p(coords[i]), B, Ns[i], M, _p(idx), _p(ctr), _vp(0), _s())
-            coords.append(ctr)
-        nidx = []
-        for i, L in enumerate(W["sa"]):
-            t = self.buf(f"bq{i}", B, Ns[i + 1], L["K"], dtype=torch.int32)
-            call("p2pb_ball_query", _p(coords[i + 1]), _p(coords[i]), B, Ns[i + 1], Ns[i], _f(L["radius"]), L["K"], _p(t), _s())
-            nidx.append(t)
-        nn3 = []
-        for j, L in enumerate(W["fp"]):
-            lvl = L["lvl"]
-            ix = self.buf(f"nn{j}.idx", B, 3, Ns[lvl], dtype=torch.int32)
-            ww = self.buf(f"nn{j}.w", B, 3, Ns[lvl])
-            call("p2pb_three_nn", _p(coords[lvl]), _p(coords[lvl + 1]), B, Ns[lvl], Ns[lvl + 1], _p(ix), _p(ww), _s())
-            nn3.append((ix, ww))
-        preps: Dict[tuple, dict] = {}
+        # ---- geometry: FPS chain, ball queries, 3-NN, voxel CSRs (coordinates only).  It is latency-bound (one CTA per
+        # patch for FPS) and independent of the features, so it runs on a side stream concurrently with the feature
+        # embedding / global PointNet / AdaGN GEMMs below (fork/join with events; captured into the same CUDA graph).
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            coords, nidx, nn3, preps = self._geometry(xt)
+            join = torch.cuda.Event()
+            join.record(side)
         # ---- point rows of the raw coordinates
         X0 = self.buf("X0", B * N, 32)
         call("p2pb_coords_to_rows", _p(xt), _p(X0), B, N, 32, 0, _s())
@@ -499,6 +528,7 @@ class Engine:
             dense.gemm_rows([cond], W["emd_w"], W["emd_b"], out=self.emd_all)
         else:
             self.emd_all = None
+        main.wait_event(join)       # geometry is needed from here on
         # ---- set abstraction
         feats = F0
         skips = []
