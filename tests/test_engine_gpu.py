@@ -149,3 +149,34 @@ def test_denoise_object_entry_point_end_to_end(tmp_path):
     out = np.loadtxt(str(tmp_path / "out.xyz"))
     assert out.shape == (6144, 3) and np.isfinite(out).all()
     assert np.abs(np.linalg.norm(out, axis=1) - 1.0).mean() < 0.1      # still the noisy unit sphere, moved a little
+
+
+@pytest.mark.parametrize("extra", [0, 3])
+def test_engine_pvdl_8192_vs_eager(extra):
+    """PVDL at the bench shapes of configs 3-4 (N=8192, data.npoints=8192; xyz-only and xyz+RGB), B=2, one network
+    evaluation: fused engine vs the eager fp32 path on the same device (same discrete geometry -> continuous compare)."""
+    from p2pb_b200.engine import get_engine
+
+    cfg = load_cfg("PVDL_SNPP", **{"data.npoints": 8192, "model.extra_feature_channels": extra})
+    model, _ = build(cfg, backend="engine")
+    B, N = 2, 8192
+    x = patch_input(B, N, seed=5).cuda()
+    g = torch.Generator().manual_seed(6)
+    xc = torch.rand(B, extra, N, generator=g).cuda() if extra else None
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    nl = model.noise_levels[torch.full((B,), 999, device="cuda", dtype=torch.long)]
+    with torch.no_grad():
+        ref = model.model(x, nl, x_cond=xc)
+        eng = get_engine(model, model.model, x.shape, None if xc is None else xc.shape)
+        if xc is not None:
+            eng.prepare_cond(xc)
+        sin = eng.time_embedding(float(nl[0].item()), None)[None].expand(B, -1).contiguous()
+        th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
+        eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
+        eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
+        eps = eng.evaluate(x.contiguous(), temb)[:, :3].reshape(B, N, 3).permute(0, 2, 1)
+    torch.backends.cudnn.allow_tf32 = True
+    err = (eps - ref).abs()
+    print(f"PVDL N=8192 extra={extra}: engine vs eager fp32: mean|err|={err.mean():.3e} max|err|={err.max():.3e} |eps|max={ref.abs().max():.2f}")
+    assert err.mean().item() <= 2e-3 and err.max().item() <= 5e-2
