@@ -78,10 +78,20 @@ int p2pb_nm_distance(const float* xyz1, const float* xyz2, int B, int n, int m, 
 /* The dense contractions: replaces cuDNN Conv1d/Conv2d(1x1) and cuBLAS Linear behind
  * /root/reference/models/pvcnn.py:174-192 and models/modules.py:337,365-370 (tcgen05 TF32 tiles fed by TMA).
  * D[M,N] = sum_i A_i[M,K_i] * W[N, sum K_i]^T + bias[N] + bias2[m / rows_per_sample, N]; up to 3 A segments replace
- * torch.cat; stats (optional) [ceil(M/128), N, 2] = per-tile column (sum, sum of squares) for the following GroupNorm. */
+ * torch.cat; stats (optional) [4*ceil(M/128), N, 2] = column (sum, sum of squares) of every 32-row block, for the
+ * following GroupNorm (reduced by p2pb_gn_coef). */
 int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2, int lda2,
                    const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D, int ldd,
                    float* stats, int M, int N, void* stream);
+
+/* same, with optional column (max, min) per 32-row block, colmm [4*ceil(M/128), N, 2]; D may be null when only statistics
+ * are needed (persistent kernel, N % 32 == 0).  p2pb_gmax_minmax turns (max, min) into max over rows of act(x*A + Bc):
+ * the global max-pool of /root/reference/models/pvcnn.py:923,930 without materialising the [B*N, C] activation. */
+int p2pb_gemm_rows_ex(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2, int lda2,
+                      const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D, int ldd,
+                      float* stats, float* colmm, int M, int N, void* stream);
+int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const float* A, const float* Bc, int act, float* gmax,
+                     void* stream);
 
 /* replaces nn.Conv3d 3x3x3 pad 1 (/root/reference/models/pvcnn.py:265-284): per-tap 5-D TMA implicit GEMM (any r = 2^k >= 8)
  * grid [B,r,r,r,Cin] channels-last, W [Cout, 27*Cin] (k = ((kx*3+ky)*3+kz)*Cin + c), D [B*r^3, ldd] */

@@ -319,6 +319,42 @@ __global__ void __launch_bounds__(256) affine_act_gmax_kernel(const float* __res
     }
 }
 
+// global max over the rows of a sample of act(x*A + Bc) from the per-tile column (max, min) of x written by the GEMM
+// epilogue: x -> fma(x, A, Bc) is monotone and Swish is unimodal (decreasing, then increasing), so the maximum over any
+// set of rows is attained at the largest or the smallest x of the column.  colmm [B*tiles, C, 2].
+__global__ void __launch_bounds__(256) gmax_minmax_kernel(const float* __restrict__ colmm, int tiles, int C,
+                                                          const float* __restrict__ A, const float* __restrict__ Bc, int act,
+                                                          float* __restrict__ gmax, int total)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int b = e / C, c = e - b * C;
+    float mx = -INFINITY, mn = INFINITY;
+    for (int t = 0; t < tiles; ++t) {
+        const float2 p = *reinterpret_cast<const float2*>(colmm + (((size_t)b * tiles + t) * C + c) * 2);
+        mx = fmaxf(mx, p.x);
+        mn = fminf(mn, p.y);
+    }
+    const float a = A[e], bb = Bc[e];
+    float y0 = fmaf(mx, a, bb), y1 = fmaf(mn, a, bb);
+    if (act == 1) {
+        y0 = swishf(y0);
+        y1 = swishf(y1);
+    }
+    gmax[e] = fmaxf(y0, y1);
+}
+
+P2PB_API int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const float* A, const float* Bc, int act, float* gmax,
+                              void* stream)
+{
+    const int total = B * C;
+    if (total == 0) return P2PB_OK;
+    P2PB_CHECK_ARG(tiles > 0, "gmax_minmax: tiles must be positive");
+    gmax_minmax_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(colmm, tiles, C, A, Bc, act, gmax, total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
 __global__ void fill_kernel(float* p, float v, long long n)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

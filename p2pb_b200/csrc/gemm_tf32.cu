@@ -184,7 +184,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     uint64_t* empty_bar = bars + stages;
     uint64_t* tmem_full_bar = bars + 2 * stages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
-    float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][BN][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // blockIdx.x = N tile (fastest varying): the CTAs that share one A tile are scheduled together, so A is read from HBM
@@ -314,25 +313,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
                 const float s1 = warp_colsum32(v, lane);
                 const float s2 = warp_colsum32(sq, lane);
-                if (lane < CW) {
-                    s_stats[((q * BN) + c * CW + lane) * 2 + 0] = s1;
-                    s_stats[((q * BN) + c * CW + lane) * 2 + 1] = s2;
-                }
-            }
-        }
-        if (args.stats != nullptr) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int t = threadIdx.x - 64;
-            for (int n = t; n < BN; n += 128) {
-                float a = 0.f, b2 = 0.f;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    a += s_stats[((w * BN) + n) * 2 + 0];
-                    b2 += s_stats[((w * BN) + n) * 2 + 1];
-                }
-                float* o = args.stats + ((size_t)m_tile * args.n_total + n0 + n) * 2;
-                o[0] = a;
-                o[1] = b2;
+                // 32-row partials: [(m_tile*4 + q), n_total, 2] (same contract as gemm_persist.cu)
+                if (lane < CW)
+                    *reinterpret_cast<float2*>(args.stats + ((size_t)(m_tile * 4 + q) * args.n_total + n0 + c * CW + lane) * 2) =
+                        make_float2(s1, s2);
             }
         }
     }
@@ -437,26 +421,36 @@ int dispatch_gemm(const CUtensorMap* maps, const GemmArgs& a, int bn, cudaStream
 // C ABI
 // ---------------------------------------------------------------------------------------------------------
 
-// development aid (tools/): bit 0 = skip the epilogue's global stores
+// persistent kernel (gemm_persist.cu); returns P2PB_ERR_UNSUPPORTED when the shape is outside its envelope
+extern int g_p2pb_gemm_mode;
+int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chunks, int conv, int cin_chunks, int tiles_per_sample,
+                          int r, const float* W, int ktot, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                          int ldd, float* stats, float* colmm, int M, int N, cudaStream_t s);
+
+// development aid (tools/, tests): bit 0 = legacy kernel skips its global stores; bit 1 = force the legacy
+// one-tile-per-CTA kernel; bit 2 = persistent kernel forms 2-CTA multicast clusters; bits 3, 4 = timing experiments
 P2PB_API int p2pb_debug_set(int flags)
 {
     g_gemm_dbg = flags;
+    g_p2pb_gemm_mode = flags;
     return P2PB_OK;
 }
 
 // rows-mode GEMM:  D[M, N] = sum_i A_i[M, K_i] * W[N, sum K_i]^T + bias + bias2[m / rows_per_sample]
 //   A_i : row-major, row pitch lda_i floats (K_i, lda_i multiples of 32 resp. 4), i < nseg <= 3 (replaces torch.cat)
 //   W   : [N, Ktot] row-major, Ktot = sum K_i;  N multiple of 16
-//   D   : [M, ldd];  stats (optional): [ceil(M/128), N, 2] per-tile column (sum, sum of squares)
-P2PB_API int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2,
-                            int lda2, const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D,
-                            int ldd, float* stats, int M, int N, void* stream)
+//   D   : [M, ldd];  stats (optional): [4*ceil(M/128), N, 2] column (sum, sum of squares) of every 32-row block
+//   colmm (optional, persistent kernel only): [4*ceil(M/128), N, 2] column (max, min) per 32-row block; D may then be null
+P2PB_API int p2pb_gemm_rows_ex(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2,
+                               int lda2, const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                               int ldd, float* stats, float* colmm, int M, int N, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     const float* Ap[3] = {A0, A1, A2};
     const int Ks[3] = {K0, K1, K2}, lds[3] = {lda0, lda1, lda2};
     P2PB_CHECK_ARG(M > 0 && N > 0 && N % 16 == 0, "gemm_rows: bad M=%d N=%d (N must be a multiple of 16)", M, N);
-    P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= N, "gemm_rows: ldd=%d must be >= N and a multiple of 4", ldd);
+    P2PB_CHECK_ARG(D == nullptr || (ldd % 4 == 0 && ldd >= N), "gemm_rows: ldd=%d must be >= N and a multiple of 4", ldd);
+    P2PB_CHECK_ARG(D != nullptr || stats != nullptr || colmm != nullptr, "gemm_rows: no output requested");
     P2PB_CHECK_ARG(bias2 == nullptr || rows_per_sample > 0, "gemm_rows: bias2 needs rows_per_sample");
     GemmArgs a = {};
     a.M = M; a.ldd = ldd; a.n_total = N; a.conv = 0; a.dbg = g_gemm_dbg;
@@ -479,6 +473,12 @@ P2PB_API int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, 
     P2PB_CHECK_ARG(nseg > 0, "gemm_rows: no A segment");
     for (int i = nseg; i < 3; ++i) maps[i] = maps[0];
     a.nseg = nseg;
+    {
+        int rc = p2pb_gemm_persist_try(maps, nseg, a.seg_chunks, 0, 0, 0, 0, W, ktot, bias, bias2, rows_per_sample, D, ldd, stats,
+                                       colmm, M, N, s);
+        if (rc != P2PB_ERR_UNSUPPORTED) return rc;
+    }
+    P2PB_CHECK_ARG(D != nullptr && colmm == nullptr, "gemm_rows: column max/min and null D need N %% 32 == 0 and an aligned D");
     const int bn = pick_bn(N);
     {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
@@ -490,10 +490,18 @@ P2PB_API int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, 
     return dispatch_gemm(maps, a, bn, s);
 }
 
+P2PB_API int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2,
+                            int lda2, const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                            int ldd, float* stats, int M, int N, void* stream)
+{
+    return p2pb_gemm_rows_ex(A0, K0, lda0, A1, K1, lda1, A2, K2, lda2, W, bias, bias2, rows_per_sample, D, ldd, stats, nullptr, M, N,
+                             stream);
+}
+
 // implicit-GEMM 3x3x3 convolution, stride 1, zero padding 1, channels-last:
 //   grid [B, r, r, r, Cin] (Cin multiple of 32; x slowest, z fastest = the reference's flat voxel index x*r^2+y*r+z)
 //   W    [Cout, 27*Cin] with k = ((kx*3+ky)*3+kz)*Cin + c  (repacked from the reference's [Cout, Cin, 3, 3, 3])
-//   D    [B*r^3, ldd] ; stats (optional) [B*r^3/128, Cout, 2]
+//   D    [B*r^3, ldd] ; stats (optional) [B*r^3/32, Cout, 2]
 P2PB_API int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
                             int Cin, int Cout, void* stream)
 {
@@ -519,6 +527,11 @@ P2PB_API int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias
         if (rc != P2PB_OK) return rc;
         maps[1] = maps[0];
         maps[2] = maps[0];
+    }
+    {
+        int rc = p2pb_gemm_persist_try(maps, 1, nullptr, 1, a.cin_chunks, a.tiles_per_sample, r, W, 27 * Cin, bias, nullptr, 0, D, ldd,
+                                       stats, nullptr, a.M, Cout, s);
+        if (rc != P2PB_ERR_UNSUPPORTED) return rc;
     }
     const int bn = pick_bn(Cout);
     {

@@ -26,13 +26,20 @@ def num_m_tiles(M: int) -> int:
     return (M + 127) // 128
 
 
+def num_stat_blocks(M: int) -> int:
+    """Rows of the ``stats`` / ``colmm`` outputs of gemm_rows / conv3d_cl: one per 32-row block of every 128-row tile."""
+    return 4 * num_m_tiles(M)
+
+
 def gemm_rows(segs: Sequence[torch.Tensor], W: torch.Tensor, bias: Optional[torch.Tensor] = None,
               bias2: Optional[torch.Tensor] = None, rows_per_sample: int = 0, out: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None) -> torch.Tensor:
+              stats: Optional[torch.Tensor] = None, ks: Optional[Sequence[int]] = None,
+              colmm: Optional[torch.Tensor] = None, store: bool = True) -> Optional[torch.Tensor]:
     """D[M,N] = cat(segs, dim=1)[M,K] @ W[N,K]^T + bias + bias2[m // rows_per_sample].
 
     ``segs``: 1-3 fp32 2-D tensors with unit inner stride (column slices of wider buffers are fine); ``ks`` optionally
-    restricts the number of leading columns used from each segment."""
+    restricts the number of leading columns used from each segment.  ``stats`` / ``colmm`` [num_stat_blocks(M), N, 2]
+    receive the column (sum, sum^2) / (max, min) of every 32-row block; ``store=False`` skips D altogether (statistics-only GEMM)."""
     assert 1 <= len(segs) <= 3
     M = segs[0].shape[0]
     N = W.shape[0]
@@ -46,12 +53,14 @@ def gemm_rows(segs: Sequence[torch.Tensor], W: torch.Tensor, bias: Optional[torc
             a += [_p(t), int(k), int(t.stride(0))]
         else:
             a += [_vp(0), 0, 0]
-    if out is None:
+    if out is None and store:
         out = torch.empty((M, N), dtype=torch.float32, device=W.device)
-    assert out.stride(1) == 1 and W.is_contiguous()
+    if not store:
+        out = None
+    assert (out is None or out.stride(1) == 1) and W.is_contiguous()
     with torch.cuda.device(W.device):
-        call("p2pb_gemm_rows", *a, _p(W), _p(bias), _p(bias2), int(rows_per_sample), _p(out), int(out.stride(0)),
-             _p(stats), int(M), int(N), _s())
+        call("p2pb_gemm_rows_ex", *a, _p(W), _p(bias), _p(bias2), int(rows_per_sample), _p(out),
+             int(out.stride(0)) if out is not None else 0, _p(stats), _p(colmm), int(M), int(N), _s())
     return out
 
 

@@ -291,17 +291,26 @@ class Engine:
         return t
 
     # ------------------------------------------------------------------------------------------------ primitives
-    def gemm(self, name, segs, ks, w, bias, n_out, rows_per_sample, bias2=None, want_stats=True, out=None):
-        """rows GEMM + (sum, sum^2) statistics in the format gn_coef expects -> (raw, stats, tiles)."""
+    def gemm(self, name, segs, ks, w, bias, n_out, rows_per_sample, bias2=None, want_stats=True, out=None, minmax=False,
+             store=True):
+        """rows GEMM + (sum, sum^2) statistics in the format gn_coef expects -> (raw, stats, tiles).
+        minmax: also per-tile column (max, min) -> self.last_colmm; store=False: statistics only (raw is None)."""
         M = segs[0].shape[0]
-        raw = out if out is not None else self.buf(name + ".raw", M, n_out)
+        raw = None
+        if store:
+            raw = out if out is not None else self.buf(name + ".raw", M, n_out)
         stats, tiles = None, 0
         fused = want_stats and rows_per_sample % 128 == 0
         if want_stats:
-            tiles = rows_per_sample // 128 if fused else 1
+            tiles = rows_per_sample // 32 if fused else 1      # the GEMM epilogue writes one partial per 32-row block
             stats = self.buf(name + ".stats", (M // rows_per_sample) * tiles, n_out, 2)
+        colmm = None
+        if minmax:
+            assert fused and n_out % 32 == 0
+            colmm = self.buf(name + ".colmm", (M // rows_per_sample) * tiles, n_out, 2)
+        self.last_colmm = colmm
         dense.gemm_rows(segs, w, bias, bias2, rows_per_sample if bias2 is not None else 0, out=raw,
-                        stats=stats if fused else None, ks=ks)
+                        stats=stats if fused else None, ks=ks, colmm=colmm, store=store)
         if want_stats and not fused:
             call("p2pb_col_stats", _p(raw), int(raw.stride(0)), M // rows_per_sample, rows_per_sample, n_out, _p(stats), _s())
         return raw, stats, tiles
@@ -367,7 +376,7 @@ class Engine:
             st2 = self.buf(f"{name}.st2", B * tiles, cout, 2)
             dense.conv3d_halo(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
         else:
-            tiles = r3 // 128
+            tiles = r3 // 32
             grid = self.buf(f"{name}.grid", B * r3, cp)
             call("p2pb_voxelize_cl", _p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]),
                  _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
@@ -510,9 +519,24 @@ class Engine:
                 if j == 2:
                     bias2 = self.buf(nm + ".gb", B, L["cout"])
                     self.linear(g_half, L["w_g"], None, 0, bias2)
-                raw, st, tl = self.gemm(nm, [x], [kx], L["w"], L["b"], L["cout"], N, bias2=bias2)
+                # the global max-pools (pvcnn.py:923-926, 930-931) come from the GEMM epilogue's column (max, min): Swish is
+                # unimodal, so max over points of Swish(GN(x)) is attained at the column's largest or smallest x.  The last
+                # layer's [B*N, 1024] output is never written.
+                mm = (j == 1 or j == 3) and N % 128 == 0
+                raw, st, tl = self.gemm(nm, [x], [kx], L["w"], L["b"], L["cout"], N, bias2=bias2, minmax=mm,
+                                        store=not (mm and j == 3))
+                colmm = self.last_colmm
                 A, Bc, _ = self.coef(nm, st, tl, L["n"], L["cout"], N)
-                if j == 1:      # activation rows AND global max over points (pvcnn.py:923-926)
+                if mm:
+                    g = self.buf(nm + ".gmax" if j == 1 else "cond", B, L["cout"])
+                    call("p2pb_gmax_minmax", _p(colmm), tl, B, L["cout"], _p(A), _p(Bc), 1, _p(g), _s())
+                    if j == 1:
+                        g_half = g
+                        out = self.buf(nm + ".act", B * N, pad32(L["cout"]))
+                        self.act(raw, A, Bc, N, L["cout"], out, act=1)
+                    else:
+                        out, cond = None, g
+                elif j == 1:      # activation rows AND global max over points (pvcnn.py:923-926)
                     out = self.buf(nm + ".act", B * N, pad32(L["cout"]))
                     g_half = self.buf(nm + ".gmax", B, L["cout"])
                     self.act(raw, A, Bc, N, L["cout"], out, act=1, gmax=g_half)

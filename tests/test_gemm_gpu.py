@@ -29,6 +29,64 @@ def test_gemm_rows_vs_fp64(M, K, N):
     _close(out, A.double() @ W.double().t() + bias.double())
 
 
+@pytest.mark.parametrize("mode", [0, 2, 4])
+@pytest.mark.parametrize("M,K,N", [(128 * 301 - 50, 96, 256), (128 * 300, 512, 1024), (40000, 64, 128), (5000, 160, 96)])
+def test_gemm_persistent_cluster_minmax(M, K, N, mode):
+    """Persistent kernel (mode 0; 2-CTA multicast clusters for the big shapes, odd tile count = unpaired tail),
+    legacy one-tile-per-CTA kernel (mode 2) and persistent without clusters (mode 4): results, GroupNorm partials and,
+    for the persistent kernel, column (max, min) and the statistics-only variant (no D)."""
+    from p2pb_b200 import dense
+    from p2pb_b200._lib import lib
+
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    T = dense.num_stat_blocks(M)
+    lib().p2pb_debug_set(mode)
+    try:
+        stats = torch.zeros(T, N, 2, device="cuda")
+        colmm = torch.zeros(T, N, 2, device="cuda") if mode != 2 else None
+        out = dense.gemm_rows([A], W, bias, stats=stats, colmm=colmm)
+        _close(out, ref)
+        assert torch.allclose(stats[..., 0].double().sum(0), out.double().sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(stats[..., 1].double().sum(0), (out.double() ** 2).sum(0), rtol=1e-4, atol=1e-2)
+        if colmm is not None:
+            assert torch.equal(colmm[..., 0].max(0).values, out.max(0).values)
+            assert torch.equal(colmm[..., 1].min(0).values, out.min(0).values)
+            stats2 = torch.zeros_like(stats)
+            colmm2 = torch.zeros_like(colmm)
+            assert dense.gemm_rows([A], W, bias, stats=stats2, colmm=colmm2, store=False) is None
+            assert torch.equal(stats2, stats) and torch.equal(colmm2, colmm)
+    finally:
+        lib().p2pb_debug_set(0)
+
+
+def test_gmax_minmax_matches_dense_pass():
+    """max over rows of Swish(x*A+B) from the column (max, min) == the dense affine_act + gmax pass."""
+    import ctypes
+
+    from p2pb_b200 import dense
+    from p2pb_b200._lib import call
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, rows, K, N = 3, 512, 64, 128
+    A = torch.randn(B * rows, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / 8
+    colmm = torch.zeros(B * rows // 32, N, 2, device="cuda")
+    out = dense.gemm_rows([A], W, None, colmm=colmm)
+    ca = torch.randn(B, N, device="cuda", generator=g)
+    cb = torch.randn(B, N, device="cuda", generator=g)
+    got = torch.empty(B, N, device="cuda")
+    vp = ctypes.c_void_p
+    call("p2pb_gmax_minmax", vp(colmm.data_ptr()), rows // 32, B, N, vp(ca.data_ptr()), vp(cb.data_ptr()), 1, vp(got.data_ptr()),
+         vp(torch.cuda.current_stream().cuda_stream))
+    y = out.view(B, rows, N) * ca[:, None] + cb[:, None]
+    ref = (y * torch.sigmoid(y)).max(1).values
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
 def test_gemm_rows_segments_bias2_stats():
     from p2pb_b200 import dense
 
@@ -43,13 +101,13 @@ def test_gemm_rows_segments_bias2_stats():
     W = torch.randn(N, 64 + 32 + 96, device="cuda", generator=g) / 14.0
     bias = torch.randn(N, device="cuda", generator=g)
     bias2 = torch.randn(B, N, device="cuda", generator=g)
-    stats = torch.zeros(dense.num_m_tiles(M), N, 2, device="cuda")
+    stats = torch.zeros(dense.num_stat_blocks(M), N, 2, device="cuda")
     out = torch.full((M, 80), 7.0, device="cuda")            # ldd > N: columns beyond N stay untouched
     dense.gemm_rows([A0, A1, A2], W, bias, bias2, rows, out=out[:, :N], stats=stats)
     ref = torch.cat([A0, A1, A2], 1).double() @ W.double().t() + bias.double() + bias2.double().repeat_interleave(rows, 0)
     _close(out[:, :N], ref)
     assert torch.all(out[:, N:] == 7.0)
-    s = stats.double().view(B, rows // 128, N, 2).sum(1)
+    s = stats.double().view(B, rows // 32, N, 2).sum(1)
     o = out[:, :N].double().view(B, rows, N)
     assert torch.allclose(s[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
@@ -67,7 +125,7 @@ def test_conv3d_vs_fp64(B, r, cin, cout):
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
     bias = torch.randn(cout, device="cuda", generator=g)
     grid = x.permute(0, 2, 3, 4, 1).contiguous()               # channels-last [B, r, r, r, cin]
-    stats = torch.zeros(B * r ** 3 // 128, cout, 2, device="cuda")
+    stats = torch.zeros(B * r ** 3 // 32, cout, 2, device="cuda")
     out = dense.conv3d_cl(grid, dense.pack_conv3d_weight(w, cin), bias, B, r, cin, cout, stats=stats)
     ref = F.conv3d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(B * r ** 3, cout)
     _close(out, ref)

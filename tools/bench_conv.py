@@ -25,7 +25,7 @@ for r, cin, cout in shapes:
     wp = dense.pack_conv3d_weight(w, cin)
     bias = torch.randn(cout, device="cuda")
     out = torch.empty(B * r ** 3, cout, device="cuda")
-    stats = torch.zeros(B * r ** 3 // 128, cout, 2, device="cuda")
+    stats = torch.zeros(B * r ** 3 // 32, cout, 2, device="cuda")
     t = timeit(lambda: dense.conv3d_cl(grid, wp, bias, B, r, cin, cout, out=out, stats=stats))
     x = grid.permute(0, 4, 1, 2, 3)  # NCDHW view with channels_last_3d strides
     tc = timeit(lambda: F.conv3d(x, w, bias, padding=1))

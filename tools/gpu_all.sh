@@ -1,0 +1,7 @@
+#!/bin/bash
+# tests + micro bench + bench line (no ncu)
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -15 gpurun_out/pytest_gpu.log
+timeout 300 python tools/bench_gemm.py > gpurun_out/bench_gemm.log 2>&1; grep -v experiments gpurun_out/bench_gemm.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.json; tail -3 gpurun_out/bench.err

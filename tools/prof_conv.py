@@ -12,7 +12,7 @@ out = torch.empty(B * r ** 3, cout, device="cuda")
 X = dense.dense_to_padded(grid, r)
 _, _, tps = dense.halo_layout(r)
 hst = torch.zeros(B * tps, cout, 2, device="cuda")
-st = torch.zeros(B * r ** 3 // 128, cout, 2, device="cuda")
+st = torch.zeros(B * r ** 3 // 32, cout, 2, device="cuda")
 for _ in range(3):
     dense.conv3d_halo(X, wp, bias, B, r, cin, cout, out=out, stats=hst)
     dense.conv3d_cl(grid, wp, bias, B, r, cin, cout, out=out, stats=st)
