@@ -103,6 +103,11 @@ int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* 
 int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int* tiles_per_sample_out);
 int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
                      int Cin, int Cout, void* stream);
+/* development aid: override the halo kernel's pipeline shape (0 = automatic) */
+int p2pb_conv_halo_tune(int w_stages, int a_stages, int G);
+/* cin_valid <= Cin: only the first cin_valid channels can be non-zero; K=8 MMAs over pure padding are skipped */
+int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                        int Cin, int cin_valid, int Cout, void* stream);
 
 /* coords [B,3,N] -> columns col0..col0+2 of rows [B*N, ld] */
 int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N, int ld, int col0, void* stream);
@@ -113,6 +118,11 @@ int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* temb, int 
                      const int* cnt, float* out, int Cp, int B, int N, int r, void* stream);
 int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* start,
                          const int* cnt, float* out, int Cp, int B, int N, int r, void* stream);
+/* sparse form: `out` is kept all-zero between calls; writes only the occupied voxel rows (clear = 0) or zeroes them again
+ * (clear = 1, after the convolution has read the grid).  ind [B,N] = flat voxel index of every point (p2pb_voxel_prep). */
+int p2pb_voxelize_padded_sparse(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* ind,
+                                const int* start, const int* cnt, float* out, int Cp, int B, int N, int r, int clear,
+                                void* stream);
 
 /* GroupNorm / AdaGN statistics -> per-(sample, channel) affine (and the SE squeeze): replaces nn.GroupNorm's reduction,
  * AdaGN.forward (/root/reference/models/modules.py:341-358) and SE3d's mean (modules.py:378) */

@@ -17,6 +17,14 @@
 // tools/ubench/mma_rate.cu on B200, one tcgen05.mma (M=128, K=32 bytes) costs max(64, N/2) cycles with a SWIZZLE_128B
 // A operand but ~115-125 cycles with an INTERLEAVE (no-swizzle) A operand, independent of the B layout.
 //
+// Mainloop order (v5): weights stream through a ring of SUB-slabs (the 3 dz-taps of one (dx, chunk, dy): 3 x [Cout][32]
+// fp32 = 12..48 KB) while the activation windows of the unit's G tiles stay resident for the whole (dx, chunk) slab:
+//   for slab (dx, chunk): for dy: [wait sub-slab] for tile g: [dy == 0: wait window g] 3 taps x 4 MMAs [dy == 2: free window g]
+// A full 9-tap slab is 144 KB at Cout = 128 and could only be single-buffered (every slab change stalled the tensor
+// core for a 144 KB L2 read, r01 profile: 480 TFLOP/s); the sub-slab ring is double/triple buffered in a third of the
+// space, and the freed shared memory holds G + 1..3 windows, so G = 4 tiles share every weight byte (2 before).
+// Separate producer warps feed the two rings so that neither blocks the other.
+//
 // Outputs for border positions inside the tile's linear range are computed but masked (not stored, not counted in the
 // GroupNorm statistics); the result is written in the dense [B*r^3, Cout] row layout the rest of the engine uses.
 #include <cuda.h>
@@ -27,20 +35,20 @@ namespace {
 
 constexpr int HBM = 128;
 constexpr int HBK = 32;
-constexpr int HALO_THREADS = 192;
+constexpr int HALO_THREADS = 224;   // warp 0: window producer, 1: MMA issuer, 2-5: epilogue, 6: weight producer
 
 struct HaloArgs {
     int B, r, P, P2, P3;      // P = r+2
     int cin_chunks;           // Cin_p / 32
+    int cin_valid;            // channels that can be non-zero (<= Cin_p): trailing K=8 MMAs of the last chunk are skipped
     int cout;
     int W;                    // window rows (odd, >= 128 + 2P + 2)
     int G;                    // tiles per work unit (their accumulators share one TMEM half)
     int halves;               // 2: units ping-pong between two 256-column TMEM halves; 1: one unit owns all 512 columns
-    int total_units;
     int tiles_per_sample, total_tiles;
     int q_first, q_last;
     int ldd;
-    int a_stages, slab_bufs;
+    int a_stages, w_stages;
     const float* X;           // padded row-major input (only used for documentation; loads go through mapX)
     const float* bias;
     float* D;                 // dense rows [B*r^3, ldd]
@@ -88,16 +96,8 @@ __device__ __forceinline__ void h_tma_load_2d(uint32_t dst, const CUtensorMap* m
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-// B: K-major SWIZZLE_128B (as gemm_tf32.cu)
-__device__ __forceinline__ uint64_t h_desc_sw128(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3ffff) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
+// Shared-memory matrix descriptors: K-major SWIZZLE_128B (8-row x 128 B atoms, SBO = 1024 B, version 1), built in the MMA
+// loop as a constant high word | (address >> 4).
 // A uses the same descriptor with a start address advanced by whole 128-byte rows inside the window (the row shift of
 // a tap): the tensor core applies the 128B swizzle to absolute shared-memory address bits, exactly as the TMA unit did
 // when it wrote the window, so no base-offset correction is needed (verified against fp64 convolutions on B200;
@@ -148,18 +148,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int slab_tap_bytes = a.cout * HBK * 4;        // one tap: [Cout][32] fp32, 128B-swizzled rows
-    const int slab_bytes = 9 * slab_tap_bytes;
+    const int tap_bytes = a.cout * HBK * 4;             // one tap: [Cout][32] fp32, 128B-swizzled rows
+    const int sub_bytes = 3 * tap_bytes;                // sub-slab: the 3 dz-taps of one (dx, chunk, dy)
     const int a_stage_bytes = a.W * 128;                // W rows x 32 channels (one 128-byte swizzle span per row)
     const int a_stage_stride = (a_stage_bytes + 1023) & ~1023;
-    uint8_t* sSlab = smem;
-    uint8_t* sA = sSlab + (size_t)a.slab_bufs * slab_bytes;
+    uint8_t* sW = smem;
+    uint8_t* sA = sW + (size_t)a.w_stages * sub_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.a_stages * a_stage_stride);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + a.a_stages;
-    uint64_t* s_full = a_empty + a.a_stages;
-    uint64_t* s_empty = s_full + a.slab_bufs;
-    uint64_t* tmem_full = s_empty + a.slab_bufs;   // [2]
+    uint64_t* w_full = a_empty + a.a_stages;
+    uint64_t* w_empty = w_full + a.w_stages;
+    uint64_t* tmem_full = w_empty + a.w_stages;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][cout][2]
@@ -173,9 +173,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             h_mbar_init(h_smem_u32(&a_full[s]), 1);
             h_mbar_init(h_smem_u32(&a_empty[s]), 1);
         }
-        for (int s = 0; s < a.slab_bufs; ++s) {
-            h_mbar_init(h_smem_u32(&s_full[s]), 1);
-            h_mbar_init(h_smem_u32(&s_empty[s]), 1);
+        for (int s = 0; s < a.w_stages; ++s) {
+            h_mbar_init(h_smem_u32(&w_full[s]), 1);
+            h_mbar_init(h_smem_u32(&w_empty[s]), 1);
         }
         for (int h = 0; h < 2; ++h) {
             h_mbar_init(h_smem_u32(&tmem_full[h]), 1);
@@ -193,83 +193,134 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_ptr_smem;
     const int nslabs = 3 * a.cin_chunks;
+    // Balanced static schedule: CTA c owns the contiguous tile range [c*T/grid, (c+1)*T/grid) and walks it in units of up
+    // to G tiles, so no CTA gets more than ceil(T/grid) tiles (a unit-granular round-robin loses up to G-1 tile-times).
+    const int tile_begin = (int)(((long long)a.total_tiles * blockIdx.x) / gridDim.x);
+    const int tile_end = (int)(((long long)a.total_tiles * (blockIdx.x + 1)) / gridDim.x);
     // Persistent CTA: work units of G tiles, unit u of this CTA accumulates in TMEM half (u & 1) so that the epilogue of
     // one unit overlaps the mainloop of the next (tmem_full / tmem_empty hand-off per half).
     const int half_cols = a.halves == 2 ? 256 : 0;
 
     if (warp == 0) {
-        // ===================== producer: weight slabs + activation windows (TMA) =====================
+        // ===================== producer A: activation windows (TMA), G per slab =====================
         if (h_elect_one()) {
-            int ait = 0, sit = 0;
-            for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x) {
-                const int tile0 = unit * a.G;
-                const int ntiles = min(a.G, a.total_tiles - tile0);
-                for (int sl = 0; sl < nslabs; ++sl, ++sit) {
+            int ast = 0;
+            uint32_t aph = 0;
+            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G) {
+                const int ntiles = min(a.G, tile_end - tile0);
+                for (int sl = 0; sl < nslabs; ++sl) {
                     const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
-                    const int sb = sit % a.slab_bufs;
-                    const uint32_t sph = (uint32_t)(sit / a.slab_bufs) & 1u;
-                    h_mbar_wait(h_smem_u32(&s_empty[sb]), sph ^ 1u);
-                    const uint32_t sfb = h_smem_u32(&s_full[sb]);
-                    h_mbar_expect_tx(sfb, (uint32_t)slab_bytes);
-                    for (int t9 = 0; t9 < 9; ++t9)
-                        h_tma_load_2d(h_smem_u32(sSlab + (size_t)sb * slab_bytes + (size_t)t9 * slab_tap_bytes), &mapW, sfb,
-                                      ((dx * 9 + t9) * a.cin_chunks + kc) * HBK, 0);
-                    for (int g = 0; g < ntiles; ++g, ++ait) {
+                    for (int g = 0; g < ntiles; ++g) {
                         const int tile = tile0 + g;
                         const int b = tile / a.tiles_per_sample;
                         const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * HBM;
                         const long long qs = (long long)q0 + (long long)(dx - 1) * a.P2 - (a.P + 1);  // window start row (>= 0)
-                        const int st = ait % a.a_stages;
-                        const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
-                        h_mbar_wait(h_smem_u32(&a_empty[st]), ph ^ 1u);
-                        const uint32_t fb = h_smem_u32(&a_full[st]);
+                        h_mbar_wait(h_smem_u32(&a_empty[ast]), aph ^ 1u);
+                        const uint32_t fb = h_smem_u32(&a_full[ast]);
                         h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
-                        h_tma_load_2d(h_smem_u32(sA + (size_t)st * a_stage_stride), &mapX, fb, kc * HBK,
+                        h_tma_load_2d(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * HBK,
                                       (int)((long long)b * a.P3 + qs));
+                        if (++ast == a.a_stages) {
+                            ast = 0;
+                            aph ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== producer W: weight sub-slabs (3 taps each) =====================
+        if (h_elect_one()) {
+            int wst = 0;
+            uint32_t wph = 0;
+            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G) {
+                for (int sl = 0; sl < nslabs; ++sl) {
+                    const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
+                    for (int dy = 0; dy < 3; ++dy) {
+                        h_mbar_wait(h_smem_u32(&w_empty[wst]), wph ^ 1u);
+                        const uint32_t fb = h_smem_u32(&w_full[wst]);
+                        h_mbar_expect_tx(fb, (uint32_t)sub_bytes);
+                        for (int dz = 0; dz < 3; ++dz)
+                            h_tma_load_2d(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
+                                          ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * HBK, 0);
+                        if (++wst == a.w_stages) {
+                            wst = 0;
+                            wph ^= 1u;
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)(HBM >> 4) << 24);
-        int ait = 0, sit = 0, it_unit = 0;
-        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x, ++it_unit) {
-            const int ntiles = min(a.G, a.total_tiles - unit * a.G);
-            const int h = a.halves == 2 ? (it_unit & 1) : 0;
-            const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
-            h_mbar_wait(h_smem_u32(&tmem_empty[h]), (use & 1u) ^ 1u);     // epilogue has drained this half
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int sl = 0; sl < nslabs; ++sl, ++sit) {
-                const int sb = sit % a.slab_bufs;
-                const uint32_t sph = (uint32_t)(sit / a.slab_bufs) & 1u;
-                h_mbar_wait(h_smem_u32(&s_full[sb]), sph);
-                for (int g = 0; g < ntiles; ++g, ++ait) {
-                    const int st = ait % a.a_stages;
-                    const uint32_t ph = (uint32_t)(ait / a.a_stages) & 1u;
-                    h_mbar_wait(h_smem_u32(&a_full[st]), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (h_elect_one()) {
-                        const uint64_t abase_d = h_desc_sw128(h_smem_u32(sA + (size_t)st * a_stage_stride));
-                        const uint64_t bbase_d = h_desc_sw128(h_smem_u32(sSlab + (size_t)sb * slab_bytes));
-                        const uint32_t dcol = tmem_base + (uint32_t)(h * half_cols + g * a.cout);
-                        const uint32_t tap_step = (uint32_t)(slab_tap_bytes >> 4);
+        // ===================== MMA issuer: ONE thread runs the whole loop =====================
+        // At N <= 64 one tcgen05.mma executes in ~49 cycles, so the issue path itself is on the critical path: the loop
+        // below keeps per-MMA work to two 32-bit adds (descriptor low words; the high word is a constant) and runs in a
+        // single elected thread, so there is no per-step warp re-convergence.
+        if (h_elect_one()) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)(HBM >> 4) << 24);
+            const uint32_t tap_step = (uint32_t)(tap_bytes >> 4);
+            const uint32_t sA_lo = (h_smem_u32(sA) & 0x3ffff) >> 4, sW_lo = (h_smem_u32(sW) & 0x3ffff) >> 4;
+            const uint32_t a_stride_lo = (uint32_t)(a_stage_stride >> 4), w_stride_lo = (uint32_t)(sub_bytes >> 4);
+            constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            int wst = 0, it_unit = 0;
+            uint32_t wph = 0;
+            int ast0 = 0;          // ring stage of the current slab's first window
+            uint32_t aph0 = 0;     // and its phase
+            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G, ++it_unit) {
+                const int ntiles = min(a.G, tile_end - tile0);
+                const int h = a.halves == 2 ? (it_unit & 1) : 0;
+                const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
+                h_mbar_wait(h_smem_u32(&tmem_empty[h]), (use & 1u) ^ 1u);     // epilogue has drained this half
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t dcol0 = tmem_base + (uint32_t)(h * half_cols);
+                for (int sl = 0; sl < nslabs; ++sl) {
+                    const int kc = sl % a.cin_chunks;
+                    int nj = (a.cin_valid - kc * HBK + 7) >> 3;     // K=8 MMAs that can see a non-zero channel
+                    nj = nj > 4 ? 4 : nj;
+                    for (int dy = 0; dy < 3; ++dy) {
+                        h_mbar_wait(h_smem_u32(&w_full[wst]), wph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_lo = sW_lo + (uint32_t)wst * w_stride_lo;
+                        // first tap (dz = -1) of this dy inside a window, in 16-byte descriptor units (128 B per row)
+                        const uint32_t row_lo = (uint32_t)(((a.P + 1) + (dy - 1) * a.P - 1) * 8);
+                        int st = ast0;
+                        uint32_t aph = aph0;
+                        for (int g = 0; g < ntiles; ++g) {
+                            if (dy == 0) {
+                                h_mbar_wait(h_smem_u32(&a_full[st]), aph);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            }
+                            const uint32_t a_lo = sA_lo + (uint32_t)st * a_stride_lo + row_lo;
+                            const uint32_t dcol = dcol0 + (uint32_t)(g * a.cout);
+                            const uint32_t first = (uint32_t)((sl | dy) != 0);
 #pragma unroll
-                        for (int t9 = 0; t9 < 9; ++t9) {
-                            const int dy = t9 / 3 - 1, dz = t9 % 3 - 1;
-                            // row offset of this tap inside the window, in 16-byte descriptor units (128 B per row)
-                            const uint64_t ad = abase_d + (uint64_t)(((a.P + 1) + dy * a.P + dz) * 8);
-                            const uint64_t bd = bbase_d + (uint64_t)(t9 * tap_step);
+                            for (int dz = 0; dz < 3; ++dz) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                h_umma_tf32(dcol, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (uint32_t)((sl | t9 | j) != 0));
+                                for (int j = 0; j < 4; ++j) {
+                                    if (j < nj)
+                                        h_umma_tf32(dcol, DESC_HI | (uint64_t)(a_lo + (uint32_t)(dz * 8 + j * 2)),
+                                                    DESC_HI | (uint64_t)(b_lo + (uint32_t)dz * tap_step + (uint32_t)(j * 2)), idesc,
+                                                    (dz | j) != 0 ? 1u : first);
+                                }
+                            }
+                            if (dy == 2) h_umma_commit(h_smem_u32(&a_empty[st]));
+                            if (++st == a.a_stages) {
+                                st = 0;
+                                aph ^= 1u;
+                            }
                         }
-                        h_umma_commit(h_smem_u32(&a_empty[st]));
-                        if (g == ntiles - 1) h_umma_commit(h_smem_u32(&s_empty[sb]));
-                        if (sl == nslabs - 1 && g == ntiles - 1) h_umma_commit(h_smem_u32(&tmem_full[h]));
+                        h_umma_commit(h_smem_u32(&w_empty[wst]));
+                        if (++wst == a.w_stages) {
+                            wst = 0;
+                            wph ^= 1u;
+                        }
+                        if (dy == 2) {      // the slab's windows are consumed: the next slab starts after them in the ring
+                            ast0 = st;
+                            aph0 = aph;
+                        }
                     }
-                    __syncwarp();
                 }
+                h_umma_commit(h_smem_u32(&tmem_full[h]));
             }
         }
     } else {
@@ -277,9 +328,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         const int qd = warp & 3;
         const int r = a.r, r3 = r * r * r;
         int it_unit = 0;
-        for (int unit = blockIdx.x; unit < a.total_units; unit += gridDim.x, ++it_unit) {
-            const int tile0 = unit * a.G;
-            const int ntiles = min(a.G, a.total_tiles - tile0);
+        for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G, ++it_unit) {
+            const int ntiles = min(a.G, tile_end - tile0);
             const int h = a.halves == 2 ? (it_unit & 1) : 0;
             const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
             h_mbar_wait(h_smem_u32(&tmem_full[h]), use & 1u);
@@ -365,35 +415,53 @@ P2PB_API int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int*
 
 // X: zero-bordered row-major grid [B*(r+2)^3 + slack rows, Cin]; W: [Cout, 27*Cin] (k = tap*Cin + c);
 // D: dense rows [B*r^3, ldd]; stats (optional): [B*tiles_per_sample, Cout, 2]
-P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
-                              int Cin, int Cout, void* stream)
+// development aid (tools/bench_conv.py): override the pipeline shape; 0 = automatic
+static int g_halo_w_stages = 0, g_halo_a_stages = 0, g_halo_G = 0;
+P2PB_API int p2pb_conv_halo_tune(int w_stages, int a_stages, int G)
+{
+    g_halo_w_stages = w_stages; g_halo_a_stages = a_stages; g_halo_G = G;
+    return P2PB_OK;
+}
+
+// cin_valid <= Cin: channels that can be non-zero (the rest is zero padding in X and W): the K=8 MMAs that would only
+// multiply padding are skipped (SA0's first conv: 35 real channels in a 64-wide layout -> 5 of 8 MMAs per tap)
+P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                                 int Cin, int cin_valid, int Cout, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
-    P2PB_CHECK_ARG(B > 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cout <= 256, "conv3d_halo: Cin=%d Cout=%d (multiples of 32, Cout<=256)", Cin, Cout);
+    P2PB_CHECK_ARG(B > 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cout <= 128, "conv3d_halo: Cin=%d Cout=%d (multiples of 32, Cout<=128)", Cin, Cout);
+    P2PB_CHECK_ARG(cin_valid > 0 && cin_valid <= Cin && cin_valid > Cin - 32, "conv3d_halo: cin_valid=%d must lie in the last 32-channel chunk of Cin=%d", cin_valid, Cin);
     P2PB_CHECK_ARG(r >= 8 && r <= 62, "conv3d_halo: r=%d out of range (TMA box rows 128+2(r+2)+2 <= 256)", r);
     P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= Cout, "conv3d_halo: bad ldd");
     HaloArgs a = {};
     a.B = B; a.r = r; a.P = r + 2; a.P2 = a.P * a.P; a.P3 = a.P2 * a.P;
-    a.cin_chunks = Cin / 32; a.cout = Cout;
+    a.cin_chunks = Cin / 32; a.cin_valid = cin_valid; a.cout = Cout;
     a.W = 128 + 2 * a.P + 2;
     a.q_first = a.P2 + a.P + 1;
     a.q_last = a.P3 - a.P2 - a.P - 2;
     a.tiles_per_sample = (a.q_last - a.q_first + 1 + HBM - 1) / HBM;
     a.total_tiles = B * a.tiles_per_sample;
-    a.halves = Cout <= 128 ? 2 : 1;
-    a.G = (a.halves == 2 ? 256 : 512) / Cout;
-    if (a.G > 8) a.G = 8;
-    a.total_units = (a.total_tiles + a.G - 1) / a.G;
+    // G tiles share every weight sub-slab; their accumulators fit one 256-column half of TMEM (G = 4 at Cout <= 64, 2 at
+    // Cout = 128) and units ping-pong between the halves, so the epilogue overlaps the next unit's mainloop (measured at
+    // Cout = 128: G = 4 without overlap 467 us, G = 2 with overlap 390 us)
+    a.G = Cout <= 64 ? 4 : 2;
+    if (g_halo_G > 0 && g_halo_G * Cout <= 512) a.G = g_halo_G;
+    a.halves = a.G * Cout <= 256 ? 2 : 1;
     a.ldd = ldd;
     a.X = X; a.bias = bias; a.D = D; a.stats = stats;
-    const int slab_bytes = 9 * Cout * HBK * 4;
+    const int sub_bytes = 3 * Cout * HBK * 4;
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
     const int budget = 225 * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
-    a.slab_bufs = (2 * slab_bytes + 3 * a_stage_stride <= budget) ? 2 : 1;
-    a.a_stages = (budget - a.slab_bufs * slab_bytes) / a_stage_stride;
-    if (a.a_stages > 6) a.a_stages = 6;
-    P2PB_CHECK_ARG(a.a_stages >= 2, "conv3d_halo: shared memory budget exceeded (Cout=%d r=%d)", Cout, r);
-    const size_t smem = 1024 + (size_t)a.slab_bufs * slab_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)4 * Cout * 2 * 4;
+    a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
+    a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
+    if (g_halo_w_stages >= 2) {
+        a.w_stages = g_halo_w_stages;
+        a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
+    }
+    if (a.a_stages > 2 * a.G) a.a_stages = 2 * a.G;
+    if (g_halo_a_stages > 0 && g_halo_a_stages < a.a_stages) a.a_stages = g_halo_a_stages;
+    P2PB_CHECK_ARG(a.a_stages >= a.G + 1, "conv3d_halo: shared memory budget exceeded (Cout=%d r=%d)", Cout, r);
+    const size_t smem = 1024 + (size_t)a.w_stages * sub_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)4 * Cout * 2 * 4;
     CUtensorMap mapW, mapX;
     {
         static PFN_encodeTiled_h enc = nullptr;
@@ -435,8 +503,14 @@ P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias,
         attr_set = true;
     }
     int grid = p2pb_num_sms();
-    if (grid > a.total_units) grid = a.total_units;
+    if (grid > a.total_tiles) grid = a.total_tiles;
     conv_halo_kernel<<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
+}
+
+P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                              int Cin, int Cout, void* stream)
+{
+    return p2pb_conv3d_halo_ex(X, W, bias, D, ldd, stats, B, r, Cin, Cin, Cout, stream);
 }

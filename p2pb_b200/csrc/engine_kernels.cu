@@ -761,6 +761,77 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
     return P2PB_OK;
 }
 
+// Sparse form of voxelize_padded for grids that are mostly empty (a 2048-point patch occupies ~5 % of a 32^3 grid):
+// the grid is kept all-zero between evaluations; this kernel writes only the occupied voxel rows (clear = 0), and after
+// the convolution has consumed the grid the same enumeration zeroes them again (clear = 1).  One thread per
+// (sorted point slot, 4 channels); the slot that starts a voxel's CSR range owns the voxel, the others exit.  The sums
+// run over the voxel's points in ascending point index exactly like the dense kernel (bit-identical result).
+__global__ void __launch_bounds__(256) voxelize_sparse_kernel(const float* __restrict__ feat, int ldf, int Cf,
+                                                              const float* __restrict__ temb, int E,
+                                                              const int* __restrict__ order, const int* __restrict__ ind,
+                                                              const int* __restrict__ start, const int* __restrict__ cnt,
+                                                              float* __restrict__ out, int Cp, int N, int r, int clear,
+                                                              unsigned total4)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total4) return;
+    const unsigned r3 = r * r * r;
+    const unsigned C4 = Cp >> 2;
+    const unsigned slot = e / C4;            // b*N + j
+    const int c0 = (int)(e - slot * C4) * 4;
+    const int b = (int)(slot / (unsigned)N);
+    const int j = (int)(slot - (unsigned)b * N);
+    const int p = order[slot];
+    const int v = ind[(size_t)b * N + p];
+    const size_t vrow = (size_t)b * r3 + v;
+    if (start[vrow] != j) return;            // not the first point of its voxel
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!clear) {
+        const int n = cnt[vrow];
+        const float inv = (float)(1.0 / (double)(float)n);
+        const int* ord = order + (size_t)b * N + j;
+        if (c0 + 3 < Cf && (ldf & 3) == 0) {
+            for (int i = 0; i < n; ++i) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + ord[i]) * ldf + c0));
+                a[0] = __fadd_rn(a[0], __fmul_rn(f.x, inv));
+                a[1] = __fadd_rn(a[1], __fmul_rn(f.y, inv));
+                a[2] = __fadd_rn(a[2], __fmul_rn(f.z, inv));
+                a[3] = __fadd_rn(a[3], __fmul_rn(f.w, inv));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                if (c < Cf) {
+                    float s = 0.f;
+                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
+                    a[k] = s;
+                } else if (c < Cf + E) {
+                    const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
+                    float s = 0.f;
+                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
+                    a[k] = s;
+                }
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * Cp + c0) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+P2PB_API int p2pb_voxelize_padded_sparse(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
+                                         const int* ind, const int* start, const int* cnt, float* out, int Cp, int B, int N,
+                                         int r, int clear, void* stream)
+{
+    P2PB_CHECK_ARG(Cp % 32 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_padded_sparse: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
+    const long long total4 = (long long)B * N * (Cp / 4);
+    P2PB_CHECK_U32(total4, "voxelize_padded_sparse");
+    if (total4 == 0) return P2PB_OK;
+    voxelize_sparse_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, ind, start, cnt,
+                                                                                   out, Cp, N, r, clear, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
 // y = swish(x*A + B) of dense conv-output rows [B*r^3, ldx] -> zero-bordered padded input rows of the next conv
 __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                                 const float* __restrict__ Bc, int C, float* __restrict__ out,

@@ -111,11 +111,12 @@ def dense_to_padded(grid: torch.Tensor, r: int) -> torch.Tensor:
 
 
 def conv3d_halo(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], B: int, r: int, cin: int, cout: int,
-                out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+                cin_valid: Optional[int] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty((B * r ** 3, cout), dtype=torch.float32, device=X.device)
     assert X.is_contiguous() and X.shape[1] == cin
     with torch.cuda.device(X.device):
-        call("p2pb_conv3d_halo", _p(X), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
-             int(cout), _s())
+        call("p2pb_conv3d_halo_ex", _p(X), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
+             int(cin if cin_valid is None else cin_valid), int(cout), _s())
     return out

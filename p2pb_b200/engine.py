@@ -366,10 +366,13 @@ class Engine:
         if halo:
             _, _, tiles = dense.halo_layout(r)
             grid = self.padded(f"{name}.grid", B, cp, r)
-            call("p2pb_voxelize_padded", _p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]),
-                 _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
+            # the grid stays all-zero between evaluations: write the occupied voxels, convolve, zero them again
+            vox_args = (_p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]), _p(prep["ind"]),
+                        _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r)
+            call("p2pb_voxelize_padded_sparse", *vox_args, 0, _s())
             st1 = self.buf(f"{name}.st1", B * tiles, cout, 2)
-            dense.conv3d_halo(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1)
+            dense.conv3d_halo(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1, cin_valid=P["cin"] + P["E"])
+            call("p2pb_voxelize_padded_sparse", *vox_args, 1, _s())
             A1, B1, _ = self.coef(f"{name}.n1", st1, tiles, P["n1"], cout, r3)
             act1 = self.padded(f"{name}.act1", B, pad32(cout), r)
             call("p2pb_affine_act_padded", _p(raw1), cout, _p(A1), _p(B1), B, cout, r, _p(act1), _s())
@@ -417,7 +420,7 @@ class Engine:
             start = self.buf(f"prep{key}.start", B, r ** 3, dtype=torch.int32)
             cnt = self.buf(f"prep{key}.cnt", B, r ** 3, dtype=torch.int32)
             call("p2pb_voxel_prep", _p(coords), B, n, r, 1, _f(0.0), _p(nc), _p(ind), _p(order), _p(start), _p(cnt), _s())
-            cache[key] = {"norm_coords": nc, "order": order, "start": start, "cnt": cnt}
+            cache[key] = {"norm_coords": nc, "order": order, "start": start, "cnt": cnt, "ind": ind}
         return cache[key]
 
     def _side_stream(self):

@@ -180,3 +180,35 @@ def test_engine_pvdl_8192_vs_eager(extra):
     err = (eps - ref).abs()
     print(f"PVDL N=8192 extra={extra}: engine vs eager fp32: mean|err|={err.mean():.3e} max|err|={err.max():.3e} |eps|max={ref.abs().max():.2f}")
     assert err.mean().item() <= 2e-3 and err.max().item() <= 5e-2
+
+
+def test_voxelize_sparse_equals_dense_and_clears():
+    """The occupied-voxels-only voxelisation (engine default) writes bit-identical rows to the dense kernel, leaves
+    every other row untouched (zero), and its clear pass restores the all-zero grid."""
+    import ctypes
+
+    from p2pb_b200 import dense
+    from p2pb_b200._lib import call
+
+    vp = ctypes.c_void_p
+    p = lambda t: vp(t.data_ptr()) if t is not None else vp(0)
+    s = vp(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, N, r, Cf, E, Cp = 3, 1024, 16, 35, 64, 128
+    coords = torch.randn(B, 3, N, device="cuda", generator=g)
+    feat = torch.randn(B * N, 64, device="cuda", generator=g)        # ldf = 64 > Cf
+    temb = torch.randn(B, E, device="cuda", generator=g)
+    nc = torch.empty(B, 3, N, device="cuda")
+    ind = torch.empty(B, N, dtype=torch.int32, device="cuda")
+    order = torch.empty(B, N, dtype=torch.int32, device="cuda")
+    start = torch.empty(B, r ** 3, dtype=torch.int32, device="cuda")
+    cnt = torch.empty(B, r ** 3, dtype=torch.int32, device="cuda")
+    call("p2pb_voxel_prep", p(coords), B, N, r, 1, ctypes.c_float(0.0), p(nc), p(ind), p(order), p(start), p(cnt), s)
+    ref = dense.alloc_padded(B, Cp, r, "cuda")
+    call("p2pb_voxelize_padded", p(feat), 64, Cf, p(temb), E, p(order), p(start), p(cnt), p(ref), Cp, B, N, r, s)
+    out = dense.alloc_padded(B, Cp, r, "cuda")
+    args = (p(feat), 64, Cf, p(temb), E, p(order), p(ind), p(start), p(cnt), p(out), Cp, B, N, r)
+    call("p2pb_voxelize_padded_sparse", *args, 0, s)
+    assert torch.equal(out, ref) and int((cnt > 0).sum()) > 0
+    call("p2pb_voxelize_padded_sparse", *args, 1, s)
+    assert int(out.count_nonzero()) == 0
