@@ -4,7 +4,7 @@ reference's ``denoise_object.py`` (flags :19-30, flow :125-170), running the B20
 
 normalise -> FPS seeds -> kNN-2048 patches -> P2PB.sample (fused engine) -> de-normalise -> FPS merge -> ``.xyz``.
 The seed / merge FPS (``torch_cluster.fps`` in the reference, start index 0) and the patch kNN (``pytorch3d.knn_points``,
-ascending distance) run on this repo's kernels (FPS) and a distance + top-k selection on the device.
+ascending distance) run on this repo's kernels: FPS and a radix-select + sort kNN (csrc/metrics.cu).
 """
 from __future__ import annotations
 
@@ -57,8 +57,7 @@ def farthest_point_sampling(pcls: torch.Tensor, num_pnts: int):
 
 def knn_patches(seeds: torch.Tensor, pcl: torch.Tensor, K: int) -> torch.Tensor:
     """K nearest points of ``pcl [N,3]`` for every seed ``[P,3]``, ascending distance (pytorch3d.ops.knn_points order)."""
-    d = torch.cdist(seeds, pcl)
-    idx = d.topk(K, dim=1, largest=False, sorted=True).indices
+    idx = ops.knn_points(seeds.contiguous().float(), pcl.contiguous().float(), K).long()
     return pcl[idx]
 
 

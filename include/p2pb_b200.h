@@ -73,6 +73,17 @@ int p2pb_trilinear_devoxelize(const float* coords, const float* grid, int B, int
 int p2pb_nm_distance(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist, int* idx,
                      unsigned long long* scratch, void* stream);
 
+/* replaces approxmatch_forward + matchcost_forward (/root/reference/metrics/PyTorchEMD/cuda/emd_kernel.cu:33-165, 211-253,
+ * called by emd_nograd.py:19-44): xyz1 [B,n,3], xyz2 [B,m,3] -> cost [B] (un-normalised; the caller divides by N).
+ * The match matrix [B,m,n] is never materialised; scratch: B*(3n+2m) floats. */
+int p2pb_emd_approx(const float* xyz1, const float* xyz2, int B, int n, int m, float* cost, float* scratch, void* stream);
+
+/* ---- patch extraction (denoise_object) ---------------------------------------------------------------------- */
+
+/* replaces pytorch3d.ops.knn_points as called at /root/reference/denoise_object.py:90-91 (un-vendored dependency):
+ * queries [Q,3], pts [N,3] -> idx int32 [Q,K] ascending squared distance (ties: lower index), dist [Q,K] optional */
+int p2pb_knn_points(const float* queries, const float* pts, int Q, int N, int K, int* idx, float* dist, void* stream);
+
 /* ==== fused channels-last engine (rows [M, ld] fp32, ld multiple of 4) ====================== */
 
 /* The dense contractions: replaces cuDNN Conv1d/Conv2d(1x1) and cuBLAS Linear behind

@@ -178,6 +178,17 @@ def emd_approxmatch_cost(xyz1, xyz2):
     return cost, match
 
 
+def knn_points(queries, points, K):
+    """pytorch3d.ops.knn_points contract (squared L2, K smallest ascending, ties by index): idx int32 [Q,K], dist [Q,K]."""
+    queries = queries.contiguous().float()
+    points = points.contiguous().float()
+    Q, N = queries.shape[0], points.shape[0]
+    idx = torch.empty((Q, K), dtype=torch.int32)
+    dist = torch.empty((Q, K), dtype=torch.float32)
+    lib().ora_knn_points(_f(queries), _f(points), Q, N, int(K), _i(idx), _f(dist))
+    return idx, dist
+
+
 _BACKWARD = ["avg_voxelize_backward", "trilinear_devoxelize_backward", "three_nearest_neighbors_interpolate_backward",
              "grouping_backward", "gather_features_backward"]
 

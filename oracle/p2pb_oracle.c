@@ -447,3 +447,33 @@ ORA_API void ora_emd_approxmatch_cost(const float *xyz1, const float *xyz2, int 
         free(ratioR);
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * kNN patch extraction: pytorch3d.ops.knn_points as called by denoise_object.py:90-91 -- an UN-VENDORED dependency of
+ * the reference (parity unpinned at this boundary).  Restated contract: squared L2 distance, the K smallest
+ * per query, ascending, ties by lower index.  queries [Q,3], pts [N,3] -> idx [Q,K], dist [Q,K] (squared).
+ * Plain insertion into a sorted K-list (O(N*K) worst case; test sizes only).
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_knn_points(const float *queries, const float *pts, int Q, int N, int K, int32_t *idx, float *dist)
+{
+    for (int q = 0; q < Q; ++q) {
+        const float qx = queries[q * 3], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
+        int32_t *bi = idx + (size_t)q * K;
+        float *bd = dist + (size_t)q * K;
+        int cnt = 0;
+        for (int i = 0; i < N; ++i) {
+            const float d = sqdist3(pts[i * 3] - qx, pts[i * 3 + 1] - qy, pts[i * 3 + 2] - qz);
+            if (cnt == K && !(d < bd[K - 1])) continue; /* ties keep the earlier (lower) index */
+            int pos = cnt < K ? cnt : K - 1;
+            while (pos > 0 && d < bd[pos - 1]) {
+                bd[pos] = bd[pos - 1];
+                bi[pos] = bi[pos - 1];
+                --pos;
+            }
+            bd[pos] = d;
+            bi[pos] = i;
+            if (cnt < K) ++cnt;
+        }
+    }
+}
+

@@ -27,7 +27,7 @@ namespace {
 
 constexpr int PBM = 128;
 constexpr int PBK = 32;
-constexpr int P_THREADS = 192;
+constexpr int P_THREADS = 320;   // warp 0: TMA producer, 1: MMA issuer, 2-9: epilogue (two warps per TMEM lane quarter)
 constexpr int PA_STAGE = PBM * PBK * 4;  // 16 KiB
 
 struct PArgs {
@@ -166,8 +166,8 @@ struct PCfg {
     static constexpr int B_STAGE = BN * PBK * 4;
     static constexpr int NACC = BN >= 256 ? 2 : 4;              // accumulators in TMEM (tiles in flight MMA -> epilogue)
     static constexpr int TM_COLS = NACC * BN;                   // BN in {32,64,128,256} -> 128..512 (powers of two)
-    static constexpr int NCB = 2;                               // staging buffers per epilogue warp (4 KiB each)
-    static constexpr int C_BYTES = 4 * NCB * 4096;
+    static constexpr int NCB = 1;                               // staging buffers per epilogue warp (4 KiB each)
+    static constexpr int C_BYTES = 8 * NCB * 4096;
     static constexpr int STAT_BYTES = 0;
 };
 
@@ -208,7 +208,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         }
         for (int h = 0; h < NACC; ++h) {
             p_mbar_init(p_smem_u32(&tfull[h]), 1);
-            p_mbar_init(p_smem_u32(&tempty[h]), 4);         // one arrival per epilogue warp
+            p_mbar_init(p_smem_u32(&tempty[h]), 8);         // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -311,9 +311,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             }
         }
     } else {
-        // ===================== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====================
+        // ===================== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31 (hardware rule) and the
+        // two warps of a lane quarter take the even / odd 32-column chunks =====================
         const int q = warp & 3;
-        uint8_t* myC = sC + (size_t)q * Cfg::NCB * 4096;
+        const int chalf = (warp - 2) >> 2;
+        uint8_t* myC = sC + (size_t)(warp - 2) * Cfg::NCB * 4096;
         const bool want_stats = a.stats != nullptr, want_mm = a.colmm != nullptr;
         int li = 0, cbuf = 0;
         for (int item = cluster_id; item < a.total_items; item += n_clusters, ++li) {
@@ -332,12 +334,16 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             if (a.bias2 != nullptr && row_ok) bias2_row = a.bias2 + (size_t)(row / a.rows_per_sample) * a.n_total;
             p_mbar_wait(p_smem_u32(&tfull[h]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (BN / 32 < 2 && chalf == 1) {     // single-chunk tiles: the odd-chunk warps have nothing to read
+                if (lane == 0) p_mbar_arrive(p_smem_u32(&tempty[h]));
+                continue;
+            }
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf; c < BN / 32; c += 2) {
                 float v[32];
                 p_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + c * 32), v);
-                if (c == BN / 32 - 1) {
-                    // accumulator fully read: hand it back to the MMA warp before the rest of the epilogue
+                if (c + 2 >= BN / 32) {
+                    // this warp's share of the accumulator is read: hand it back to the MMA warp before the rest of the epilogue
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (lane == 0) p_mbar_arrive(p_smem_u32(&tempty[h]));
                 }
@@ -374,13 +380,26 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     // column `lane` of the 32 x 32 block: element (r, lane) sits at r*128 + (((lane>>2) ^ (r&7))<<4) + (lane&3)*4
                     float s1 = 0.f, s2 = 0.f, mx = -INFINITY, mn = INFINITY;
                     const uint8_t* colp = buf + (lane & 3) * 4;
-#pragma unroll 8
-                    for (int r = 0; r < nvalid; ++r) {
-                        const float x = *reinterpret_cast<const float*>(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
-                        s1 += x;
-                        s2 = fmaf(x, x, s2);
-                        mx = fmaxf(mx, x);
-                        mn = fminf(mn, x);
+                    if (nvalid == 32) {
+                        float x[32];
+#pragma unroll
+                        for (int r = 0; r < 32; ++r)
+                            x[r] = *reinterpret_cast<const float*>(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            s1 += x[r];
+                            s2 = fmaf(x[r], x[r], s2);
+                            mx = fmaxf(mx, x[r]);
+                            mn = fminf(mn, x[r]);
+                        }
+                    } else {
+                        for (int r = 0; r < nvalid; ++r) {
+                            const float x = *reinterpret_cast<const float*>(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
+                            s1 += x;
+                            s2 = fmaf(x, x, s2);
+                            mx = fmaxf(mx, x);
+                            mn = fminf(mn, x);
+                        }
                     }
                     if (tile_ok) {
                         // 32-row partials go straight to global: [(m_tile*4 + q), n_total, 2], coalesced 256 B per warp

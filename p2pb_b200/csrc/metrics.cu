@@ -79,3 +79,265 @@ P2PB_API int p2pb_nm_distance(const float* xyz1, const float* xyz2, int B, int n
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
+
+// =========================================================================================================
+// Approximate earth mover's distance (forward): replaces approxmatch + matchcost
+//   (metrics/PyTorchEMD/cuda/emd_kernel.cu:33-165, 211-253; called by emd_nograd.py:19-44).
+// Same annealed soft assignment: levels j = 7..-2 (level = -4^j, 0 at j = -2), three all-pairs passes per level
+//   (1) ratioL[k] = remainL[k] / (1e-9 + sum_l e^{level d(k,l)} remainR[l])
+//   (2) sumr = remainR[l] sum_k e^{level d} ratioL[k];  ratioR[l] = min(remainR/(sumr+1e-9), 1) remainR;  remainR -= sumr (>= 0)
+//   (3) w(k,l) = e^{level d} ratioL[k] ratioR[l];  match[l,k] += w;  remainL[k] -= sum_l w (>= 0)
+// and cost = sum_{k,l} d(k,l) match[l,k] with the SQUARED distance d (this fork, :236-237).
+// B200 design: the reference runs one 512-thread CTA per cloud (<<<32,512>>>: at most 32 SMs) and materialises
+// match [B,m,n] (268 MB per cloud at 8192 points) only to contract it with d afterwards.  Here every pass is its own
+// launch over (row tiles x B) CTAs -- a warp per row, lanes striding the other cloud -- and pass (3) accumulates
+// sum_l d*w per row directly, so match is never stored: memory O(n+m), all SMs busy.  fp32, __expf like the reference;
+// the summation order differs (warp tree vs one thread per row), so results agree to fp tolerance, not bitwise.
+// =========================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256) emd_pass_kernel(const float* __restrict__ rows_xyz, const float* __restrict__ cols_xyz, int R,
+                                                       int C, float level, const float* __restrict__ col_w,
+                                                       float* __restrict__ remain_row, float* __restrict__ ratio_row,
+                                                       float* __restrict__ cost_row)
+{
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + warp;
+    if (k >= R) return;
+    const float* pr = rows_xyz + ((size_t)b * R + k) * 3;
+    const float x1 = pr[0], y1 = pr[1], z1 = pr[2];
+    const float* pc = cols_xyz + (size_t)b * C * 3;
+    const float* w = col_w + (size_t)b * C;
+    float acc = 0.f, dacc = 0.f;
+    for (int l = lane; l < C; l += 32) {
+        const float dx = pc[l * 3] - x1, dy = pc[l * 3 + 1] - y1, dz = pc[l * 3 + 2] - z1;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float e = __expf(level * d) * w[l];
+        acc += e;
+        if (MODE == 3) dacc = fmaf(d, e, dacc);
+    }
+    acc = warp_sum(acc);
+    if (MODE == 3) dacc = warp_sum(dacc);
+    if (lane != 0) return;
+    const size_t o = (size_t)b * R + k;
+    if (MODE == 1) {
+        ratio_row[o] = remain_row[o] / (1e-9f + acc);
+    } else if (MODE == 2) {
+        const float rem = remain_row[o];
+        const float sumr = acc * rem;
+        const float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+        ratio_row[o] = consumption * rem;
+        remain_row[o] = fmaxf(0.0f, rem - sumr);
+    } else {
+        const float rl = ratio_row[o];
+        cost_row[o] += dacc * rl;
+        remain_row[o] = fmaxf(0.0f, remain_row[o] - acc * rl);
+    }
+}
+
+__global__ void emd_init_kernel(float* remainL, float* remainR, float* cost_row, int n, int m, float multiL, float multiR,
+                                long long totalL, long long totalR)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < totalL) {
+        remainL[i] = multiL;
+        cost_row[i] = 0.f;
+    }
+    if (i < totalR) remainR[i] = multiR;
+}
+
+__global__ void __launch_bounds__(256) emd_cost_kernel(const float* __restrict__ cost_row, int n, float* __restrict__ cost)
+{
+    __shared__ double s[8];
+    const int b = blockIdx.x;
+    double a = 0.0;
+    for (int k = threadIdx.x; k < n; k += 256) a += (double)cost_row[(size_t)b * n + k];
+    a = warp_sum_d(a);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += s[i];
+        cost[b] = (float)t;
+    }
+}
+
+// xyz1 [B,n,3], xyz2 [B,m,3] -> cost [B] (un-normalised, like matchcost_forward); scratch: B*(3n+2m) floats
+P2PB_API int p2pb_emd_approx(const float* xyz1, const float* xyz2, int B, int n, int m, float* cost, float* scratch, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    P2PB_CHECK_ARG(B >= 0 && n > 0 && m > 0, "emd_approx: bad sizes");
+    P2PB_CHECK_ARG(scratch != nullptr, "emd_approx: scratch of B*(3n+2m) floats required");
+    if (B == 0) return P2PB_OK;
+    float* remainL = scratch;
+    float* ratioL = remainL + (size_t)B * n;
+    float* cost_row = ratioL + (size_t)B * n;
+    float* remainR = cost_row + (size_t)B * n;
+    float* ratioR = remainR + (size_t)B * m;
+    const float multiL = n >= m ? 1.f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.f;  // integer division, :38-43
+    const long long tl = (long long)B * n, tr = (long long)B * m;
+    emd_init_kernel<<<p2pb_cdiv(tl > tr ? tl : tr, 256), 256, 0, s>>>(remainL, remainR, cost_row, n, m, multiL, multiR, tl, tr);
+    P2PB_LAUNCH_OK();
+    const dim3 gl(p2pb_cdiv(n, 8), B), gr(p2pb_cdiv(m, 8), B);
+    for (int j = 7; j >= -2; --j) {
+        const float level = j == -2 ? 0.f : -powf(4.0f, (float)j);
+        emd_pass_kernel<1><<<gl, 256, 0, s>>>(xyz1, xyz2, n, m, level, remainR, remainL, ratioL, nullptr);
+        P2PB_LAUNCH_OK();
+        emd_pass_kernel<2><<<gr, 256, 0, s>>>(xyz2, xyz1, m, n, level, ratioL, remainR, ratioR, nullptr);
+        P2PB_LAUNCH_OK();
+        emd_pass_kernel<3><<<gl, 256, 0, s>>>(xyz1, xyz2, n, m, level, ratioR, remainL, ratioL, cost_row);
+        P2PB_LAUNCH_OK();
+    }
+    emd_cost_kernel<<<B, 256, 0, s>>>(cost_row, n, cost);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// =========================================================================================================
+// kNN patch extraction: for every query the K nearest points of one cloud, ascending distance (ties: lower index).
+// Replaces pytorch3d.ops.knn_points as called by denoise_object.py:90-91 (K = 2048 neighbours of each FPS seed in a
+// 10k..150k point cloud; return_sorted default True) -- an un-vendored dependency of the reference: the
+// contract reproduced is "squared L2, K smallest, sorted ascending".
+// One CTA per query: (1) 4-pass radix select on the fp32 distance bits (non-negative floats order like unsigned ints)
+// finds the K-th smallest distance T, (2) an index-ordered compaction takes everything below T plus the first
+// (K - #below) points at exactly T, (3) a shared-memory bitonic sort of the packed (distance bits, index) keys orders
+// them.  Distances are recomputed per pass (3 loads + 3 FMAs) instead of being stored.
+// =========================================================================================================
+#define KNN_THREADS 1024
+
+__device__ __forceinline__ unsigned knn_dist_bits(const float* __restrict__ pts, int i, float qx, float qy, float qz)
+{
+    return __float_as_uint(sqdist3(pts[i * 3] - qx, pts[i * 3 + 1] - qy, pts[i * 3 + 2] - qz));
+}
+
+__global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const float* __restrict__ queries, const float* __restrict__ pts,
+                                                                 int N, int K, int Kp2, int* __restrict__ idx_out,
+                                                                 float* __restrict__ dist_out)
+{
+    extern __shared__ unsigned long long s_keys[];   // [Kp2]
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_scan[KNN_THREADS / 32];
+    __shared__ unsigned s_prefix, s_remaining, s_nsel, s_neq;
+    const int q = blockIdx.x, t = threadIdx.x;
+    const float qx = queries[q * 3], qy = queries[q * 3 + 1], qz = queries[q * 3 + 2];
+    // ---- (1) radix select: after the 4 passes `prefix` is the bit pattern of the K-th smallest distance
+    if (t == 0) {
+        s_prefix = 0;
+        s_remaining = (unsigned)K;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (t < 256) s_hist[t] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = t; i < N; i += KNN_THREADS) {
+            const unsigned d = knn_dist_bits(pts, i, qx, qy, qz);
+            if ((d & mask) == prefix) atomicAdd(&s_hist[(d >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (t == 0) {
+            unsigned rem = s_remaining, bin = 0;
+            for (; bin < 256; ++bin) {
+                const unsigned c = s_hist[bin];
+                if (rem <= c) break;
+                rem -= c;
+            }
+            s_prefix = prefix | (bin << shift);
+            s_remaining = rem;          // rank of the K-th smallest inside the selected bin (1-based)
+        }
+        __syncthreads();
+    }
+    const unsigned T = s_prefix;
+    const unsigned take_eq = s_remaining;    // how many points at exactly T belong to the K nearest
+    // ---- (2) compaction in index order (block-wide scans per chunk of KNN_THREADS points)
+    if (t == 0) {
+        s_nsel = 0;
+        s_neq = 0;
+    }
+    for (int i = t; i < Kp2; i += KNN_THREADS) s_keys[i] = ~0ull;
+    __syncthreads();
+    for (int i0 = 0; i0 < N; i0 += KNN_THREADS) {
+        const int i = i0 + t;
+        unsigned d = 0xffffffffu;
+        if (i < N) d = knn_dist_bits(pts, i, qx, qy, qz);
+        const bool below = i < N && d < T, eq = i < N && d == T;
+        // packed scan: low 16 bits count `below`, high 16 bits count `eq`
+        unsigned v = (below ? 1u : 0u) | (eq ? 0x10000u : 0u);
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((t & 31) >= o) inc += n;
+        }
+        if ((t & 31) == 31) s_scan[t >> 5] = inc;
+        __syncthreads();
+        if (t < 32) {
+            unsigned w = s_scan[t];
+            unsigned winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, winc, o);
+                if (t >= o) winc += n;
+            }
+            s_scan[t] = winc - w;    // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const unsigned excl = s_scan[t >> 5] + inc - v;
+        const unsigned base_below = s_nsel, base_eq = s_neq;
+        // points below T fill [0, K - take_eq) in index order; the first take_eq points at exactly T fill the rest from the end
+        if (below) {
+            s_keys[base_below + (excl & 0xffffu)] = ((unsigned long long)d << 32) | (unsigned)i;
+        } else if (eq) {
+            const unsigned rank_eq = base_eq + (excl >> 16);
+            if (rank_eq < take_eq) s_keys[(unsigned)K - 1u - rank_eq] = ((unsigned long long)d << 32) | (unsigned)i;
+        }
+        __syncthreads();
+        if (t == KNN_THREADS - 1) {
+            s_nsel = base_below + ((excl + v) & 0xffffu);
+            s_neq = base_eq + ((excl + v) >> 16);
+        }
+        __syncthreads();
+    }
+    // ---- (3) bitonic sort of the Kp2 keys (padding keys are all-ones and sink to the end)
+    for (int size = 2; size <= Kp2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = t; i < Kp2 / 2; i += KNN_THREADS) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = s_keys[lo], b = s_keys[hi];
+                if ((a > b) == up) {
+                    s_keys[lo] = b;
+                    s_keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = t; i < K; i += KNN_THREADS) {
+        const unsigned long long key = s_keys[i];
+        idx_out[(size_t)q * K + i] = (int)(unsigned)key;
+        if (dist_out != nullptr) dist_out[(size_t)q * K + i] = __uint_as_float((unsigned)(key >> 32));
+    }
+}
+
+// queries [Q,3], pts [N,3] -> idx int32 [Q,K] (ascending distance, ties by index), dist [Q,K] squared (optional)
+P2PB_API int p2pb_knn_points(const float* queries, const float* pts, int Q, int N, int K, int* idx, float* dist, void* stream)
+{
+    P2PB_CHECK_ARG(Q >= 0 && N > 0 && K > 0 && K <= N, "knn_points: need 0 < K <= N (Q=%d N=%d K=%d)", Q, N, K);
+    P2PB_CHECK_ARG(K <= 16384, "knn_points: K=%d exceeds the shared-memory sort (16384)", K);
+    P2PB_CHECK_ARG(N < (1 << 30), "knn_points: N too large");
+    if (Q == 0) return P2PB_OK;
+    int Kp2 = 2;
+    while (Kp2 < K) Kp2 <<= 1;
+    const size_t smem = (size_t)Kp2 * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) {
+        P2PB_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        attr_set = true;
+    }
+    knn_select_kernel<<<Q, KNN_THREADS, smem, (cudaStream_t)stream>>>(queries, pts, N, K, Kp2, idx, dist);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}

@@ -182,3 +182,46 @@ def calculate_cd(pred: torch.Tensor, gt: torch.Tensor):
         gt = gt.transpose(-1, -2)
     d1, d2, _, _ = chamfer_forward(pred.contiguous(), gt.contiguous())
     return (d1.mean(dim=1) + d2.mean(dim=1)).cpu().tolist()
+
+
+def emd_approx(xyz1: torch.Tensor, xyz2: torch.Tensor) -> torch.Tensor:
+    """``emd_cuda.matchcost_forward(xyz1, xyz2, emd_cuda.approxmatch_forward(xyz1, xyz2))`` without the match matrix:
+    xyz1 [B,n,3], xyz2 [B,m,3] -> un-normalised cost [B] (metrics/PyTorchEMD/cuda/emd_kernel.cu:33-165, 211-253)."""
+    _chk(xyz1, torch.float32, "xyz1", 3)
+    _chk(xyz2, torch.float32, "xyz2", 3)
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    cost = torch.empty((B,), dtype=torch.float32, device=dev)
+    scratch = torch.empty((B * (3 * n + 2 * m),), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_emd_approx", _ptr(xyz1), _ptr(xyz2), B, n, m, _ptr(cost), _ptr(scratch), _stream())
+    return cost
+
+
+def earth_mover_distance_nograd(xyz1: torch.Tensor, xyz2: torch.Tensor, transpose: bool = True) -> torch.Tensor:
+    """metrics/PyTorchEMD/emd_nograd.py:19-44: approximate EMD / N; inputs [B,3,N] (transpose=True) or [B,N,3]."""
+    if xyz1.dim() == 2:
+        xyz1 = xyz1.unsqueeze(0)
+    if xyz2.dim() == 2:
+        xyz2 = xyz2.unsqueeze(0)
+    if transpose:
+        xyz1 = xyz1.transpose(1, 2)
+        xyz2 = xyz2.transpose(1, 2)
+    assert xyz1.shape[-1] == 3, f"require it to be B,N,3; get: {xyz1.shape}"
+    return emd_approx(xyz1.contiguous(), xyz2.contiguous()) / float(xyz1.shape[1])
+
+
+def knn_points(queries: torch.Tensor, points: torch.Tensor, K: int, return_dist: bool = False):
+    """K nearest ``points [N,3]`` of every ``queries [Q,3]`` row, ascending squared distance, ties by lower index
+    (``pytorch3d.ops.knn_points(..., return_sorted=True)`` as used at denoise_object.py:90-91) -> idx int32 [Q,K]."""
+    _chk(queries, torch.float32, "queries", 2)
+    _chk(points, torch.float32, "points", 2)
+    Q, N = queries.shape[0], points.shape[0]
+    dev = points.device
+    idx = torch.empty((Q, K), dtype=torch.int32, device=dev)
+    dist = torch.empty((Q, K), dtype=torch.float32, device=dev) if return_dist else None
+    with torch.cuda.device(dev):
+        call("p2pb_knn_points", _ptr(queries), _ptr(points), Q, N, int(K), _ptr(idx), _ptr(dist), _stream())
+    return (idx, dist) if return_dist else idx
+

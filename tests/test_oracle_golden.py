@@ -136,3 +136,23 @@ def test_oracle_damped_loop_matches_reference_loop(golden_dir):
     sd = OM.make_state_dict(cfg, seed=0, head_scale=float(z["head_scale"]))
     out = OM.sample(sd, cfg, torch.from_numpy(z["x_start"]), None, steps=int(z["T"]), log_count=int(z["T"]))
     np.testing.assert_allclose(out["x_chain"].numpy(), z["x_chain"], atol=1e-5, rtol=0)
+
+
+def test_oracle_knn_matches_stable_sort():
+    """oracle kNN (pytorch3d.ops.knn_points contract: squared L2, ascending, ties by lower index) == numpy stable
+    argsort of the same fp32 distances, including a lattice cloud where most distances tie."""
+    g = torch.Generator().manual_seed(4)
+    for pts in (torch.randn(700, 3, generator=g), torch.randint(0, 4, (500, 3), generator=g).float() * 0.25):
+        q = pts[::97].contiguous()
+        idx, dist = OO.knn_points(q, pts, 64)
+        for i in range(q.shape[0]):
+            np.testing.assert_array_equal(idx[i].numpy(), np.argsort(_sq(q[i], pts), kind="stable")[:64])
+            assert np.all(np.diff(dist[i].numpy()) >= 0)
+
+
+def _sq(q, pts):
+    """fp32 squared distance with the oracle's contraction order: t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)."""
+    d = (pts - q).numpy().astype(np.float32)
+    t = (d[:, 1] * d[:, 1]).astype(np.float32)
+    t = (d[:, 0].astype(np.float64) * d[:, 0].astype(np.float64) + t.astype(np.float64)).astype(np.float32)
+    return (d[:, 2].astype(np.float64) * d[:, 2].astype(np.float64) + t.astype(np.float64)).astype(np.float32)

@@ -1,7 +1,7 @@
 #!/bin/bash
-# engine + gemm tests, halo sweep, bench line
+# all gpu tests, gemm bench, bench line
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
-timeout 300 python tools/bench_halo.py > gpurun_out/bench_halo.log 2>&1; cut -c1-75 gpurun_out/bench_halo.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-400 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 300 python tools/bench_gemm.py > gpurun_out/bench_gemm.log 2>&1; grep -v experiments gpurun_out/bench_gemm.log | cut -c1-150
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-300 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
