@@ -27,6 +27,9 @@ def lib() -> ctypes.CDLL:
                 "(or __graft_entry__.build()). There is no CPU fallback.")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.p2pb_last_error.restype = ctypes.c_char_p
+        kb = os.environ.get("P2PB_SMEM_KB")
+        if kb:
+            check(_lib.p2pb_set_smem_budget_kb(int(kb)), "p2pb_set_smem_budget_kb")
     return _lib
 
 

@@ -35,3 +35,17 @@ int p2pb_num_sms()
 }
 
 P2PB_API int p2pb_device_sm_count() { return p2pb_num_sms(); }
+
+// Dynamic shared memory the persistent tensor-core kernels may take per CTA (KiB).  Anything left of the SM's 228 KiB
+// is what lets small kernels of the other half-batch chain (DualEngine) become resident next to them.
+int g_p2pb_smem_budget_kb = 227;
+P2PB_API int p2pb_set_smem_budget_kb(int kb)
+{
+    if (kb < 128 || kb > 227) {
+        p2pb_set_error("smem budget %d KiB out of range [128, 227]", kb);
+        return P2PB_ERR_INVALID;
+    }
+    g_p2pb_smem_budget_kb = kb;
+    return P2PB_OK;
+}
+

@@ -44,7 +44,18 @@ extern unsigned long long g_p2pb_launches;  // kernels launched through this lib
         }                                                                                     \
     } while (0)
 
+// Small kernels must be able to share an SM with the persistent tensor-core kernels (which hold ~220 KB of dynamic shared
+// memory per SM): an SM's shared-memory carve-out can only change while the SM is idle, so a kernel that prefers the
+// default (L1-heavy) carve-out waits for the big kernel to drain instead of running next to it.  Host-side and
+// idempotent; the hot path replays a CUDA graph, so it costs nothing there.
+static inline void p2pb_prefer_max_smem(const void* kernel)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 static inline int p2pb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+extern int g_p2pb_smem_budget_kb;  // see p2pb_set_smem_budget_kb (abi_common.cu)
 
 // number of SMs of the current device (148 on B200), cached
 int p2pb_num_sms();

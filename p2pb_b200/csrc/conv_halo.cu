@@ -451,7 +451,7 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
     a.X = X; a.bias = bias; a.D = D; a.stats = stats;
     const int sub_bytes = 3 * Cout * HBK * 4;
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
-    const int budget = 225 * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
+    const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
     a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
     if (g_halo_w_stages >= 2) {

@@ -39,6 +39,7 @@ P2PB_API int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N,
 {
     const long long total = (long long)B * N;
     if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)coords_to_rows_kernel);
     coords_to_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(coords, rows, N, ld, col0, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -104,6 +105,7 @@ P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* t
     const long long total4 = (long long)B * r3 * (Cp / 4);
     P2PB_CHECK_U32(total4, "voxelize_cl");
     if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)voxelize_cl_kernel);
     voxelize_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
                                                                                Cp, N, r3, total4);
     P2PB_LAUNCH_OK();
@@ -196,6 +198,7 @@ P2PB_API int p2pb_gn_coef(const float* stats, int tiles, int B, int C, int group
     P2PB_CHECK_ARG(groups > 0 && C % groups == 0 && cpg <= 128 && (cpg & (cpg - 1)) == 0,
                    "gn_coef: C=%d groups=%d (group width must be a power of two <= 128)", C, groups);
     if (B == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)gn_coef_kernel);
     gn_coef_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(stats, tiles, C, groups, (float)rows_per_sample, gamma, beta, emd,
                                                                 ld_emd, emd_off, eps, coefA, coefB, ymean);
     P2PB_LAUNCH_OK();
@@ -223,6 +226,7 @@ __global__ void col_stats_kernel(const float* __restrict__ x, int ld, int rows, 
 P2PB_API int p2pb_col_stats(const float* x, int ld, int B, int rows, int C, float* out, void* stream)
 {
     if (B == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)col_stats_kernel);
     col_stats_kernel<<<dim3(p2pb_cdiv(C, 128), B), 128, 0, (cudaStream_t)stream>>>(x, ld, rows, C, out);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -250,22 +254,36 @@ __device__ __forceinline__ float4 affine4(float4 x, float4 a, float4 b)
     return y;
 }
 
+// 4 float4 per thread (all loads issued before the first use): the pass is HBM-bound and one 16-byte load per thread
+// does not keep enough bytes in flight (measured 4.0 TB/s with 1, see profiles/)
 template <int ACT>
 __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                          const float* __restrict__ Bc, int rows_per_sample, int C,
                                                          float* __restrict__ out, int ldo, unsigned total4)
 {
-    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total4) return;
     const unsigned C4 = C >> 2;
-    const unsigned mu = e / C4;
-    const int c = (int)(e - mu * C4) * 4;
-    const size_t m = mu;
-    const size_t b = mu / (unsigned)rows_per_sample;
-    const float4 xv = *reinterpret_cast<const float4*>(x + m * ldx + c);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(A + b * C + c));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c));
-    *reinterpret_cast<float4*>(out + m * ldo + c) = affine4<ACT>(xv, a, bb);
+    const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    float4 xv[4], a[4], bb[4];
+    size_t m[4];
+    int c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned e = e0 + k * blockDim.x;
+        if (e < total4) {
+            const unsigned mu = e / C4;
+            c[k] = (int)(e - mu * C4) * 4;
+            m[k] = mu;
+            const size_t b = mu / (unsigned)rows_per_sample;
+            xv[k] = *reinterpret_cast<const float4*>(x + m[k] * ldx + c[k]);
+            a[k] = __ldg(reinterpret_cast<const float4*>(A + b * C + c[k]));
+            bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned e = e0 + k * blockDim.x;
+        if (e < total4) *reinterpret_cast<float4*>(out + m[k] * ldo + c[k]) = affine4<ACT>(xv[k], a[k], bb[k]);
+    }
 }
 
 template <int ACT>
@@ -350,6 +368,7 @@ P2PB_API int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const
     const int total = B * C;
     if (total == 0) return P2PB_OK;
     P2PB_CHECK_ARG(tiles > 0, "gmax_minmax: tiles must be positive");
+    p2pb_prefer_max_smem((const void*)gmax_minmax_kernel);
     gmax_minmax_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(colmm, tiles, C, A, Bc, act, gmax, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -371,13 +390,14 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     const int B = M / rows_per_sample;
     if (gmax != nullptr) {
         P2PB_CHECK_ARG(pool == 1, "affine_act: gmax and pool are exclusive");
+        p2pb_prefer_max_smem((const void*)fill_kernel);
         fill_kernel<<<p2pb_cdiv((long long)B * C, 256), 256, 0, s>>>(gmax, -INFINITY, (long long)B * C);
         P2PB_LAUNCH_OK();
         int rows_per_cta = p2pb_cdiv(rows_per_sample, p2pb_cdiv(4 * p2pb_num_sms(), B));
         if (rows_per_cta < 8) rows_per_cta = 8;
         dim3 grid(p2pb_cdiv(rows_per_sample, rows_per_cta), B);
-        if (act) affine_act_gmax_kernel<1><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax);
-        else affine_act_gmax_kernel<0><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax);
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_gmax_kernel<1>); affine_act_gmax_kernel<1><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_gmax_kernel<0>); affine_act_gmax_kernel<0><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax); }
         P2PB_LAUNCH_OK();
         return P2PB_OK;
     }
@@ -385,13 +405,13 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     if (pool == 1) {
         const long long total4 = (long long)M * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act");
-        if (act) affine_act_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4);
-        else affine_act_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4);
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1>); affine_act_kernel<1><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0>); affine_act_kernel<0><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
     } else {
         const long long total4 = (long long)(M / pool) * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act(pool)");
-        if (act) affine_act_pool_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4);
-        else affine_act_pool_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4);
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<1>); affine_act_pool_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<0>); affine_act_pool_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
     }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -465,6 +485,7 @@ P2PB_API int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, cons
     const long long total4 = (long long)B * N * (C / 4);
     P2PB_CHECK_U32(total4, "devox_cl");
     if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)devox_cl_kernel);
     devox_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(ncoords, raw, ldg, A, Bc, se, praw, ldp, pA, pB, out,
                                                                             ldo, C, N, r, total4);
     P2PB_LAUNCH_OK();
@@ -511,6 +532,7 @@ P2PB_API int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* co
     const long long total = (long long)B * M * U * (Cf / 4 + 1);
     P2PB_CHECK_U32(total, "group_rows");
     if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)group_rows_kernel);
     group_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
                                                                              U, total);
     P2PB_LAUNCH_OK();
@@ -555,6 +577,7 @@ P2PB_API int p2pb_interp_rows(const float* f, int ldf, const int* idx, const flo
     const long long total4 = (long long)B * N * (C / 4);
     P2PB_CHECK_U32(total4, "interp_rows");
     if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)interp_rows_kernel);
     interp_rows_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(f, ldf, idx, w, out, ldo, C, N, M, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -594,6 +617,7 @@ P2PB_API int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw
 {
     const long long total = (long long)B * O;
     if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)linear_small_kernel);
     linear_small_kernel<<<p2pb_cdiv(total * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, W, ldw, bias, K, O, act, out, ldo,
                                                                                     total);
     P2PB_LAUNCH_OK();
@@ -648,6 +672,7 @@ P2PB_API int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N
 {
     P2PB_CHECK_ARG(N > 0 && N <= 64, "attention_small: N=%d tokens (bottleneck only, <= 64)", N);
     if (B == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)attention_small_kernel);
     attention_small_kernel<<<B * H, dim3(32, 32), 0, (cudaStream_t)stream>>>(qkv, ldq, H, N, out, ldo);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -683,6 +708,7 @@ P2PB_API int p2pb_bridge_update(const float* xt, const float* eps, int lde, cons
 {
     const long long total = (long long)B * N;
     if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)bridge_update_kernel);
     bridge_update_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, eps, lde, coef, clip, xt_next, pred_x0, N,
                                                                                 total);
     P2PB_LAUNCH_OK();
@@ -755,6 +781,7 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
     const long long total4 = (long long)B * r * r * r * (Cp / 4);
     P2PB_CHECK_U32(total4, "voxelize_padded");
     if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)voxelize_padded_kernel);
     voxelize_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
                                                                                    Cp, N, r, total4);
     P2PB_LAUNCH_OK();
@@ -826,6 +853,7 @@ P2PB_API int p2pb_voxelize_padded_sparse(const float* feat, int ldf, int Cf, con
     const long long total4 = (long long)B * N * (Cp / 4);
     P2PB_CHECK_U32(total4, "voxelize_padded_sparse");
     if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)voxelize_sparse_kernel);
     voxelize_sparse_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, ind, start, cnt,
                                                                                    out, Cp, N, r, clear, total4);
     P2PB_LAUNCH_OK();
@@ -837,18 +865,31 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
                                                                 const float* __restrict__ Bc, int C, float* __restrict__ out,
                                                                 int r, unsigned total4)
 {
-    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total4) return;
     const unsigned r3 = r * r * r;
     const unsigned C4 = C >> 2;
-    const unsigned vrow = e / C4;
-    const int c = (int)(e - vrow * C4) * 4;
-    const int b = (int)(vrow / r3);
-    const int v = (int)(vrow - (unsigned)b * r3);
-    const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)vrow * ldx + c);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c));
-    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * C + c) = affine4<1>(xv, a, bb);
+    const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    float4 xv[4], a[4], bb[4];
+    size_t orow[4];
+    int c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {      // 4 float4 per thread, loads first (see affine_act_kernel)
+        const unsigned e = e0 + k * blockDim.x;
+        if (e < total4) {
+            const unsigned vrow = e / C4;
+            c[k] = (int)(e - vrow * C4) * 4;
+            const int b = (int)(vrow / r3);
+            const int v = (int)(vrow - (unsigned)b * r3);
+            orow[k] = padded_row(b, v, r);
+            xv[k] = *reinterpret_cast<const float4*>(x + (size_t)vrow * ldx + c[k]);
+            a[k] = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c[k]));
+            bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned e = e0 + k * blockDim.x;
+        if (e < total4) *reinterpret_cast<float4*>(out + orow[k] * C + c[k]) = affine4<1>(xv[k], a[k], bb[k]);
+    }
 }
 
 P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, float* out,
@@ -858,7 +899,8 @@ P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, con
     const long long total4 = (long long)B * r * r * r * (C / 4);
     P2PB_CHECK_U32(total4, "affine_act_padded");
     if (total4 == 0) return P2PB_OK;
-    affine_act_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, r, total4);
+    p2pb_prefer_max_smem((const void*)affine_act_padded_kernel);
+    affine_act_padded_kernel<<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, r, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

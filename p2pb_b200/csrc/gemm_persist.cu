@@ -461,7 +461,7 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
 {
     using Cfg = PCfg<BN>;
     const int fixed = 1024 + Cfg::C_BYTES + Cfg::STAT_BYTES + 512;
-    int stages = (227 * 1024 - fixed) / (PA_STAGE + Cfg::B_STAGE);
+    int stages = (g_p2pb_smem_budget_kb * 1024 - fixed) / (PA_STAGE + Cfg::B_STAGE);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     a.stages = stages;

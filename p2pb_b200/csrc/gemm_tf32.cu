@@ -397,6 +397,7 @@ int launch_gemm(const CUtensorMap* maps, const GemmArgs& a, cudaStream_t s)
     }
     dim3 grid(a.n_total / BN, p2pb_cdiv(a.M, BM));
     P2PB_CHECK_ARG(grid.y <= 65535u, "gemm: M=%d needs %u row tiles (> 65535): split the batch", a.M, grid.y);
+    p2pb_prefer_max_smem((const void*)gemm_tf32_kernel<BN>);
     gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], a, stages);
     P2PB_LAUNCH_OK();
     return P2PB_OK;

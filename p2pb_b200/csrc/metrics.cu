@@ -72,9 +72,11 @@ P2PB_API int p2pb_nm_distance(const float* xyz1, const float* xyz2, int B, int n
     int seg_len = p2pb_cdiv(m, segs);
     seg_len = p2pb_cdiv(seg_len, NM_TILE) * NM_TILE;
     segs = p2pb_cdiv(m, seg_len);
+    p2pb_prefer_max_smem((const void*)nm_distance_kernel);
     nm_distance_kernel<<<dim3(gx, B, segs), 128, 0, s>>>(xyz1, xyz2, n, m, seg_len, scratch);
     P2PB_LAUNCH_OK();
     const long long total = (long long)B * n;
+    p2pb_prefer_max_smem((const void*)nm_unpack_kernel);
     nm_unpack_kernel<<<p2pb_cdiv(total, 256), 256, 0, s>>>(scratch, dist, idx, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -176,18 +178,23 @@ P2PB_API int p2pb_emd_approx(const float* xyz1, const float* xyz2, int B, int n,
     float* ratioR = remainR + (size_t)B * m;
     const float multiL = n >= m ? 1.f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.f;  // integer division, :38-43
     const long long tl = (long long)B * n, tr = (long long)B * m;
+    p2pb_prefer_max_smem((const void*)emd_init_kernel);
     emd_init_kernel<<<p2pb_cdiv(tl > tr ? tl : tr, 256), 256, 0, s>>>(remainL, remainR, cost_row, n, m, multiL, multiR, tl, tr);
     P2PB_LAUNCH_OK();
     const dim3 gl(p2pb_cdiv(n, 8), B), gr(p2pb_cdiv(m, 8), B);
     for (int j = 7; j >= -2; --j) {
         const float level = j == -2 ? 0.f : -powf(4.0f, (float)j);
+        p2pb_prefer_max_smem((const void*)emd_pass_kernel<1>);
         emd_pass_kernel<1><<<gl, 256, 0, s>>>(xyz1, xyz2, n, m, level, remainR, remainL, ratioL, nullptr);
         P2PB_LAUNCH_OK();
+        p2pb_prefer_max_smem((const void*)emd_pass_kernel<2>);
         emd_pass_kernel<2><<<gr, 256, 0, s>>>(xyz2, xyz1, m, n, level, ratioL, remainR, ratioR, nullptr);
         P2PB_LAUNCH_OK();
+        p2pb_prefer_max_smem((const void*)emd_pass_kernel<3>);
         emd_pass_kernel<3><<<gl, 256, 0, s>>>(xyz1, xyz2, n, m, level, ratioR, remainL, ratioL, cost_row);
         P2PB_LAUNCH_OK();
     }
+    p2pb_prefer_max_smem((const void*)emd_cost_kernel);
     emd_cost_kernel<<<B, 256, 0, s>>>(cost_row, n, cost);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -337,6 +344,7 @@ P2PB_API int p2pb_knn_points(const float* queries, const float* pts, int Q, int 
         P2PB_CUDA_OK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         attr_set = true;
     }
+    p2pb_prefer_max_smem((const void*)knn_select_kernel);
     knn_select_kernel<<<Q, KNN_THREADS, smem, (cudaStream_t)stream>>>(queries, pts, N, K, Kp2, idx, dist);
     P2PB_LAUNCH_OK();
     return P2PB_OK;

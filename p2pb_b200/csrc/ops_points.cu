@@ -135,6 +135,7 @@ static int launch_fps_reg(const float* coords, int B, int N, int M, int* idx, fl
     const size_t smem = (size_t)3 * N * sizeof(float);
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(fps_reg_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p2pb_prefer_max_smem((const void*)fps_reg_kernel<P, T>);
     fps_reg_kernel<P, T><<<B, T, smem, s>>>(coords, N, M, idx, centers);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -157,6 +158,7 @@ P2PB_API int p2pb_furthest_point_sampling(const float* coords, int B, int N, int
     if (N <= 16384) return launch_fps_reg<16, 1024>(coords, B, N, M, idx, centers, s);
     P2PB_CHECK_ARG(scratch != nullptr, "fps: N=%d > 16384 needs a B*N float scratch buffer", N);
     P2PB_CHECK_ARG(centers == nullptr, "fps: fused centre gather only for N <= 16384");
+    p2pb_prefer_max_smem((const void*)fps_global_kernel);
     fps_global_kernel<<<B, 1024, 0, s>>>(coords, N, M, scratch, idx);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -185,6 +187,7 @@ P2PB_API int p2pb_gather_features(const float* feat, const int* idx, float* out,
     P2PB_CHECK_ARG(B >= 0 && C > 0 && N > 0 && M >= 0, "gather: bad sizes");
     if (B == 0 || M == 0) return P2PB_OK;
     dim3 grid(p2pb_cdiv(M, 256), C < 64 ? C : 64, B);
+    p2pb_prefer_max_smem((const void*)gather_cf_kernel);
     gather_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, idx, out, C, N, M);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -249,6 +252,7 @@ P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, i
     // enough CTAs per patch to fill the chip, but not so many that staging the points dominates
     const int want = p2pb_cdiv(2 * p2pb_num_sms(), B);
     if (gx > want) gx = want < 1 ? 1 : want;
+    p2pb_prefer_max_smem((const void*)ball_query_kernel<WARPS>);
     ball_query_kernel<WARPS><<<dim3(gx, B), WARPS * 32, smem, (cudaStream_t)stream>>>(centers, points, M, N, r2, U, out);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -327,6 +331,7 @@ P2PB_API int p2pb_three_nn(const float* points, const float* centers, int B, int
     P2PB_CHECK_ARG(smem <= 200 * 1024, "three_nn: M=%d too large for shared-memory staging", M);
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p2pb_prefer_max_smem((const void*)three_nn_kernel);
     three_nn_kernel<<<dim3(p2pb_cdiv(N, 256), B), 256, smem, (cudaStream_t)stream>>>(points, centers, N, M, idx, w);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -339,6 +344,7 @@ P2PB_API int p2pb_three_nn_interpolate(const float* points, const float* centers
     if (rc != P2PB_OK || B == 0) return rc;
     P2PB_CHECK_ARG(C > 0, "three_nn_interpolate: bad C");
     dim3 grid(p2pb_cdiv(N, 256), C < 64 ? C : 64, B);
+    p2pb_prefer_max_smem((const void*)interp_cf_kernel);
     interp_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cfeat, idx, w, out, C, N, M);
     P2PB_LAUNCH_OK();
     return P2PB_OK;

@@ -148,6 +148,7 @@ static int launch_voxel_prep(const int* icoords, const float* fcoords, int B, in
     const size_t smem = (size_t)Np2 * sizeof(unsigned);
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(voxel_prep_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p2pb_prefer_max_smem((const void*)voxel_prep_kernel<1024>);
     voxel_prep_kernel<1024><<<B, 1024, smem, s>>>(icoords, fcoords, N, Np2, r, normalize, eps, norm_coords, ind, order,
                                                   start, cnt);
     P2PB_LAUNCH_OK();
@@ -201,6 +202,7 @@ P2PB_API int p2pb_avg_voxelize(const float* feat, const int* coords, int B, int 
     if (rc != P2PB_OK || B == 0) return rc;
     const int r3 = r * r * r;
     dim3 grid(p2pb_cdiv(r3, 256), C < 32 ? C : 32, B);
+    p2pb_prefer_max_smem((const void*)voxelize_cf_kernel);
     voxelize_cf_kernel<<<grid, 256, 0, s>>>(feat, scratch_order, scratch_start, cnt, out, C, N, r3);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -271,6 +273,7 @@ P2PB_API int p2pb_trilinear_devoxelize(const float* coords, const float* grid, i
     P2PB_CHECK_ARG(B >= 0 && C > 0 && N > 0 && r > 0, "devoxelize: bad sizes");
     if (B == 0) return P2PB_OK;
     dim3 g(p2pb_cdiv(N, 256), C < 32 ? C : 32, B);
+    p2pb_prefer_max_smem((const void*)devox_cf_kernel);
     devox_cf_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(coords, grid, out, C, N, r);
     P2PB_LAUNCH_OK();
     return P2PB_OK;

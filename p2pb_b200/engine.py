@@ -632,15 +632,13 @@ class Engine:
                 xs_buf[li].copy_(xt)
                 li += 1
 
-    def sample(self, x1, x_cond, pairs, log_steps, clip):
-        """pairs = [(prev_step, step)] in sampling order -> (xs, pred_x0s) [B, log_count, 3, N], logged steps flipped
-        to ascending time like ``sample_ddpm`` (p2pb.py:215-262)."""
+    def prepare(self, x1, x_cond, pairs, log_steps):
+        """Upload the per-step host tables and this call's inputs into the static buffers -> (log_set, xs_buf, x0_buf)."""
         B, N, E = self.B, self.N, self.E
         p = self.p2pb
         T = len(pairs)
         log_set = set(log_steps)
         n_log = sum(1 for prev, _ in pairs if prev in log_set)
-        key = (tuple(pairs), tuple(sorted(log_set)), bool(clip))
         # per-step host tables: sinusoid of the noise level, posterior scalars (fp32, same op order as p_posterior)
         sin = self.buf("temb.sin", T, E)
         coef = self.buf("coef", T, 3)
@@ -648,12 +646,19 @@ class Engine:
         coef_h = torch.tensor([p.posterior_coefs(prev, step) for prev, step in pairs], dtype=torch.float32)
         sin.copy_(sin_h)
         coef.copy_(coef_h.to(self.dev))
-        xt = self.buf("xt", B, 3, N)
-        xt.copy_(x1.detach().to(self.dev, torch.float32))
+        self.buf("xt", B, 3, N).copy_(x1.detach().to(self.dev, torch.float32))
         if x_cond is not None:
             self.prepare_cond(x_cond.detach().to(self.dev, torch.float32))
         xs_buf = self.buf(f"xs{n_log}", n_log, B, 3, N)
         x0_buf = self.buf(f"x0s{n_log}", n_log, B, 3, N)
+        return log_set, xs_buf, x0_buf
+
+    def sample(self, x1, x_cond, pairs, log_steps, clip):
+        """pairs = [(prev_step, step)] in sampling order -> (xs, pred_x0s) [B, log_count, 3, N], logged steps flipped
+        to ascending time like ``sample_ddpm`` (p2pb.py:215-262)."""
+        log_set, xs_buf, x0_buf = self.prepare(x1, x_cond, pairs, log_steps)
+        xt = self.buf("xt", self.B, 3, self.N)
+        key = (tuple(pairs), tuple(sorted(log_set)), bool(clip))
         if os.environ.get("P2PB_NO_GRAPH"):     # debugging aid: same kernels, no graph capture
             self._run_loop(pairs, log_set, clip, xs_buf, x0_buf)
             xs = torch.flip(xs_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
@@ -678,13 +683,94 @@ class Engine:
         return xs, x0s
 
 
-def get_engine(p2pb, net, x_shape, cond_shape) -> Engine:
+class DualEngine:
+    """Two half-batch engines whose T-step loops run as two INDEPENDENT chains on two streams inside one CUDA graph.
+
+    Patches never interact (GroupNorm / SE / attention are per sample), so the two halves need no synchronisation
+    until the end of the call.  The evaluation is a strict chain of ~210 kernels of which ~90 are tiny, latency-bound
+    launches (GroupNorm coefficients, per-sample linears, FPS, ...) that leave the GPU nearly idle; the big tensor-core
+    kernels are persistent one-CTA-per-SM kernels that cannot overlap each other.  With two chains the small kernels of
+    one half run in the shadow of the other half's convolutions / GEMMs."""
+
+    dtype_name = Engine.dtype_name
+
+    def __init__(self, p2pb, net, B: int, N: int, F: int):
+        assert B % 2 == 0
+        self.B, self.N, self.F = B, N, F
+        self.halves = [Engine(p2pb, net, B // 2, N, F), Engine(p2pb, net, B // 2, N, F)]
+        self.dev = self.halves[0].dev
+        self._graphs: Dict[tuple, tuple] = {}
+        self._stream2 = torch.cuda.Stream(device=self.dev)
+        self.kernels_per_sample = 0
+
+    def _run_both(self, pairs, prep, clip):
+        """Fork: half 0 on the current stream, half 1 on the second stream; join."""
+        cur = torch.cuda.current_stream()
+        self._stream2.wait_stream(cur)
+        self.halves[0]._run_loop(pairs, prep[0][0], clip, prep[0][1], prep[0][2])
+        with torch.cuda.stream(self._stream2):
+            self.halves[1]._run_loop(pairs, prep[1][0], clip, prep[1][1], prep[1][2])
+        cur.wait_stream(self._stream2)
+
+    def sample(self, x1, x_cond, pairs, log_steps, clip):
+        h = self.B // 2
+        parts = [(x1[:h], None if x_cond is None else x_cond[:h]), (x1[h:], None if x_cond is None else x_cond[h:])]
+        prep = [e.prepare(x, c, pairs, log_steps) for e, (x, c) in zip(self.halves, parts)]
+        key = (tuple(pairs), tuple(sorted(prep[0][0])), bool(clip))
+        if os.environ.get("P2PB_NO_GRAPH"):
+            self._run_both(pairs, prep, clip)
+        else:
+            two_graphs = os.environ.get("P2PB_DUAL_MODE", "") == "2graphs"
+            if key not in self._graphs:
+                l0 = launch_count()
+                self._run_both(pairs, prep, clip)         # eager first run: allocates every buffer
+                self.kernels_per_sample = launch_count() - l0
+                torch.cuda.synchronize(self.dev)
+                for e, (x, c) in zip(self.halves, parts):
+                    e.buf("xt", h, 3, self.N).copy_(x.detach().to(self.dev, torch.float32))
+                if two_graphs:
+                    gs = []
+                    for e, pr in zip(self.halves, prep):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            e._run_loop(pairs, pr[0], clip, pr[1], pr[2])
+                        gs.append(g)
+                    self._graphs[key] = tuple(gs)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run_both(pairs, prep, clip)
+                    self._graphs[key] = (g,)
+                for e, (x, c) in zip(self.halves, parts):
+                    e.buf("xt", h, 3, self.N).copy_(x.detach().to(self.dev, torch.float32))
+            gs = self._graphs[key]
+            if len(gs) == 1:
+                gs[0].replay()
+            else:
+                cur = torch.cuda.current_stream()
+                if getattr(self, "_stream1", None) is None:
+                    self._stream1 = torch.cuda.Stream(device=self.dev)
+                for st, g in zip((self._stream1, self._stream2), gs):
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        g.replay()
+                for st in (self._stream1, self._stream2):
+                    cur.wait_stream(st)
+        xs = torch.cat([torch.flip(p[1].permute(1, 0, 2, 3), dims=(1,)) for p in prep], 0)
+        x0s = torch.cat([torch.flip(p[2].permute(1, 0, 2, 3), dims=(1,)) for p in prep], 0)
+        return xs, x0s
+
+
+def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False):
+    """Engine for (net, B, N, F), built once.  allow_dual (the sampling loop): batches of >= 16 patches are split into
+    two half-batch chains (DualEngine) unless P2PB_DUAL=0."""
     B, _, N = x_shape
     F = 0 if cond_shape is None else cond_shape[1]
-    key = (id(net), B, N, F)
+    dual = allow_dual and B >= 16 and B % 2 == 0 and os.environ.get("P2PB_DUAL", "1") != "0"
+    key = (id(net), B, N, F, dual)
     eng = p2pb._engines.get(key)
     if eng is None:
-        eng = Engine(p2pb, net, B, N, F)
+        eng = DualEngine(p2pb, net, B, N, F) if dual else Engine(p2pb, net, B, N, F)
         p2pb._engines[key] = eng
     p2pb.last_engine = eng
     return eng

@@ -167,7 +167,7 @@ class P2PB(nn.Module):
         if backend == "engine" and self.ot_ode and self.objective == "pred_noise":
             from .engine import get_engine
 
-            eng = get_engine(self, net, x1.shape, None if x_cond is None else x_cond.shape)
+            eng = get_engine(self, net, x1.shape, None if x_cond is None else x_cond.shape, allow_dual=True)
             xs, x0s = eng.sample(x1, x_cond, pairs, log_steps, clip_denoise)
         else:
             xt = x1.detach().to(self.device)
