@@ -110,6 +110,34 @@ __device__ __forceinline__ void h_umma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// ---- cta_group::2 (CTA pair, M = 256 = one tile per CTA) forms; bit 24 of a shared::cluster address selects the CTA in the
+// pair, clearing it addresses the leader's barrier (same convention as gemm_persist.cu)
+constexpr uint32_t H_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void h_tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void h_umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void h_umma_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)0x3)
+                 : "memory");
+}
+__device__ __forceinline__ void h_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void h_umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -143,12 +171,20 @@ __device__ __forceinline__ float h_colsum32(float (&v)[32], int lane)
     return v[0];
 }
 
+// PAIR: two CTAs of a cluster form a cta_group::2 pair.  Each MMA has M = 256 = one 128-row tile per CTA against the SAME
+// weights; CTA r keeps only weight rows [Cout/2 r, Cout/2 (r+1)) of every tap in its shared memory (the tensor core reads
+// the other half from the peer), so per SM the weight bytes fetched from L2, written to and read from shared memory halve.
+// At N = Cout <= 64 the shared-memory operand fetch is the binding resource (profiles/r01_ncu_conv.md), at Cout = 128
+// the L2 -> SM weight stream was.  The leader CTA issues all MMAs; both CTAs load their own windows / weight halves and
+// run their own epilogue.
+template <bool PAIR>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const HaloArgs a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int tap_bytes = a.cout * HBK * 4;             // one tap: [Cout][32] fp32, 128B-swizzled rows
+    constexpr int NC = PAIR ? 2 : 1;
+    const int tap_bytes = (a.cout / NC) * HBK * 4;      // one tap: [Cout (/2 in pair mode)][32] fp32, 128B-swizzled rows
     const int sub_bytes = 3 * tap_bytes;                // sub-slab: the 3 dz-taps of one (dx, chunk, dy)
     const int a_stage_bytes = a.W * 128;                // W rows x 32 channels (one 128-byte swizzle span per row)
     const int a_stage_stride = (a_stage_bytes + 1023) & ~1023;
@@ -165,6 +201,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][cout][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank = 0;
+    if (PAIR) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        h_cluster_sync();
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -179,24 +220,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         }
         for (int h = 0; h < 2; ++h) {
             h_mbar_init(h_smem_u32(&tmem_full[h]), 1);
-            h_mbar_init(h_smem_u32(&tmem_empty[h]), 4);   // one arrival per epilogue warp
+            h_mbar_init(h_smem_u32(&tmem_empty[h]), 4 * NC);   // one arrival per epilogue warp (of both CTAs in pair mode)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_ptr_smem)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_ptr_smem)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(h_smem_u32(tmem_ptr_smem)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) h_cluster_sync();       // the peer's barriers exist before anything is signalled across the pair
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_ptr_smem;
     const int nslabs = 3 * a.cin_chunks;
     // Balanced static schedule: CTA c owns the contiguous tile range [c*T/grid, (c+1)*T/grid) and walks it in units of up
     // to G tiles, so no CTA gets more than ceil(T/grid) tiles (a unit-granular round-robin loses up to G-1 tile-times).
-    const int tile_begin = (int)(((long long)a.total_tiles * blockIdx.x) / gridDim.x);
-    const int tile_end = (int)(((long long)a.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+    // (pair mode: the range belongs to the cluster; slot g of a unit is tile tile0 + 2g + rank, and when the range is odd
+    // the last slot of CTA 1 is a dummy that recomputes tile0 and stores nothing)
+    const int n_owner = (int)gridDim.x / NC, owner = (int)blockIdx.x / NC;
+    const int tile_begin = (int)(((long long)a.total_tiles * owner) / n_owner);
+    const int tile_end = (int)(((long long)a.total_tiles * (owner + 1)) / n_owner);
     // Persistent CTA: work units of G tiles, unit u of this CTA accumulates in TMEM half (u & 1) so that the epilogue of
     // one unit overlaps the mainloop of the next (tmem_full / tmem_empty hand-off per half).
     const int half_cols = a.halves == 2 ? 256 : 0;
@@ -206,20 +257,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         if (h_elect_one()) {
             int ast = 0;
             uint32_t aph = 0;
-            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G) {
-                const int ntiles = min(a.G, tile_end - tile0);
+            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += NC * a.G) {
+                const int ntiles = min(a.G, (tile_end - tile0 + NC - 1) / NC);
                 for (int sl = 0; sl < nslabs; ++sl) {
                     const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
                     for (int g = 0; g < ntiles; ++g) {
-                        const int tile = tile0 + g;
+                        int tile = tile0 + NC * g + (int)rank;
+                        if (tile >= tile_end) tile = tile0;       // dummy slot of an odd range (pair mode)
                         const int b = tile / a.tiles_per_sample;
                         const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * HBM;
                         const long long qs = (long long)q0 + (long long)(dx - 1) * a.P2 - (a.P + 1);  // window start row (>= 0)
                         h_mbar_wait(h_smem_u32(&a_empty[ast]), aph ^ 1u);
-                        const uint32_t fb = h_smem_u32(&a_full[ast]);
-                        h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
-                        h_tma_load_2d(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * HBK,
-                                      (int)((long long)b * a.P3 + qs));
+                        if (!PAIR) {
+                            const uint32_t fb = h_smem_u32(&a_full[ast]);
+                            h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
+                            h_tma_load_2d(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * HBK,
+                                          (int)((long long)b * a.P3 + qs));
+                        } else {
+                            // both windows of the pair complete on the LEADER's barrier, armed with the bytes of both
+                            const uint32_t fb = h_smem_u32(&a_full[ast]) & H_PEER_MASK;
+                            if (rank == 0) h_mbar_expect_tx(fb, (uint32_t)(2 * a_stage_bytes));
+                            h_tma_load_2d_pair(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * HBK,
+                                               (int)((long long)b * a.P3 + qs));
+                        }
                         if (++ast == a.a_stages) {
                             ast = 0;
                             aph ^= 1u;
@@ -233,16 +293,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         if (h_elect_one()) {
             int wst = 0;
             uint32_t wph = 0;
-            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G) {
+            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += NC * a.G) {
                 for (int sl = 0; sl < nslabs; ++sl) {
                     const int dx = sl / a.cin_chunks, kc = sl - dx * a.cin_chunks;
                     for (int dy = 0; dy < 3; ++dy) {
                         h_mbar_wait(h_smem_u32(&w_empty[wst]), wph ^ 1u);
-                        const uint32_t fb = h_smem_u32(&w_full[wst]);
-                        h_mbar_expect_tx(fb, (uint32_t)sub_bytes);
-                        for (int dz = 0; dz < 3; ++dz)
-                            h_tma_load_2d(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
-                                          ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * HBK, 0);
+                        if (!PAIR) {
+                            const uint32_t fb = h_smem_u32(&w_full[wst]);
+                            h_mbar_expect_tx(fb, (uint32_t)sub_bytes);
+                            for (int dz = 0; dz < 3; ++dz)
+                                h_tma_load_2d(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
+                                              ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * HBK, 0);
+                        } else {
+                            // this CTA's half of the output channels of every tap; completes on the leader's barrier
+                            const uint32_t fb = h_smem_u32(&w_full[wst]) & H_PEER_MASK;
+                            if (rank == 0) h_mbar_expect_tx(fb, (uint32_t)(2 * sub_bytes));
+                            for (int dz = 0; dz < 3; ++dz)
+                                h_tma_load_2d_pair(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
+                                                   ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * HBK, (int)rank * (a.cout / 2));
+                        }
                         if (++wst == a.w_stages) {
                             wst = 0;
                             wph ^= 1u;
@@ -256,8 +325,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         // At N <= 64 one tcgen05.mma executes in ~49 cycles, so the issue path itself is on the critical path: the loop
         // below keeps per-MMA work to two 32-bit adds (descriptor low words; the high word is a constant) and runs in a
         // single elected thread, so there is no per-step warp re-convergence.
-        if (h_elect_one()) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)(HBM >> 4) << 24);
+        if ((!PAIR || rank == 0) && h_elect_one()) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)((NC * HBM) >> 4) << 24);
             const uint32_t tap_step = (uint32_t)(tap_bytes >> 4);
             const uint32_t sA_lo = (h_smem_u32(sA) & 0x3ffff) >> 4, sW_lo = (h_smem_u32(sW) & 0x3ffff) >> 4;
             const uint32_t a_stride_lo = (uint32_t)(a_stage_stride >> 4), w_stride_lo = (uint32_t)(sub_bytes >> 4);
@@ -266,11 +335,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             uint32_t wph = 0;
             int ast0 = 0;          // ring stage of the current slab's first window
             uint32_t aph0 = 0;     // and its phase
-            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G, ++it_unit) {
-                const int ntiles = min(a.G, tile_end - tile0);
+            for (int tile0 = tile_begin; tile0 < tile_end; tile0 += NC * a.G, ++it_unit) {
+                const int ntiles = min(a.G, (tile_end - tile0 + NC - 1) / NC);
                 const int h = a.halves == 2 ? (it_unit & 1) : 0;
                 const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
-                h_mbar_wait(h_smem_u32(&tmem_empty[h]), (use & 1u) ^ 1u);     // epilogue has drained this half
+                h_mbar_wait(h_smem_u32(&tmem_empty[h]), (use & 1u) ^ 1u);     // epilogue(s) have drained this half
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t dcol0 = tmem_base + (uint32_t)(h * half_cols);
                 for (int sl = 0; sl < nslabs; ++sl) {
@@ -297,19 +366,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                             for (int dz = 0; dz < 3; ++dz) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    if (j < nj)
-                                        h_umma_tf32(dcol, DESC_HI | (uint64_t)(a_lo + (uint32_t)(dz * 8 + j * 2)),
-                                                    DESC_HI | (uint64_t)(b_lo + (uint32_t)dz * tap_step + (uint32_t)(j * 2)), idesc,
-                                                    (dz | j) != 0 ? 1u : first);
+                                    if (j < nj) {
+                                        const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(dz * 8 + j * 2));
+                                        const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)dz * tap_step + (uint32_t)(j * 2));
+                                        if (PAIR) h_umma_tf32_pair(dcol, ad, bd, idesc, (dz | j) != 0 ? 1u : first);
+                                        else h_umma_tf32(dcol, ad, bd, idesc, (dz | j) != 0 ? 1u : first);
+                                    }
                                 }
                             }
-                            if (dy == 2) h_umma_commit(h_smem_u32(&a_empty[st]));
+                            if (dy == 2) {
+                                if (PAIR) h_umma_commit_pair(h_smem_u32(&a_empty[st]));
+                                else h_umma_commit(h_smem_u32(&a_empty[st]));
+                            }
                             if (++st == a.a_stages) {
                                 st = 0;
                                 aph ^= 1u;
                             }
                         }
-                        h_umma_commit(h_smem_u32(&w_empty[wst]));
+                        if (PAIR) h_umma_commit_pair(h_smem_u32(&w_empty[wst]));
+                        else h_umma_commit(h_smem_u32(&w_empty[wst]));
                         if (++wst == a.w_stages) {
                             wst = 0;
                             wph ^= 1u;
@@ -320,7 +395,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         }
                     }
                 }
-                h_umma_commit(h_smem_u32(&tmem_full[h]));
+                if (PAIR) h_umma_commit_pair(h_smem_u32(&tmem_full[h]));
+                else h_umma_commit(h_smem_u32(&tmem_full[h]));
             }
         }
     } else {
@@ -328,18 +404,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         const int qd = warp & 3;
         const int r = a.r, r3 = r * r * r;
         int it_unit = 0;
-        for (int tile0 = tile_begin; tile0 < tile_end; tile0 += a.G, ++it_unit) {
-            const int ntiles = min(a.G, tile_end - tile0);
+        for (int tile0 = tile_begin; tile0 < tile_end; tile0 += NC * a.G, ++it_unit) {
+            const int ntiles = min(a.G, (tile_end - tile0 + NC - 1) / NC);
             const int h = a.halves == 2 ? (it_unit & 1) : 0;
             const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
             h_mbar_wait(h_smem_u32(&tmem_full[h]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int g = 0; g < ntiles; ++g) {
-                const int tile = tile0 + g;
+                const int tile = tile0 + NC * g + (int)rank;
+                const bool tile_ok = tile < tile_end;         // false only for the dummy slot of an odd range (pair mode)
                 const int b = tile / a.tiles_per_sample;
                 const int q = a.q_first + (tile - b * a.tiles_per_sample) * HBM + qd * 32 + lane;
                 const int x = q / a.P2, rem = q - x * a.P2, y = rem / a.P, z = rem - y * a.P;
-                const bool ok = q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
+                const bool ok = tile_ok && q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
                 const size_t v = (size_t)b * r3 + (size_t)(x - 1) * r * r + (size_t)(y - 1) * r + (size_t)(z - 1);
                 float* drow = a.D + v * a.ldd;
                 for (int c = 0; c < a.cout / 32; ++c) {
@@ -369,7 +446,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 if (a.stats != nullptr) {
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     const int t = threadIdx.x - 64;
-                    for (int n = t; n < a.cout; n += 128) {
+                    for (int n = t; tile_ok && n < a.cout; n += 128) {
                         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
@@ -385,14 +462,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             }
             // this half of TMEM may be overwritten by the MMA warp again
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_smem_u32(&tmem_empty[h])) : "memory");
+            if (lane == 0) {
+                if (PAIR) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(h_smem_u32(&tmem_empty[h]) & H_PEER_MASK) : "memory");
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_smem_u32(&tmem_empty[h])) : "memory");
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) h_cluster_sync();       // nobody leaves while the peer may still signal / read this CTA
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -417,9 +499,12 @@ P2PB_API int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int*
 // D: dense rows [B*r^3, ldd]; stats (optional): [B*tiles_per_sample, Cout, 2]
 // development aid (tools/bench_conv.py): override the pipeline shape; 0 = automatic
 static int g_halo_w_stages = 0, g_halo_a_stages = 0, g_halo_G = 0;
+static int g_halo_pair = 1;   // 1: cta_group::2 CTA pairs when there is enough work; 0: independent CTAs (p2pb_conv_halo_tune G < 0)
 P2PB_API int p2pb_conv_halo_tune(int w_stages, int a_stages, int G)
 {
-    g_halo_w_stages = w_stages; g_halo_a_stages = a_stages; g_halo_G = G;
+    g_halo_w_stages = w_stages; g_halo_a_stages = a_stages;
+    g_halo_pair = G < 0 ? 0 : 1;       // a negative G selects the un-paired kernel with |G| (0 = automatic) tiles per unit
+    g_halo_G = G < 0 ? (G == -1 ? 0 : -G) : G;
     return P2PB_OK;
 }
 
@@ -449,7 +534,9 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
     a.halves = a.G * Cout <= 256 ? 2 : 1;
     a.ldd = ldd;
     a.X = X; a.bias = bias; a.D = D; a.stats = stats;
-    const int sub_bytes = 3 * Cout * HBK * 4;
+    const int n_sms = p2pb_num_sms();
+    const bool pair = g_halo_pair && a.total_tiles >= 2 * n_sms && n_sms >= 2;
+    const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * HBK * 4;     // per CTA: pair mode keeps half of the output channels
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
     const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
@@ -475,7 +562,7 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
         P2PB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
         cuuint64_t dims[2] = {(cuuint64_t)27 * Cin, (cuuint64_t)Cout};
         cuuint64_t str[1] = {(cuuint64_t)27 * Cin * 4};
-        cuuint32_t box[2] = {HBK, (cuuint32_t)Cout};
+        cuuint32_t box[2] = {HBK, (cuuint32_t)(pair ? Cout / 2 : Cout)};
         cuuint32_t estr[2] = {1, 1};
         CUresult rc = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), dims, str, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -499,12 +586,29 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
     }
     static bool attr_set = false;
     if (!attr_set) {
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    int grid = p2pb_num_sms();
-    if (grid > a.total_tiles) grid = a.total_tiles;
-    conv_halo_kernel<<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_sms & ~1), 1, 1);
+        cfg.blockDim = dim3(HALO_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, mapW, mapX, a));
+    } else {
+        int grid = n_sms;
+        if (grid > a.total_tiles) grid = a.total_tiles;
+        conv_halo_kernel<false><<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
+    }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

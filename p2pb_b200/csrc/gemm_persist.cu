@@ -150,6 +150,45 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, float* v)
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// ---- cta_group::2 (CTA pair) forms.  The peer bit (bit 24) of a shared::cluster address selects the CTA inside the pair;
+// clearing it addresses the LEADER's (rank 0) copy of a barrier from either CTA.
+constexpr uint32_t P_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void p_tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void p_tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2,
+                                                   int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+// M = 256 across the pair: CTA r supplies A rows [128r, 128r+128) and B rows [N/2 r, N/2 (r+1)) from ITS shared memory (same
+// offsets in both CTAs) and receives D rows [128r, 128r+128) x N in ITS tensor memory.  Issued by the leader only.
+__device__ __forceinline__ void p_umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void p_umma_commit_pair_mc(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void p_mbar_arrive_cluster(uint32_t cluster_bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+
 __device__ __forceinline__ uint32_t p_cluster_ctarank()
 {
     uint32_t r;
@@ -182,8 +221,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stages = a.stages;
     uint8_t* sA = smem;
+    constexpr int B_STAGE = CL == 3 ? Cfg::B_STAGE / 2 : Cfg::B_STAGE;   // pair mode: each CTA stores only its half of the weight tile
     uint8_t* sB = sA + (size_t)stages * PA_STAGE;
-    uint8_t* sC = sB + (size_t)stages * Cfg::B_STAGE;
+    uint8_t* sC = sB + (size_t)stages * B_STAGE;
     float* s_stats = reinterpret_cast<float*>(sC + Cfg::C_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stats) + Cfg::STAT_BYTES);
     uint64_t* full_bar = bars;
@@ -193,10 +233,14 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     uint64_t* tempty = tfull + NACC;        // [NACC]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty + NACC);
 
+    // CL = 1: independent CTAs; 2: 2-CTA cluster, cta_group::1 MMAs, multicast weights; 3: CTA pair, cta_group::2 MMAs (M = 256)
+    constexpr bool PAIR = CL == 3;
+    constexpr int NCTA = CL == 1 ? 1 : 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CL > 1 ? p_cluster_ctarank() : 0u;
-    const int cluster_id = (int)blockIdx.x / CL;
-    const int n_clusters = (int)gridDim.x / CL;
+    const int cluster_id = (int)blockIdx.x / NCTA;
+    const int n_clusters = (int)gridDim.x / NCTA;
+    if (PAIR) p_cluster_sync();
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -204,19 +248,26 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapD) : "memory");
         for (int s = 0; s < stages; ++s) {
             p_mbar_init(p_smem_u32(&full_bar[s]), 1);
-            p_mbar_init(p_smem_u32(&empty_bar[s]), CL);     // one tcgen05.commit arrival per CTA of the cluster
+            p_mbar_init(p_smem_u32(&empty_bar[s]), CL == 2 ? 2 : 1);   // multicast mode: one tcgen05.commit arrival per CTA
         }
         for (int h = 0; h < NACC; ++h) {
             p_mbar_init(p_smem_u32(&tfull[h]), 1);
-            p_mbar_init(p_smem_u32(&tempty[h]), 8);         // one arrival per epilogue warp
+            p_mbar_init(p_smem_u32(&tempty[h]), PAIR ? 16 : 8);   // one arrival per epilogue warp (of both CTAs in pair mode)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p_smem_u32(tmem_ptr_smem)),
-                     "r"((uint32_t)Cfg::TM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p_smem_u32(tmem_ptr_smem)),
+                         "r"((uint32_t)Cfg::TM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(p_smem_u32(tmem_ptr_smem)),
+                         "r"((uint32_t)Cfg::TM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -232,7 +283,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const int sc0 = a.seg_chunks[0], sc1 = a.seg_chunks[1], sc2 = a.seg_chunks[2];
             for (int item = cluster_id; item < a.total_items; item += n_clusters) {
                 const int n_tile = item % a.n_tiles;
-                int m_tile = (item / a.n_tiles) * CL + (int)rank;
+                int m_tile = (item / a.n_tiles) * NCTA + (int)rank;
                 if (m_tile >= a.m_tiles) m_tile = a.m_tiles - 1;   // odd tail of a pair: redo a valid tile, epilogue skips it
                 const int m0 = m_tile * PBM, n0 = n_tile * BN;
                 int cb = 0, cx = 0, cy = 0;
@@ -245,12 +296,16 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 int seg = 0, seg_it = 0, tap = 0, kc = 0;
                 for (int it = 0; it < a.total_chunks; ++it) {
                     p_mbar_wait(p_smem_u32(&empty_bar[st]), ph ^ 1u);
-                    const uint32_t fb = p_smem_u32(&full_bar[st]);
-                    p_mbar_expect_tx(fb, PA_STAGE + Cfg::B_STAGE);
+                    // pair mode: every load of both CTAs signals the LEADER's full barrier, which the leader arms with the
+                    // bytes of both CTAs (2 A tiles + the two halves of the weight tile)
+                    const uint32_t fb = PAIR ? (p_smem_u32(&full_bar[st]) & P_PEER_MASK) : p_smem_u32(&full_bar[st]);
+                    if (!PAIR) p_mbar_expect_tx(fb, PA_STAGE + Cfg::B_STAGE);
+                    else if (rank == 0) p_mbar_expect_tx(fb, 2 * PA_STAGE + Cfg::B_STAGE);
                     const uint32_t dstA = p_smem_u32(sA + (size_t)st * PA_STAGE);
                     if (a.conv) {
                         const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
-                        p_tma_load_5d(dstA, &mapA0, fb, kc * PBK, dz, cy + dy, cx + dx, cb);
+                        if (PAIR) p_tma_load_5d_pair(dstA, &mapA0, fb, kc * PBK, dz, cy + dy, cx + dx, cb);
+                        else p_tma_load_5d(dstA, &mapA0, fb, kc * PBK, dz, cy + dy, cx + dx, cb);
                         if (++kc == a.cin_chunks) {
                             kc = 0;
                             ++tap;
@@ -261,15 +316,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                             ++seg;
                         }
                         const CUtensorMap* mp = seg == 0 ? &mapA0 : (seg == 1 ? &mapA1 : &mapA2);
-                        p_tma_load_2d(dstA, mp, fb, seg_it * PBK, m0);
+                        if (PAIR) p_tma_load_2d_pair(dstA, mp, fb, seg_it * PBK, m0);
+                        else p_tma_load_2d(dstA, mp, fb, seg_it * PBK, m0);
                         ++seg_it;
                     }
-                    const uint32_t dstB = p_smem_u32(sB + (size_t)st * Cfg::B_STAGE);
+                    const uint32_t dstB = p_smem_u32(sB + (size_t)st * B_STAGE);
                     if (CL == 1) {
                         p_tma_load_2d(dstB, &mapB, fb, it * PBK, n0);
-                    } else {
+                    } else if (CL == 2) {
                         // this CTA's half of the weight tile goes to both CTAs (same offset), and signals both full barriers
                         p_tma_load_2d_mc(dstB + rank * (Cfg::B_STAGE / 2), &mapB, fb, it * PBK, n0 + (int)rank * (BN / 2), (uint16_t)0x3);
+                    } else {
+                        // pair: this CTA keeps only ITS half of the weight rows (the MMA reads the other half from the peer)
+                        p_tma_load_2d_pair(dstB, &mapB, fb, it * PBK, n0 + (int)rank * (BN / 2));
                     }
                     if (++st == stages) {
                         st = 0;
@@ -279,34 +338,43 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
+        // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)((PAIR ? 2 * PBM : PBM) >> 4) << 24);
         int st = 0;
         uint32_t ph = 0;
         int li = 0;
-        for (int item = cluster_id; item < a.total_items; item += n_clusters, ++li) {
-            const int h = li % NACC;
-            const uint32_t use = (uint32_t)(li / NACC);
-            p_mbar_wait(p_smem_u32(&tempty[h]), (use & 1u) ^ 1u);     // the epilogue has drained this accumulator
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t dcol = tmem_base + (uint32_t)(h * BN);
-            for (int it = 0; it < a.total_chunks; ++it) {
-                p_mbar_wait(p_smem_u32(&full_bar[st]), ph);
+        if (!PAIR || rank == 0) {
+            for (int item = cluster_id; item < a.total_items; item += n_clusters, ++li) {
+                const int h = li % NACC;
+                const uint32_t use = (uint32_t)(li / NACC);
+                p_mbar_wait(p_smem_u32(&tempty[h]), (use & 1u) ^ 1u);     // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (p_elect_one()) {
-                    const uint64_t ad = p_desc_sw128(p_smem_u32(sA + (size_t)st * PA_STAGE));
-                    const uint64_t bd = p_desc_sw128(p_smem_u32(sB + (size_t)st * Cfg::B_STAGE));
+                const uint32_t dcol = tmem_base + (uint32_t)(h * BN);
+                for (int it = 0; it < a.total_chunks; ++it) {
+                    p_mbar_wait(p_smem_u32(&full_bar[st]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (p_elect_one()) {
+                        const uint64_t ad = p_desc_sw128(p_smem_u32(sA + (size_t)st * PA_STAGE));
+                        const uint64_t bd = p_desc_sw128(p_smem_u32(sB + (size_t)st * B_STAGE));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        p_umma_tf32(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
-                    if (CL == 1) p_umma_commit(p_smem_u32(&empty_bar[st]));
-                    else p_umma_commit_mc(p_smem_u32(&empty_bar[st]), (uint16_t)0x3);
-                    if (it == a.total_chunks - 1) p_umma_commit(p_smem_u32(&tfull[h]));
-                }
-                __syncwarp();
-                if (++st == stages) {
-                    st = 0;
-                    ph ^= 1u;
+                        for (int k = 0; k < 4; ++k) {
+                            if (PAIR) p_umma_tf32_pair(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                            else p_umma_tf32(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                        }
+                        if (CL == 1) p_umma_commit(p_smem_u32(&empty_bar[st]));
+                        else if (CL == 2) p_umma_commit_mc(p_smem_u32(&empty_bar[st]), (uint16_t)0x3);
+                        else p_umma_commit_pair_mc(p_smem_u32(&empty_bar[st]), (uint16_t)0x3);
+                        if (it == a.total_chunks - 1) {
+                            if (PAIR) p_umma_commit_pair_mc(p_smem_u32(&tfull[h]), (uint16_t)0x3);
+                            else p_umma_commit(p_smem_u32(&tfull[h]));
+                        }
+                    }
+                    __syncwarp();
+                    if (++st == stages) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
                 }
             }
         }
@@ -320,7 +388,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         int li = 0, cbuf = 0;
         for (int item = cluster_id; item < a.total_items; item += n_clusters, ++li) {
             const int n_tile = item % a.n_tiles;
-            const int m_tile = (item / a.n_tiles) * CL + (int)rank;
+            const int m_tile = (item / a.n_tiles) * NCTA + (int)rank;
             const bool tile_ok = m_tile < a.m_tiles;
             const int m0 = m_tile * PBM, n0 = n_tile * BN;
             const int h = li % NACC;
@@ -335,7 +403,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             p_mbar_wait(p_smem_u32(&tfull[h]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (BN / 32 < 2 && chalf == 1) {     // single-chunk tiles: the odd-chunk warps have nothing to read
-                if (lane == 0) p_mbar_arrive(p_smem_u32(&tempty[h]));
+                if (lane == 0) {
+                    if (PAIR) p_mbar_arrive_cluster(p_smem_u32(&tempty[h]) & P_PEER_MASK);
+                    else p_mbar_arrive(p_smem_u32(&tempty[h]));
+                }
                 continue;
             }
 #pragma unroll 1
@@ -345,7 +416,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 if (c + 2 >= BN / 32) {
                     // this warp's share of the accumulator is read: hand it back to the MMA warp before the rest of the epilogue
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    if (lane == 0) p_mbar_arrive(p_smem_u32(&tempty[h]));
+                    if (lane == 0) {
+                        if (PAIR) p_mbar_arrive_cluster(p_smem_u32(&tempty[h]) & P_PEER_MASK);   // the leader's MMA warp owns the hand-off
+                        else p_mbar_arrive(p_smem_u32(&tempty[h]));
+                    }
                 }
                 const int nb = n0 + c * 32;
                 if (a.dbg & 8) continue;
@@ -418,7 +492,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     if (CL > 1) p_cluster_sync();      // nobody leaves while the peer may still multicast into / signal this CTA
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TM_COLS) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TM_COLS) : "memory");
     }
 }
 
@@ -461,28 +536,30 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
 {
     using Cfg = PCfg<BN>;
     const int fixed = 1024 + Cfg::C_BYTES + Cfg::STAT_BYTES + 512;
-    int stages = (g_p2pb_smem_budget_kb * 1024 - fixed) / (PA_STAGE + Cfg::B_STAGE);
+    constexpr int b_stage = CL == 3 ? Cfg::B_STAGE / 2 : Cfg::B_STAGE;
+    int stages = (g_p2pb_smem_budget_kb * 1024 - fixed) / (PA_STAGE + b_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     a.stages = stages;
-    const size_t smem = (size_t)fixed + (size_t)stages * (PA_STAGE + Cfg::B_STAGE);
+    const size_t smem = (size_t)fixed + (size_t)stages * (PA_STAGE + b_stage);
     static bool attr_set = false;
     if (!attr_set) {
         P2PB_CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int m_items = (a.m_tiles + CL - 1) / CL;
+    constexpr int NCTA = CL == 1 ? 1 : 2;
+    const int m_items = (a.m_tiles + NCTA - 1) / NCTA;
     a.total_items = m_items * a.n_tiles;
-    int n_clusters = p2pb_num_sms() / CL;
+    int n_clusters = p2pb_num_sms() / NCTA;
     if (n_clusters > a.total_items) n_clusters = a.total_items;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_clusters * CL), 1, 1);
+    cfg.gridDim = dim3((unsigned)(n_clusters * NCTA), 1, 1);
     cfg.blockDim = dim3(P_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -494,7 +571,8 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
 
 }  // namespace
 
-int g_p2pb_gemm_mode = 0;   // bit 1: force the legacy one-tile-per-CTA kernel; bit 2: form 2-CTA multicast clusters; bits 3,4: timing experiments
+int g_p2pb_gemm_mode = 0;   // bit 1: force the legacy one-tile-per-CTA kernel; bit 2: 2-CTA multicast clusters instead of CTA pairs;
+                            // bits 3,4: timing experiments; bit 5: never form CTA pairs (cta_group::2)
 
 // Returns P2PB_ERR_UNSUPPORTED (without setting an error) when the shape is outside this kernel's envelope; the
 // caller then uses the legacy kernel (gemm_tf32.cu).  mapsA: up to 3 prepared A maps (rows mode: box {32,128};
@@ -522,13 +600,15 @@ int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chu
     a.dbg = g_p2pb_gemm_mode;
     a.bias = bias; a.bias2 = bias2; a.stats = stats; a.colmm = colmm;
     // 2-CTA cluster with multicast weights when the weight tile dominates the operand traffic and there is enough work
-    const bool cl2 = (g_p2pb_gemm_mode & 4) && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
+    // CTA pairs (cta_group::2, M = 256): each SM fetches only half of the weight tile -> for the tensor-bound shapes
+    const bool pair = !(g_p2pb_gemm_mode & 32) && !(g_p2pb_gemm_mode & 4) && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
+    const bool cl2 = !pair && (g_p2pb_gemm_mode & 4) && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
     CUtensorMap maps[5];
     for (int i = 0; i < 3; ++i) maps[i] = mapsA[i < nseg ? i : 0];
     {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)ktot * 4};
-        cuuint32_t box[2] = {PBK, (cuuint32_t)(cl2 ? bn / 2 : bn)};
+        cuuint32_t box[2] = {PBK, (cuuint32_t)((cl2 || pair) ? bn / 2 : bn)};
         int rc = p_make_map(&maps[3], W, 2, dims, str, box);
         if (rc != P2PB_OK) return rc;
     }
@@ -540,6 +620,12 @@ int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chu
         if (rc != P2PB_OK) return rc;
     } else {
         maps[4] = maps[3];
+    }
+    if (pair) {
+        switch (bn) {
+            case 256: return p_launch<256, 3>(maps, a, s);
+            case 128: return p_launch<128, 3>(maps, a, s);
+        }
     }
     if (cl2) {
         switch (bn) {

@@ -429,7 +429,8 @@ int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chu
                           int ldd, float* stats, float* colmm, int M, int N, cudaStream_t s);
 
 // development aid (tools/, tests): bit 0 = legacy kernel skips its global stores; bit 1 = force the legacy
-// one-tile-per-CTA kernel; bit 2 = persistent kernel forms 2-CTA multicast clusters; bits 3, 4 = timing experiments
+// one-tile-per-CTA kernel; bit 2 = persistent kernel forms 2-CTA multicast clusters instead of cta_group::2 pairs;
+// bits 3, 4 = timing experiments; bit 5 = persistent kernel never forms CTA pairs
 P2PB_API int p2pb_debug_set(int flags)
 {
     g_gemm_dbg = flags;

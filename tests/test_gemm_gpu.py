@@ -29,11 +29,12 @@ def test_gemm_rows_vs_fp64(M, K, N):
     _close(out, A.double() @ W.double().t() + bias.double())
 
 
-@pytest.mark.parametrize("mode", [0, 2, 4])
+@pytest.mark.parametrize("mode", [0, 2, 4, 32])
 @pytest.mark.parametrize("M,K,N", [(128 * 301 - 50, 96, 256), (128 * 300, 512, 1024), (40000, 64, 128), (5000, 160, 96)])
 def test_gemm_persistent_cluster_minmax(M, K, N, mode):
-    """Persistent kernel (mode 0; 2-CTA multicast clusters for the big shapes, odd tile count = unpaired tail),
-    legacy one-tile-per-CTA kernel (mode 2) and persistent without clusters (mode 4): results, GroupNorm partials and,
+    """Persistent kernel with cta_group::2 CTA pairs, M = 256, for the big shapes (mode 0; odd tile count = unpaired tail),
+    legacy one-tile-per-CTA kernel (mode 2), persistent with 2-CTA multicast clusters (mode 4) and persistent with
+    independent CTAs only (mode 32): results, GroupNorm partials and,
     for the persistent kernel, column (max, min) and the statistics-only variant (no D)."""
     from p2pb_b200 import dense
     from p2pb_b200._lib import lib
@@ -152,9 +153,11 @@ def test_conv3d_padded_channels_and_permutation():
 
 
 @pytest.mark.parametrize("B,r,cin,cout", [(1, 8, 32, 32), (2, 16, 64, 64), (1, 32, 32, 32), (2, 32, 64, 64), (1, 16, 128, 128),
-                                          (3, 16, 128, 64), (1, 32, 64, 32)])
+                                          (3, 16, 128, 64), (1, 32, 64, 32), (8, 16, 64, 64), (9, 16, 128, 128), (3, 32, 64, 32),
+                                          (15, 16, 32, 32)])
 def test_conv3d_halo_vs_fp64(B, r, cin, cout):
-    """Halo-reuse conv (chunk-planar padded input, un-swizzled A descriptors, stationary weight slabs)."""
+    """Halo-reuse conv (row-shifted windows, sub-slab weight ring).  The larger batches (>= 296 tiles) run as
+    cta_group::2 CTA pairs (M = 256), including odd tile counts (dummy slot) -- (9,16,..): 369 tiles, (15,16,..): 615."""
     import torch.nn.functional as F
 
     from p2pb_b200 import dense

@@ -26,7 +26,7 @@ for (M, K, N) in [(131072, 32, 128), (131072, 128, 256), (131072, 256, 512), (13
     stats = torch.zeros(dense.num_stat_blocks(M), N, 2, device="cuda")
     colmm = torch.zeros(dense.num_stat_blocks(M), N, 2, device="cuda")
     res = []
-    for mode in (2, 0, 4):
+    for mode in (2, 32, 4, 0):
         lib().p2pb_debug_set(mode)
         res.append(timeit(lambda: dense.gemm_rows([A], W, bias, out=out, stats=stats)))
     lib().p2pb_debug_set(0)
@@ -43,8 +43,8 @@ for (M, K, N) in [(131072, 32, 128), (131072, 128, 256), (131072, 256, 512), (13
     torch.backends.cuda.matmul.allow_tf32 = True
     tl = timeit(lambda: torch.nn.functional.linear(A, W, bias))
     fl = 2.0 * M * K * N; by = 4.0 * (M * K + M * N)
-    print(f"M={M:8d} K={K:4d} N={N:4d}: {res[0]*1e3:7.1f} | {res[1]*1e3:7.1f} | {res[2]*1e3:7.1f} | {res[3]*1e3:7.1f} | torch-tf32 {tl*1e3:7.1f}"
-          f" | ideal hbm {by/6.4e12*1e6:6.1f} tensor {fl/1.15e15*1e6:6.1f} | best {fl/min(res[:3])/1e9:7.1f} TFLOP/s {by/min(res[:3])/1e6:7.1f} GB/s")
+    print(f"M={M:8d} K={K:4d} N={N:4d}: {res[0]*1e3:7.1f} | {res[1]*1e3:7.1f} | {res[2]*1e3:7.1f} | pair {res[3]*1e3:7.1f} | {res[4]*1e3:7.1f} | torch-tf32 {tl*1e3:7.1f}"
+          f" | ideal hbm {by/6.4e12*1e6:6.1f} tensor {fl/1.15e15*1e6:6.1f} | best {fl/min(res[:4])/1e9:7.1f} TFLOP/s {by/min(res[:4])/1e6:7.1f} GB/s")
 
 print("conv3d r=8 (per-tap implicit GEMM): us legacy | persist | persist+cluster")
 for (B, r, cin, cout) in [(64, 8, 256, 256), (64, 8, 256, 128), (64, 8, 128, 128)]:
@@ -53,9 +53,9 @@ for (B, r, cin, cout) in [(64, 8, 256, 256), (64, 8, 256, 128), (64, 8, 128, 128
     bias = torch.randn(cout, device="cuda"); out = torch.empty(B * r ** 3, cout, device="cuda")
     stats = torch.zeros(B * r ** 3 // 32, cout, 2, device="cuda")
     res = []
-    for mode in (2, 0, 4):
+    for mode in (2, 32, 4, 0):
         lib().p2pb_debug_set(mode)
         res.append(timeit(lambda: dense.conv3d_cl(grid, w, bias, B, r, cin, cout, out=out, stats=stats)))
     lib().p2pb_debug_set(0)
     fl = 2.0 * B * r ** 3 * 27 * cin * cout
-    print(f"B={B} r={r} {cin}->{cout}: {res[0]*1e3:7.1f} | {res[1]*1e3:7.1f} | {res[2]*1e3:7.1f} | best {fl/min(res)/1e9:7.1f} TFLOP/s")
+    print(f"B={B} r={r} {cin}->{cout}: {res[0]*1e3:7.1f} | {res[1]*1e3:7.1f} | {res[2]*1e3:7.1f} | pair {res[3]*1e3:7.1f} | best {fl/min(res)/1e9:7.1f} TFLOP/s")

@@ -1,4 +1,5 @@
-"""Dev tool: halo-conv pipeline sweep on the PVDS layer shapes (B=64): (w_stages, a_stages, G) overrides vs automatic."""
+"""Dev tool: halo-conv pipeline sweep on the PVDS layer shapes (B=64): (w_stages, a_stages, G) overrides vs automatic;
+G < 0 selects the un-paired (cta_group::1) kernel: -1 = automatic G, -k = k tiles per unit."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +19,7 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 
-for r, cin, cin_valid, cout in [(32, 64, 35, 32), (32, 32, 32, 32), (16, 192, 192, 64), (16, 64, 64, 64), (16, 128, 128, 128), (32, 64, 64, 64)]:
+for r, cin, cin_valid, cout in [(32, 64, 35, 32), (32, 32, 32, 32), (16, 128, 128, 64), (16, 64, 64, 64), (16, 128, 128, 128), (32, 64, 64, 64)]:
     grid = torch.randn(B, r, r, r, cin, device="cuda")
     grid[..., cin_valid:] = 0
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda") / (27 * cin) ** 0.5
@@ -30,7 +31,7 @@ for r, cin, cin_valid, cout in [(32, 64, 35, 32), (32, 32, 32, 32), (16, 192, 19
     hst = torch.zeros(B * tps, cout, 2, device="cuda")
     fl = 2.0 * B * r ** 3 * 27 * cin_valid * cout
     line = f"r={r} {cin}({cin_valid})->{cout}:"
-    for cfg in [(0, 0, 0), (2, 0, 0), (3, 0, 0), (0, 5, 0), (0, 0, 2), (0, 0, 3), (0, 0, 8)]:
+    for cfg in [(0, 0, 0), (0, 0, -1), (2, 0, 0), (3, 0, 0), (0, 0, 2), (0, 0, 3), (0, 0, -2)]:
         lib().p2pb_conv_halo_tune(*cfg)
         try:
             t = timeit(lambda: dense.conv3d_halo(X, wp, bias, B, r, cin, cout, out=out, stats=hst, cin_valid=cin_valid))
