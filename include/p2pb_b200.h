@@ -121,6 +121,10 @@ int p2pb_conv_halo_tune(int w_stages, int a_stages, int G);
 /* cin_valid <= Cin: only the first cin_valid channels can be non-zero; K=8 MMAs over pure padding are skipped */
 int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
                         int Cin, int cin_valid, int Cout, void* stream);
+/* IEEE-half operand variant: X [rows, Cin] and W [Cout, 27*Cin] are __half (Cin a multiple of 64; same 10-bit mantissa as
+ * the tf32 operands of the fp32 entry point), bias / accumulation / D / stats fp32 */
+int p2pb_conv3d_halo_f16(const void* X, const void* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                         int Cin, int cin_valid, int Cout, void* stream);
 
 /* coords [B,3,N] -> columns col0..col0+2 of rows [B*N, ld] */
 int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N, int ld, int col0, void* stream);
@@ -136,6 +140,9 @@ int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const float* temb, 
 int p2pb_voxelize_padded_sparse(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* ind,
                                 const int* start, const int* cnt, float* out, int Cp, int B, int N, int r, int clear,
                                 void* stream);
+int p2pb_voxelize_padded_sparse_f16(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
+                                    const int* ind, const int* start, const int* cnt, void* out, int Cp, int B, int N, int r,
+                                    int clear, void* stream);
 
 /* GroupNorm / AdaGN statistics -> per-(sample, channel) affine (and the SE squeeze): replaces nn.GroupNorm's reduction,
  * AdaGN.forward (/root/reference/models/modules.py:341-358) and SE3d's mean (modules.py:378) */
@@ -150,6 +157,9 @@ int p2pb_affine_act(const float* x, int ldx, const float* A, const float* Bc, in
                     int pool, float* out, int ldo, float* gmax, void* stream);
 int p2pb_affine_act_padded(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, float* out,
                            void* stream);
+/* IEEE-half output rows of pitch ldo halves (operand of p2pb_conv3d_halo_f16) */
+int p2pb_affine_act_padded_f16(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, void* out, int ldo,
+                               void* stream);
 
 /* trilinear devoxelize of the raw conv output with AdaGN*SE folded in + Swish(AdaGN(point branch)) add
  * (trilinear_devox_gpu.cu:21-109 + /root/reference/models/pvcnn.py:318-328) */

@@ -110,6 +110,26 @@ __device__ __forceinline__ void h_umma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// kind::f16 with IEEE half operands: K = 16 per instruction at the cost of a K = 8 tf32 one.  Half has the SAME 10-bit
+// mantissa as tf32 (the tensor core drops the low 13 mantissa bits of an fp32 operand in kind::tf32), products are exact
+// and accumulation is fp32 in both kinds, so as long as the operands fit half's exponent range (post-GroupNorm/Swish
+// activations, O(1) weights) the arithmetic class is unchanged while every operand byte carries twice the channels.
+__device__ __forceinline__ void h_umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void h_umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
 // ---- cta_group::2 (CTA pair, M = 256 = one tile per CTA) forms; bit 24 of a shared::cluster address selects the CTA in the
 // pair, clearing it addresses the leader's barrier (same convention as gemm_persist.cu)
 constexpr uint32_t H_PEER_MASK = 0xFEFFFFFFu;
@@ -177,14 +197,17 @@ __device__ __forceinline__ float h_colsum32(float (&v)[32], int lane)
 // At N = Cout <= 64 the shared-memory operand fetch is the binding resource (profiles/r01_ncu_conv.md), at Cout = 128
 // the L2 -> SM weight stream was.  The leader CTA issues all MMAs; both CTAs load their own windows / weight halves and
 // run their own epilogue.
-template <bool PAIR>
+// F16: operands are IEEE half (X and W); a 128-byte chunk row then holds 64 channels and one MMA covers K = 16.
+template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const HaloArgs a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NC = PAIR ? 2 : 1;
-    const int tap_bytes = (a.cout / NC) * HBK * 4;      // one tap: [Cout (/2 in pair mode)][32] fp32, 128B-swizzled rows
+    constexpr int CHK = F16 ? 64 : 32;                  // channels per 128-byte chunk row
+    constexpr int KMMA = F16 ? 16 : 8;                  // channels per MMA
+    const int tap_bytes = (a.cout / NC) * 128;          // one tap: [Cout (/2 in pair mode)] rows of one 128B-swizzled chunk
     const int sub_bytes = 3 * tap_bytes;                // sub-slab: the 3 dz-taps of one (dx, chunk, dy)
     const int a_stage_bytes = a.W * 128;                // W rows x 32 channels (one 128-byte swizzle span per row)
     const int a_stage_stride = (a_stage_bytes + 1023) & ~1023;
@@ -271,13 +294,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         if (!PAIR) {
                             const uint32_t fb = h_smem_u32(&a_full[ast]);
                             h_mbar_expect_tx(fb, (uint32_t)a_stage_bytes);
-                            h_tma_load_2d(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * HBK,
+                            h_tma_load_2d(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * CHK,
                                           (int)((long long)b * a.P3 + qs));
                         } else {
                             // both windows of the pair complete on the LEADER's barrier, armed with the bytes of both
                             const uint32_t fb = h_smem_u32(&a_full[ast]) & H_PEER_MASK;
                             if (rank == 0) h_mbar_expect_tx(fb, (uint32_t)(2 * a_stage_bytes));
-                            h_tma_load_2d_pair(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * HBK,
+                            h_tma_load_2d_pair(h_smem_u32(sA + (size_t)ast * a_stage_stride), &mapX, fb, kc * CHK,
                                                (int)((long long)b * a.P3 + qs));
                         }
                         if (++ast == a.a_stages) {
@@ -303,14 +326,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                             h_mbar_expect_tx(fb, (uint32_t)sub_bytes);
                             for (int dz = 0; dz < 3; ++dz)
                                 h_tma_load_2d(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
-                                              ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * HBK, 0);
+                                              ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * CHK, 0);
                         } else {
                             // this CTA's half of the output channels of every tap; completes on the leader's barrier
                             const uint32_t fb = h_smem_u32(&w_full[wst]) & H_PEER_MASK;
                             if (rank == 0) h_mbar_expect_tx(fb, (uint32_t)(2 * sub_bytes));
                             for (int dz = 0; dz < 3; ++dz)
                                 h_tma_load_2d_pair(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
-                                                   ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * HBK, (int)rank * (a.cout / 2));
+                                                   ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * CHK, (int)rank * (a.cout / 2));
                         }
                         if (++wst == a.w_stages) {
                             wst = 0;
@@ -326,7 +349,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         // below keeps per-MMA work to two 32-bit adds (descriptor low words; the high word is a constant) and runs in a
         // single elected thread, so there is no per-step warp re-convergence.
         if ((!PAIR || rank == 0) && h_elect_one()) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((uint32_t)((NC * HBM) >> 4) << 24);
+            // instruction descriptor: D = f32; A, B = tf32 (format 2) or f16 (format 0), both K-major; N >> 3 @17, M >> 4 @24
+            const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(a.cout >> 3) << 17) |
+                                   ((uint32_t)((NC * HBM) >> 4) << 24);
             const uint32_t tap_step = (uint32_t)(tap_bytes >> 4);
             const uint32_t sA_lo = (h_smem_u32(sA) & 0x3ffff) >> 4, sW_lo = (h_smem_u32(sW) & 0x3ffff) >> 4;
             const uint32_t a_stride_lo = (uint32_t)(a_stage_stride >> 4), w_stride_lo = (uint32_t)(sub_bytes >> 4);
@@ -344,7 +369,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 const uint32_t dcol0 = tmem_base + (uint32_t)(h * half_cols);
                 for (int sl = 0; sl < nslabs; ++sl) {
                     const int kc = sl % a.cin_chunks;
-                    int nj = (a.cin_valid - kc * HBK + 7) >> 3;     // K=8 MMAs that can see a non-zero channel
+                    int nj = (a.cin_valid - kc * CHK + KMMA - 1) / KMMA;     // MMAs that can see a non-zero channel
                     nj = nj > 4 ? 4 : nj;
                     for (int dy = 0; dy < 3; ++dy) {
                         h_mbar_wait(h_smem_u32(&w_full[wst]), wph);
@@ -369,8 +394,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                                     if (j < nj) {
                                         const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(dz * 8 + j * 2));
                                         const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)dz * tap_step + (uint32_t)(j * 2));
-                                        if (PAIR) h_umma_tf32_pair(dcol, ad, bd, idesc, (dz | j) != 0 ? 1u : first);
-                                        else h_umma_tf32(dcol, ad, bd, idesc, (dz | j) != 0 ? 1u : first);
+                                        const uint32_t acc = (dz | j) != 0 ? 1u : first;
+                                        if (PAIR && F16) h_umma_f16_pair(dcol, ad, bd, idesc, acc);
+                                        else if (PAIR) h_umma_tf32_pair(dcol, ad, bd, idesc, acc);
+                                        else if (F16) h_umma_f16(dcol, ad, bd, idesc, acc);
+                                        else h_umma_tf32(dcol, ad, bd, idesc, acc);
                                     }
                                 }
                             }
@@ -510,33 +538,37 @@ P2PB_API int p2pb_conv_halo_tune(int w_stages, int a_stages, int G)
 
 // cin_valid <= Cin: channels that can be non-zero (the rest is zero padding in X and W): the K=8 MMAs that would only
 // multiply padding are skipped (SA0's first conv: 35 real channels in a 64-wide layout -> 5 of 8 MMAs per tap)
-P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
-                                 int Cin, int cin_valid, int Cout, void* stream)
+static int conv3d_halo_impl(const void* X, const void* W, const float* bias, float* D, int ldd, float* stats, int B, int r, int Cin,
+                           int cin_valid, int Cout, bool f16, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
-    P2PB_CHECK_ARG(B > 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cout <= 128, "conv3d_halo: Cin=%d Cout=%d (multiples of 32, Cout<=128)", Cin, Cout);
-    P2PB_CHECK_ARG(cin_valid > 0 && cin_valid <= Cin && cin_valid > Cin - 32, "conv3d_halo: cin_valid=%d must lie in the last 32-channel chunk of Cin=%d", cin_valid, Cin);
+    const int chk = f16 ? 64 : 32, esz = f16 ? 2 : 4;
+    P2PB_CHECK_ARG(B > 0 && Cin % chk == 0 && Cout % 32 == 0 && Cout <= 128, "conv3d_halo: Cin=%d Cout=%d (Cin %% %d, Cout %% 32, Cout<=128)", Cin, Cout, chk);
+    P2PB_CHECK_ARG(cin_valid > 0 && cin_valid <= Cin && cin_valid > Cin - chk, "conv3d_halo: cin_valid=%d must lie in the last %d-channel chunk of Cin=%d", cin_valid, chk, Cin);
     P2PB_CHECK_ARG(r >= 8 && r <= 62, "conv3d_halo: r=%d out of range (TMA box rows 128+2(r+2)+2 <= 256)", r);
     P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= Cout, "conv3d_halo: bad ldd");
     HaloArgs a = {};
     a.B = B; a.r = r; a.P = r + 2; a.P2 = a.P * a.P; a.P3 = a.P2 * a.P;
-    a.cin_chunks = Cin / 32; a.cin_valid = cin_valid; a.cout = Cout;
+    a.cin_chunks = Cin / chk; a.cin_valid = cin_valid; a.cout = Cout;
     a.W = 128 + 2 * a.P + 2;
     a.q_first = a.P2 + a.P + 1;
     a.q_last = a.P3 - a.P2 - a.P - 2;
     a.tiles_per_sample = (a.q_last - a.q_first + 1 + HBM - 1) / HBM;
     a.total_tiles = B * a.tiles_per_sample;
+    const bool pair_hint = g_halo_pair && a.total_tiles >= 2 * p2pb_num_sms();
+    // (half operands in CTA pairs at Cout = 64: G = 2 measured faster than 4 -- 459 vs 526 us at 64 -> 64 @ 32^3 -- the
+    // weight stream is already a quarter of the tf32 single-CTA one and shorter units balance better)
     // G tiles share every weight sub-slab; their accumulators fit one 256-column half of TMEM (G = 4 at Cout <= 64, 2 at
     // Cout = 128) and units ping-pong between the halves, so the epilogue overlaps the next unit's mainloop (measured at
     // Cout = 128: G = 4 without overlap 467 us, G = 2 with overlap 390 us)
-    a.G = Cout <= 64 ? 4 : 2;
+    a.G = (Cout <= 32 || (Cout <= 64 && !(f16 && pair_hint))) ? 4 : 2;
     if (g_halo_G > 0 && g_halo_G * Cout <= 512) a.G = g_halo_G;
     a.halves = a.G * Cout <= 256 ? 2 : 1;
     a.ldd = ldd;
-    a.X = X; a.bias = bias; a.D = D; a.stats = stats;
+    a.X = reinterpret_cast<const float*>(X); a.bias = bias; a.D = D; a.stats = stats;
     const int n_sms = p2pb_num_sms();
     const bool pair = g_halo_pair && a.total_tiles >= 2 * n_sms && n_sms >= 2;
-    const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * HBK * 4;     // per CTA: pair mode keeps half of the output channels
+    const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * 128;     // per CTA: pair mode keeps half of the output channels
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
     const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
@@ -560,11 +592,12 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
                 enc = reinterpret_cast<PFN_encodeTiled_h>(p);
         }
         P2PB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+        const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
         cuuint64_t dims[2] = {(cuuint64_t)27 * Cin, (cuuint64_t)Cout};
-        cuuint64_t str[1] = {(cuuint64_t)27 * Cin * 4};
-        cuuint32_t box[2] = {HBK, (cuuint32_t)(pair ? Cout / 2 : Cout)};
+        cuuint64_t str[1] = {(cuuint64_t)27 * Cin * esz};
+        cuuint32_t box[2] = {(cuuint32_t)chk, (cuuint32_t)(pair ? Cout / 2 : Cout)};
         cuuint32_t estr[2] = {1, 1};
-        CUresult rc = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), dims, str, box, estr,
+        CUresult rc = enc(&mapW, dt, 2, const_cast<void*>(W), dims, str, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) {
@@ -574,9 +607,9 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
         int slack = 0;
         p2pb_conv_halo_layout(r, nullptr, &slack, nullptr);
         cuuint64_t xdims[2] = {(cuuint64_t)Cin, (cuuint64_t)B * a.P3 + (cuuint64_t)slack};
-        cuuint64_t xstr[1] = {(cuuint64_t)Cin * 4};
-        cuuint32_t xbox[2] = {HBK, (cuuint32_t)a.W};
-        rc = enc(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), xdims, xstr, xbox, estr,
+        cuuint64_t xstr[1] = {(cuuint64_t)Cin * esz};
+        cuuint32_t xbox[2] = {(cuuint32_t)chk, (cuuint32_t)a.W};
+        rc = enc(&mapX, dt, 2, const_cast<void*>(X), xdims, xstr, xbox, estr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) {
@@ -586,8 +619,10 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
     }
     static bool attr_set = false;
     if (!attr_set) {
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     if (pair) {
@@ -603,14 +638,30 @@ P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bi
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, mapW, mapX, a));
+        if (f16) P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, true>, mapW, mapX, a));
+        else P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, false>, mapW, mapX, a));
     } else {
         int grid = n_sms;
         if (grid > a.total_tiles) grid = a.total_tiles;
-        conv_halo_kernel<false><<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
+        if (f16) conv_halo_kernel<false, true><<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
+        else conv_halo_kernel<false, false><<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
     }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
+}
+
+P2PB_API int p2pb_conv3d_halo_ex(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                                 int Cin, int cin_valid, int Cout, void* stream)
+{
+    return conv3d_halo_impl(X, W, bias, D, ldd, stats, B, r, Cin, cin_valid, Cout, false, stream);
+}
+
+// IEEE-half operands (X [rows, Cin] and W [Cout, 27*Cin] as __half, Cin a multiple of 64), fp32 accumulate / bias / output:
+// same 10-bit operand mantissa as the tf32 path, twice the channels per operand byte and per MMA
+P2PB_API int p2pb_conv3d_halo_f16(const void* X, const void* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                                  int Cin, int cin_valid, int Cout, void* stream)
+{
+    return conv3d_halo_impl(X, W, bias, D, ldd, stats, B, r, Cin, cin_valid, Cout, true, stream);
 }
 
 P2PB_API int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,

@@ -12,6 +12,8 @@
 //   linear_small     per-sample small Linear (AdaGN/temb/SE/attention-sized matvecs), warp per output
 //   attention_small  bottleneck LinearAttention core (softmax over tokens, 32x32 context per head)
 //   bridge_update    pred_x0 = xt - std*eps ; xt <- mu_x0*pred_x0 + mu_xn*xt           (p2pb.py:155-165,190-213)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // Flat element indices are split with 32-bit unsigned divisions (a 64-bit division costs ~10x more ALU work than the
@@ -788,16 +790,28 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
     return P2PB_OK;
 }
 
+// store 4 consecutive channels as fp32 or as IEEE half (round to nearest): the conv operands of the half path
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__half* p, float4 v)
+{
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&lo);
+    u.y = *reinterpret_cast<const unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
 // Sparse form of voxelize_padded for grids that are mostly empty (a 2048-point patch occupies ~5 % of a 32^3 grid):
 // the grid is kept all-zero between evaluations; this kernel writes only the occupied voxel rows (clear = 0), and after
 // the convolution has consumed the grid the same enumeration zeroes them again (clear = 1).  One thread per
 // (sorted point slot, 4 channels); the slot that starts a voxel's CSR range owns the voxel, the others exit.  The sums
 // run over the voxel's points in ascending point index exactly like the dense kernel (bit-identical result).
+template <typename OUT>
 __global__ void __launch_bounds__(256) voxelize_sparse_kernel(const float* __restrict__ feat, int ldf, int Cf,
                                                               const float* __restrict__ temb, int E,
                                                               const int* __restrict__ order, const int* __restrict__ ind,
                                                               const int* __restrict__ start, const int* __restrict__ cnt,
-                                                              float* __restrict__ out, int Cp, int N, int r, int clear,
+                                                              OUT* __restrict__ out, int Cp, int N, int r, int clear,
                                                               unsigned total4)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,27 +856,49 @@ __global__ void __launch_bounds__(256) voxelize_sparse_kernel(const float* __res
             }
         }
     }
-    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * Cp + c0) = make_float4(a[0], a[1], a[2], a[3]);
+    store4(out + padded_row(b, v, r) * Cp + c0, make_float4(a[0], a[1], a[2], a[3]));
+}
+
+static int voxelize_sparse_impl(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* ind,
+                                const int* start, const int* cnt, void* out, int Cp, int B, int N, int r, int clear, bool f16,
+                                void* stream)
+{
+    P2PB_CHECK_ARG(Cp % 32 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_padded_sparse: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
+    const long long total4 = (long long)B * N * (Cp / 4);
+    P2PB_CHECK_U32(total4, "voxelize_padded_sparse");
+    if (total4 == 0) return P2PB_OK;
+    if (f16) {
+        p2pb_prefer_max_smem((const void*)voxelize_sparse_kernel<__half>);
+        voxelize_sparse_kernel<__half><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+            feat, ldf, Cf, temb, E, order, ind, start, cnt, reinterpret_cast<__half*>(out), Cp, N, r, clear, total4);
+    } else {
+        p2pb_prefer_max_smem((const void*)voxelize_sparse_kernel<float>);
+        voxelize_sparse_kernel<float><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+            feat, ldf, Cf, temb, E, order, ind, start, cnt, reinterpret_cast<float*>(out), Cp, N, r, clear, total4);
+    }
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
 }
 
 P2PB_API int p2pb_voxelize_padded_sparse(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
                                          const int* ind, const int* start, const int* cnt, float* out, int Cp, int B, int N,
                                          int r, int clear, void* stream)
 {
-    P2PB_CHECK_ARG(Cp % 32 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_padded_sparse: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
-    const long long total4 = (long long)B * N * (Cp / 4);
-    P2PB_CHECK_U32(total4, "voxelize_padded_sparse");
-    if (total4 == 0) return P2PB_OK;
-    p2pb_prefer_max_smem((const void*)voxelize_sparse_kernel);
-    voxelize_sparse_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, ind, start, cnt,
-                                                                                   out, Cp, N, r, clear, total4);
-    P2PB_LAUNCH_OK();
-    return P2PB_OK;
+    return voxelize_sparse_impl(feat, ldf, Cf, temb, E, order, ind, start, cnt, out, Cp, B, N, r, clear, false, stream);
+}
+
+// same, the grid is IEEE half (operand of p2pb_conv3d_halo_f16); sums are formed in fp32 exactly as above, rounded once
+P2PB_API int p2pb_voxelize_padded_sparse_f16(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
+                                             const int* ind, const int* start, const int* cnt, void* out, int Cp, int B, int N,
+                                             int r, int clear, void* stream)
+{
+    return voxelize_sparse_impl(feat, ldf, Cf, temb, E, order, ind, start, cnt, out, Cp, B, N, r, clear, true, stream);
 }
 
 // y = swish(x*A + B) of dense conv-output rows [B*r^3, ldx] -> zero-bordered padded input rows of the next conv
+template <typename OUT>
 __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
-                                                                const float* __restrict__ Bc, int C, float* __restrict__ out,
+                                                                const float* __restrict__ Bc, int C, OUT* __restrict__ out, int ldo,
                                                                 int r, unsigned total4)
 {
     const unsigned r3 = r * r * r;
@@ -888,7 +924,7 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const unsigned e = e0 + k * blockDim.x;
-        if (e < total4) *reinterpret_cast<float4*>(out + orow[k] * C + c[k]) = affine4<1>(xv[k], a[k], bb[k]);
+        if (e < total4) store4(out + orow[k] * ldo + c[k], affine4<1>(xv[k], a[k], bb[k]));
     }
 }
 
@@ -899,8 +935,24 @@ P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, con
     const long long total4 = (long long)B * r * r * r * (C / 4);
     P2PB_CHECK_U32(total4, "affine_act_padded");
     if (total4 == 0) return P2PB_OK;
-    p2pb_prefer_max_smem((const void*)affine_act_padded_kernel);
-    affine_act_padded_kernel<<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, r, total4);
+    p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<float>);
+    affine_act_padded_kernel<float><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, C, r, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// same with IEEE-half output rows of pitch ldo >= C halves (ldo a multiple of 64: the 64-channel chunks of the half conv;
+// columns C..ldo-1 are never written and stay zero)
+P2PB_API int p2pb_affine_act_padded_f16(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, void* out,
+                                        int ldo, void* stream)
+{
+    P2PB_CHECK_ARG(C % 32 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ldo >= C, "affine_act_padded_f16: C %% 32, ldx %% 4, ldo >= C");
+    const long long total4 = (long long)B * r * r * r * (C / 4);
+    P2PB_CHECK_U32(total4, "affine_act_padded_f16");
+    if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<__half>);
+    affine_act_padded_kernel<__half><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

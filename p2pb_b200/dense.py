@@ -95,17 +95,17 @@ def halo_layout(r: int):
     return a.value, b.value, c.value
 
 
-def alloc_padded(B: int, C: int, r: int, device) -> torch.Tensor:
+def alloc_padded(B: int, C: int, r: int, device, dtype=torch.float32) -> torch.Tensor:
     """Zero-initialised X[B*(r+2)^3 + slack, C]; border rows stay zero forever (kernels only write interior rows)."""
     P3, slack, _ = halo_layout(r)
-    return torch.zeros(B * P3 + slack, C, dtype=torch.float32, device=device)
+    return torch.zeros(B * P3 + slack, C, dtype=dtype, device=device)
 
 
 def dense_to_padded(grid: torch.Tensor, r: int) -> torch.Tensor:
-    """Test helper (torch ops): channels-last dense grid [B, r, r, r, C] -> padded row-major layout."""
+    """Test helper (torch ops): channels-last dense grid [B, r, r, r, C] -> padded row-major layout (dtype kept)."""
     B, C = grid.shape[0], grid.shape[-1]
     P = r + 2
-    X = alloc_padded(B, C, r, grid.device)
+    X = alloc_padded(B, C, r, grid.device, grid.dtype)
     X[: B * P ** 3].view(B, P, P, P, C)[:, 1:-1, 1:-1, 1:-1, :] = grid
     return X
 
@@ -115,8 +115,9 @@ def conv3d_halo(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], 
                 cin_valid: Optional[int] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty((B * r ** 3, cout), dtype=torch.float32, device=X.device)
-    assert X.is_contiguous() and X.shape[1] == cin
+    assert X.is_contiguous() and X.shape[1] == cin and X.dtype == W.dtype
+    entry = "p2pb_conv3d_halo_f16" if X.dtype == torch.float16 else "p2pb_conv3d_halo_ex"
     with torch.cuda.device(X.device):
-        call("p2pb_conv3d_halo_ex", _p(X), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
+        call(entry, _p(X), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
              int(cin if cin_valid is None else cin_valid), int(cout), _s())
     return out

@@ -45,6 +45,15 @@ def pad32(c: int) -> int:
     return (c + 31) // 32 * 32
 
 
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+# Operands of the large-grid voxel convolutions (conv_halo) are stored as IEEE half: same 10-bit mantissa as the tf32
+# operands the tensor core would otherwise truncate them to, twice the channels per byte and per MMA (conv_halo.cu).
+HALO_F16 = os.environ.get("P2PB_HALO_F16", "1") != "0"
+
+
 class _AdaGN:
     """Packed norm parameters: gamma/beta + offset of this layer's (factor, bias) block in the batched emd GEMM."""
 
@@ -119,10 +128,17 @@ class Engine:
         perm_full = perm + list(range(c_in, c_in + E))
         cp = pad32(c_in + E)
         P = {"cout": cout, "cin": c_in, "E": E, "cp": cp, "r": int(mod.resolution)}
-        P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full)
+        halo = int(mod.resolution) >= 16 and cout <= 128 and cout % 32 == 0   # large grid / few channels: conv_halo.cu
+        P["halo"] = halo
+        if halo and HALO_F16:
+            P["cp"] = cp = pad64(c_in + E)
+            P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
+            P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
+        else:
+            P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full)
+            P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad32(cout))
         P["b1"] = self._w(conv1.bias)
         P["n1"] = self._norm(n1)
-        P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad32(cout))
         P["b2"] = self._w(conv2.bias)
         P["n2"] = self._norm(n2)
         if se is not None:
@@ -282,11 +298,11 @@ class Engine:
         assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
         return t
 
-    def padded(self, name: str, B: int, C: int, r: int) -> torch.Tensor:
+    def padded(self, name: str, B: int, C: int, r: int, dtype=torch.float32) -> torch.Tensor:
         """Zero-bordered padded-linear conv input [B*(r+2)^3 + slack, C] (conv_halo.cu); borders stay zero forever."""
         t = self._bufs.get(name)
         if t is None:
-            t = dense.alloc_padded(B, C, r, self.dev)
+            t = dense.alloc_padded(B, C, r, self.dev, dtype)
             self._bufs[name] = t
         return t
 
@@ -359,25 +375,32 @@ class Engine:
         """PVConv (pvcnn.py:306-334): voxel branch + point branch -> rows [B*n_pts, cout]."""
         B, r, cout, cp = self.B, P["r"], P["cout"], P["cp"]
         r3 = r ** 3
-        halo = r >= 16 and cout <= 128 and cout % 32 == 0        # large grid / few channels: halo-reuse conv (conv_halo.cu)
+        halo = P["halo"]
         raw1 = self.buf(f"{name}.raw1", B * r3, cout)
         raw2 = self.buf(f"{name}.raw2", B * r3, cout)
         tvox = _p(temb if P["E"] else None)
         if halo:
+            f16 = P["w1"].dtype == torch.float16
+            dt = torch.float16 if f16 else torch.float32
+            sfx = "_f16" if f16 else ""
+            c2 = pad64(cout) if f16 else pad32(cout)
             _, _, tiles = dense.halo_layout(r)
-            grid = self.padded(f"{name}.grid", B, cp, r)
+            grid = self.padded(f"{name}.grid", B, cp, r, dt)
             # the grid stays all-zero between evaluations: write the occupied voxels, convolve, zero them again
             vox_args = (_p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]), _p(prep["ind"]),
                         _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r)
-            call("p2pb_voxelize_padded_sparse", *vox_args, 0, _s())
+            call("p2pb_voxelize_padded_sparse" + sfx, *vox_args, 0, _s())
             st1 = self.buf(f"{name}.st1", B * tiles, cout, 2)
             dense.conv3d_halo(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1, cin_valid=P["cin"] + P["E"])
-            call("p2pb_voxelize_padded_sparse", *vox_args, 1, _s())
+            call("p2pb_voxelize_padded_sparse" + sfx, *vox_args, 1, _s())
             A1, B1, _ = self.coef(f"{name}.n1", st1, tiles, P["n1"], cout, r3)
-            act1 = self.padded(f"{name}.act1", B, pad32(cout), r)
-            call("p2pb_affine_act_padded", _p(raw1), cout, _p(A1), _p(B1), B, cout, r, _p(act1), _s())
+            act1 = self.padded(f"{name}.act1", B, c2, r, dt)
+            if f16:
+                call("p2pb_affine_act_padded_f16", _p(raw1), cout, _p(A1), _p(B1), B, cout, r, _p(act1), c2, _s())
+            else:
+                call("p2pb_affine_act_padded", _p(raw1), cout, _p(A1), _p(B1), B, cout, r, _p(act1), _s())
             st2 = self.buf(f"{name}.st2", B * tiles, cout, 2)
-            dense.conv3d_halo(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
+            dense.conv3d_halo(act1, P["w2"], P["b2"], B, r, c2, cout, out=raw2, stats=st2, cin_valid=cout)
         else:
             tiles = r3 // 32
             grid = self.buf(f"{name}.grid", B * r3, cp)

@@ -212,6 +212,12 @@ def test_voxelize_sparse_equals_dense_and_clears():
     assert torch.equal(out, ref) and int((cnt > 0).sum()) > 0
     call("p2pb_voxelize_padded_sparse", *args, 1, s)
     assert int(out.count_nonzero()) == 0
+    outh = dense.alloc_padded(B, Cp, r, "cuda", torch.float16)       # half grid: same sums, rounded once
+    argsh = args[:9] + (p(outh),) + args[10:]
+    call("p2pb_voxelize_padded_sparse_f16", *argsh, 0, s)
+    assert torch.equal(outh, ref.half())
+    call("p2pb_voxelize_padded_sparse_f16", *argsh, 1, s)
+    assert int(outh.count_nonzero()) == 0
 
 
 def test_dual_chain_engine_equals_single_chain(monkeypatch):

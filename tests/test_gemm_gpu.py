@@ -177,3 +177,37 @@ def test_conv3d_halo_vs_fp64(B, r, cin, cout):
     o = out.double().view(B, -1, cout)
     assert torch.allclose(s[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,r,cin,cin_valid,cout", [(1, 16, 64, 64, 64), (2, 32, 64, 35, 32), (9, 16, 128, 128, 128), (3, 32, 64, 32, 32),
+                                                    (15, 16, 128, 100, 64)])
+def test_conv3d_halo_half_operands_vs_fp64(B, r, cin, cin_valid, cout):
+    """IEEE-half operand variant (kind::f16, 64 channels per chunk, K-valid MMA skipping), un-paired and CTA-pair
+    launches: compared with the fp64 convolution of the SAME half-rounded operands at the tf32 tolerance (half and
+    tf32 share the 10-bit mantissa) and with the fp32-operand kernel."""
+    import torch.nn.functional as F
+
+    from p2pb_b200 import dense
+
+    g = torch.Generator(device="cuda").manual_seed(r + cin + cout)
+    x = torch.randn(B, cin, r, r, r, device="cuda", generator=g)
+    x[:, cin_valid:] = 0
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
+    w[:, cin_valid:] = 0
+    bias = torch.randn(cout, device="cuda", generator=g)
+    xh, wh = x.half(), w.half()
+    X = dense.dense_to_padded(xh.permute(0, 2, 3, 4, 1).contiguous(), r)
+    _, _, tps = dense.halo_layout(r)
+    stats = torch.zeros(B * tps, cout, 2, device="cuda")
+    out = torch.full((B * r ** 3, cout), float("nan"), device="cuda")
+    dense.conv3d_halo(X, dense.pack_conv3d_weight(wh.float(), cin).half(), bias, B, r, cin, cout, out=out, stats=stats,
+                      cin_valid=cin_valid)
+    ref = F.conv3d(xh.double(), wh.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(B * r ** 3, cout)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-6, err          # exact products, fp32 accumulation
+    ref32 = F.conv3d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(B * r ** 3, cout)
+    _close(out, ref32)                                               # vs the un-rounded operands: tf32-class error
+    s = stats.double().view(B, tps, cout, 2).sum(1)
+    o = out.double().view(B, -1, cout)
+    assert torch.allclose(s[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)

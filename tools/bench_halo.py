@@ -31,12 +31,18 @@ for r, cin, cin_valid, cout in [(32, 64, 35, 32), (32, 32, 32, 32), (16, 128, 12
     hst = torch.zeros(B * tps, cout, 2, device="cuda")
     fl = 2.0 * B * r ** 3 * 27 * cin_valid * cout
     line = f"r={r} {cin}({cin_valid})->{cout}:"
-    for cfg in [(0, 0, 0), (0, 0, -1), (2, 0, 0), (3, 0, 0), (0, 0, 2), (0, 0, 3), (0, 0, -2)]:
+    c64 = (cin + 63) // 64 * 64
+    gh = torch.zeros(B, r, r, r, c64, device="cuda", dtype=torch.float16); gh[..., :cin] = grid.half()
+    Xh = dense.dense_to_padded(gh, r)
+    wh = torch.zeros(cout, c64, 3, 3, 3, device="cuda"); wh[:, :cin] = w
+    wph = dense.pack_conv3d_weight(wh, c64).half()
+    for cfg in [(0, 0, 0), (0, 0, -1), (0, 0, 2), (0, 0, 3)]:
         lib().p2pb_conv_halo_tune(*cfg)
         try:
             t = timeit(lambda: dense.conv3d_halo(X, wp, bias, B, r, cin, cout, out=out, stats=hst, cin_valid=cin_valid))
-            line += f"  {cfg}: {t*1e3:6.0f}us {fl/t/1e9:5.0f}TF"
+            th = timeit(lambda: dense.conv3d_halo(Xh, wph, bias, B, r, c64, cout, out=out, stats=hst, cin_valid=cin_valid))
+            line += f"  {cfg}: tf32 {t*1e3:5.0f}us {fl/t/1e9:4.0f}TF | half {th*1e3:5.0f}us {fl/th/1e9:4.0f}TF"
         except Exception as ex:
-            line += f"  {cfg}: n/a"
+            line += f"  {cfg}: n/a {ex}"
     lib().p2pb_conv_halo_tune(0, 0, 0)
     print(line, flush=True)
