@@ -62,7 +62,9 @@ class _AdaGN:
 
 
 class Engine:
-    dtype_name = "tf32"
+    # arithmetic of the contractions: 10-bit-mantissa operands (tf32 for the GEMMs / r=8 convs, IEEE half -- the same
+    # mantissa -- for the r>=16 voxel convs), fp32 accumulation; everything else fp32
+    dtype_name = "tf32+f16(10-bit mantissa operands), fp32 accumulate" if HALO_F16 else "tf32"
 
     def __init__(self, p2pb, net, B: int, N: int, F: int):
         self.p2pb, self.net = p2pb, net

@@ -1,14 +1,14 @@
 """Live roofline measurement of the dominant kernel for bench.py.
 
 Dominant kernel of the PVDS N=2048 hot path = the 3x3x3 voxel convolution at r=32 (conv_halo_kernel): per network
-evaluation it accounts for ~45 % of the GPU time (profiles/launches_engine_r1*.csv).  Measured here on its largest
-instance (fp_layers.3.1 voxel_layers.0/.4: 64 -> 64 channels on a 32^3 grid, one launch per batch of B patches) with
-CUDA events on the launching stream, inputs larger than L2 (B=64: 644 MB input + 537 MB output per launch).
+evaluation it accounts for ~45 % of the GPU time (profiles/r01_launches.md).  Measured here on its largest instance
+(fp_layers.3.1 voxel_layers.0/.4: 64 -> 64 channels on a 32^3 grid) exactly as the engine launches it: IEEE-half
+operands (kind::f16, fp32 accumulate), cta_group::2 CTA pairs, one launch per chain (B/2 patches when the engine splits
+the batch into two chains), CUDA events on the launching stream, inputs larger than L2 (B=32: 161 MB in + 268 MB out).
 
 achieved = algorithmic FLOPs per launch / mean launch time, algorithmic FLOPs = 2 * B * r^3 * 27 * Cin * Cout
-(SURVEY.md §8d counts 7.2478 GFLOP per patch for this layer).  Bound: tensor.  peak = measured dense TF32 rate =
-half of the measured cuBLAS bf16 rate in MEASURED_PEAKS.json (TF32 runs at half the bf16 MMA rate: K=8 vs K=16 per
-instruction at equal issue cost; confirmed by tools/ubench/mma_rate.cu: 1151 vs 2302 TFLOP/s at N>=128)."""
+(SURVEY.md 8d counts 7.2478 GFLOP per patch for this layer).  Bound: tensor.  peak = the measured dense 16-bit rate
+(cuBLAS bf16 in MEASURED_PEAKS.json; kind::f16 and kind::bf16 issue at the same rate)."""
 from __future__ import annotations
 
 import json
@@ -33,12 +33,17 @@ def measured_peaks():
 
 
 def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
+    from .engine import HALO_F16, DualEngine
+
     r, cin, cout = 32, 64, 64
+    if isinstance(getattr(model, "last_engine", None), DualEngine):
+        B = B // 2                       # the engine launches the kernel once per half-batch chain
+    dt = torch.float16 if HALO_F16 else torch.float32
     g = torch.Generator(device=dev).manual_seed(0)
-    X = dense.alloc_padded(B, cin, r, dev)
+    X = dense.alloc_padded(B, cin, r, dev, dt)
     P = r + 2
-    X[: B * P ** 3].view(B, P, P, P, cin)[:, 1:-1, 1:-1, 1:-1, :] = torch.randn(B, r, r, r, cin, device=dev, generator=g)
-    w = torch.randn(cout, 27 * cin, device=dev, generator=g) / (27 * cin) ** 0.5
+    X[: B * P ** 3].view(B, P, P, P, cin)[:, 1:-1, 1:-1, 1:-1, :] = torch.randn(B, r, r, r, cin, device=dev, generator=g).to(dt)
+    w = (torch.randn(cout, 27 * cin, device=dev, generator=g) / (27 * cin) ** 0.5).to(dt)
     bias = torch.zeros(cout, device=dev)
     out = torch.empty(B * r ** 3, cout, device=dev)
     _, _, tps = dense.halo_layout(r)
@@ -56,16 +61,20 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
     flops = 2.0 * B * r ** 3 * 27 * cin * cout
     achieved = flops / (ms * 1e-3) / 1e12
     bf16_peak, _, how = measured_peaks()
-    peak = bf16_peak / 2.0
+    peak = bf16_peak if HALO_F16 else bf16_peak / 2.0
+    esz = 2.0 if HALO_F16 else 4.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("conv_halo_64x64_r32_B64_dram_bytes")
+            key = f"conv_halo_64x64_r32_B{B}_{'f16' if HALO_F16 else 'tf32'}_dram_bytes"
+            traffic = json.load(open(tp)).get(key)
         except Exception:
             traffic = None
-    return {"bound": "tensor", "kernel": "conv_halo_kernel (3x3x3 conv, 64->64 ch, 32^3 grid, TF32 tcgen05)",
+    kind = "IEEE-half operands, kind::f16" if HALO_F16 else "TF32"
+    return {"bound": "tensor", "kernel": f"conv_halo_kernel (3x3x3 conv, 64->64 ch, 32^3 grid, {B} patches per launch, {kind}, "
+                                         "fp32 accumulate, cta_group::2 tcgen05)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "ms_per_launch": ms, "flops_per_launch": flops,
-            "algorithmic_bytes_per_launch": 4.0 * B * ((r + 2) ** 3 * cin + r ** 3 * cout),
-            "peak_source": f"{how}: bf16 {bf16_peak:.1f} TFLOP/s / 2 for TF32"}
+            "algorithmic_bytes_per_launch": B * (esz * (r + 2) ** 3 * cin + 4.0 * r ** 3 * cout),
+            "peak_source": f"{how}: dense 16-bit rate {bf16_peak:.1f} TFLOP/s" + ("" if HALO_F16 else " / 2 for TF32")}
