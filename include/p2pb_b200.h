@@ -106,6 +106,20 @@ int p2pb_gemm_rows_ex(const float* A0, int K0, int lda0, const float* A1, int K1
 int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const float* A, const float* Bc, int act, float* gmax,
                      void* stream);
 
+/* IEEE-half operand variants of the two entry points above: A segments / grid and W are __half (K_i resp. Cin multiples
+ * of 64, lda multiples of 8), bias / accumulation / D / stats / colmm fp32.  Half keeps the 10-bit mantissa a tf32 operand
+ * has inside the tensor core; producers: p2pb_affine_act_f16, p2pb_voxelize_cl_f16, p2pb_coords_to_rows_f16. */
+int p2pb_gemm_rows_f16(const void* A0, int K0, int lda0, const void* A1, int K1, int lda1, const void* A2, int K2, int lda2,
+                       const void* W, const float* bias, const float* bias2, int rows_per_sample, float* D, int ldd,
+                       float* stats, float* colmm, int M, int N, void* stream);
+int p2pb_conv3d_cl_f16(const void* grid, const void* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                       int Cin, int Cout, void* stream);
+int p2pb_affine_act_f16(const float* x, int ldx, const float* A, const float* Bc, int rows_per_sample, int M, int C, int act,
+                        void* out, int ldo, void* stream);
+int p2pb_voxelize_cl_f16(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* start,
+                         const int* cnt, void* out, int Cp, int B, int N, int r, void* stream);
+int p2pb_coords_to_rows_f16(const float* coords, void* rows, int B, int N, int ld, int col0, void* stream);
+
 /* replaces nn.Conv3d 3x3x3 pad 1 (/root/reference/models/pvcnn.py:265-284): per-tap 5-D TMA implicit GEMM (any r = 2^k >= 8)
  * grid [B,r,r,r,Cin] channels-last, W [Cout, 27*Cin] (k = ((kx*3+ky)*3+kz)*Cin + c), D [B*r^3, ldd] */
 int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,

@@ -18,6 +18,17 @@
 
 // Flat element indices are split with 32-bit unsigned divisions (a 64-bit division costs ~10x more ALU work than the
 // 16 bytes each thread moves); every launcher checks that the element count fits.
+// store 4 consecutive channels as fp32 or as IEEE half (round to nearest): the conv operands of the half path
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__half* p, float4 v)
+{
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&lo);
+    u.y = *reinterpret_cast<const unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
 #define P2PB_CHECK_U32(total, what) P2PB_CHECK_ARG((total) < 4294967296LL, what ": %lld elements exceed the 32-bit index range, split the batch", (long long)(total))
 
 // ---------------------------------------------------------------------------------------------------------
@@ -37,6 +48,32 @@ __global__ void coords_to_rows_kernel(const float* __restrict__ coords, float* _
     o[2] = c[n + 2 * N];
 }
 
+__global__ void coords_to_rows_f16_kernel(const float* __restrict__ coords, __half* __restrict__ rows, int N, int ld, int col0,
+                                          long long total)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / N;
+    const int n = (int)(i - b * N);
+    const float* c = coords + b * 3 * N;
+    __half* o = rows + i * ld + col0;
+    o[0] = __float2half_rn(c[n]);
+    o[1] = __float2half_rn(c[n + N]);
+    o[2] = __float2half_rn(c[n + 2 * N]);
+}
+
+// same, IEEE-half rows (A operand of p2pb_gemm_rows_f16)
+P2PB_API int p2pb_coords_to_rows_f16(const float* coords, void* rows, int B, int N, int ld, int col0, void* stream)
+{
+    const long long total = (long long)B * N;
+    if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)coords_to_rows_f16_kernel);
+    coords_to_rows_f16_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(coords, reinterpret_cast<__half*>(rows), N, ld,
+                                                                                    col0, total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
 P2PB_API int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N, int ld, int col0, void* stream)
 {
     const long long total = (long long)B * N;
@@ -53,10 +90,11 @@ P2PB_API int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N,
 //   Cf <= c < Cf+E : the same scatter-mean applied to the broadcast time embedding temb[b, c-Cf]
 //   else           : 0 (channel padding for the 32-wide K chunks of the conv)
 // ---------------------------------------------------------------------------------------------------------
+template <typename OUT>
 __global__ void __launch_bounds__(256) voxelize_cl_kernel(const float* __restrict__ feat, int ldf, int Cf,
                                                           const float* __restrict__ temb, int E,
                                                           const int* __restrict__ order, const int* __restrict__ start,
-                                                          const int* __restrict__ cnt, float* __restrict__ out, int Cp,
+                                                          const int* __restrict__ cnt, OUT* __restrict__ out, int Cp,
                                                           int N, int r3, unsigned total4)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,7 +134,7 @@ __global__ void __launch_bounds__(256) voxelize_cl_kernel(const float* __restric
             }
         }
     }
-    reinterpret_cast<float4*>(out)[e] = acc;
+    store4(out + (size_t)e * 4, acc);
 }
 
 P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
@@ -107,9 +145,25 @@ P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* t
     const long long total4 = (long long)B * r3 * (Cp / 4);
     P2PB_CHECK_U32(total4, "voxelize_cl");
     if (total4 == 0) return P2PB_OK;
-    p2pb_prefer_max_smem((const void*)voxelize_cl_kernel);
-    voxelize_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
-                                                                               Cp, N, r3, total4);
+    p2pb_prefer_max_smem((const void*)voxelize_cl_kernel<float>);
+    voxelize_cl_kernel<float><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
+                                                                                      Cp, N, r3, total4);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// same with an IEEE-half grid (A operand of p2pb_conv3d_cl_f16); fp32 sums, rounded once
+P2PB_API int p2pb_voxelize_cl_f16(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* start,
+                                  const int* cnt, void* out, int Cp, int B, int N, int r, void* stream)
+{
+    P2PB_CHECK_ARG(Cp % 4 == 0 && Cf + E <= Cp && Cf > 0, "voxelize_cl_f16: bad channels Cf=%d E=%d Cp=%d", Cf, E, Cp);
+    const int r3 = r * r * r;
+    const long long total4 = (long long)B * r3 * (Cp / 4);
+    P2PB_CHECK_U32(total4, "voxelize_cl_f16");
+    if (total4 == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)voxelize_cl_kernel<__half>);
+    voxelize_cl_kernel<__half><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt,
+                                                                                       reinterpret_cast<__half*>(out), Cp, N, r3, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -258,10 +312,10 @@ __device__ __forceinline__ float4 affine4(float4 x, float4 a, float4 b)
 
 // 4 float4 per thread (all loads issued before the first use): the pass is HBM-bound and one 16-byte load per thread
 // does not keep enough bytes in flight (measured 4.0 TB/s with 1, see profiles/)
-template <int ACT>
+template <int ACT, typename OUT>
 __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                          const float* __restrict__ Bc, int rows_per_sample, int C,
-                                                         float* __restrict__ out, int ldo, unsigned total4)
+                                                         OUT* __restrict__ out, int ldo, unsigned total4)
 {
     const unsigned C4 = C >> 2;
     const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
@@ -284,7 +338,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const unsigned e = e0 + k * blockDim.x;
-        if (e < total4) *reinterpret_cast<float4*>(out + m[k] * ldo + c[k]) = affine4<ACT>(xv[k], a[k], bb[k]);
+        if (e < total4) store4(out + m[k] * ldo + c[k], affine4<ACT>(xv[k], a[k], bb[k]));
     }
 }
 
@@ -407,14 +461,31 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     if (pool == 1) {
         const long long total4 = (long long)M * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act");
-        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1>); affine_act_kernel<1><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
-        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0>); affine_act_kernel<0><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); affine_act_kernel<1, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); affine_act_kernel<0, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
     } else {
         const long long total4 = (long long)(M / pool) * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act(pool)");
         if (act) { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<1>); affine_act_pool_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
         else { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<0>); affine_act_pool_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
     }
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// affine_act with IEEE-half output rows (A operand of the half GEMM / conv entry points); no pooling
+P2PB_API int p2pb_affine_act_f16(const float* x, int ldx, const float* A, const float* Bc, int rows_per_sample, int M, int C, int act,
+                                 void* out, int ldo, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    P2PB_CHECK_ARG(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && out != nullptr, "affine_act_f16: C/ld must be multiples of 4");
+    P2PB_CHECK_ARG(rows_per_sample > 0 && M % rows_per_sample == 0, "affine_act_f16: bad row partition");
+    if (M == 0) return P2PB_OK;
+    const long long total4 = (long long)M * (C / 4);
+    P2PB_CHECK_U32(total4, "affine_act_f16");
+    __half* o = reinterpret_cast<__half*>(out);
+    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); affine_act_kernel<1, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4); }
+    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); affine_act_kernel<0, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4); }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -788,17 +859,6 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
                                                                                    Cp, N, r, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
-}
-
-// store 4 consecutive channels as fp32 or as IEEE half (round to nearest): the conv operands of the half path
-__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void store4(__half* p, float4 v)
-{
-    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<const unsigned*>(&lo);
-    u.y = *reinterpret_cast<const unsigned*>(&hi);
-    *reinterpret_cast<uint2*>(p) = u;
 }
 
 // Sparse form of voxelize_padded for grids that are mostly empty (a 2048-point patch occupies ~5 % of a 32^3 grid):

@@ -40,6 +40,7 @@ struct PArgs {
     int stages;
     int store;
     int dbg;
+    int f16;        // operands are IEEE half: a 128-byte chunk row holds 64 K-elements, one MMA (kind::f16) covers K = 16
     const float* bias;
     const float* bias2;
     float* stats;   // [4*m_tiles, n_total, 2]  (sum, sum^2) of each 32-row block
@@ -126,6 +127,15 @@ __device__ __forceinline__ void p_umma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// kind::f16 (IEEE half operands, fp32 accumulate): same 10-bit operand mantissa as kind::tf32, K = 16 per instruction
+__device__ __forceinline__ void p_umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void p_umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -175,6 +185,14 @@ __device__ __forceinline__ void p_umma_tf32_pair(uint32_t tmem_d, uint64_t adesc
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void p_umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
         : "memory");
 }
@@ -280,6 +298,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (p_elect_one()) {
             int st = 0;
             uint32_t ph = 0;
+            const int chk = a.f16 ? 64 : 32;     // K-elements per 128-byte chunk row
             const int sc0 = a.seg_chunks[0], sc1 = a.seg_chunks[1], sc2 = a.seg_chunks[2];
             for (int item = cluster_id; item < a.total_items; item += n_clusters) {
                 const int n_tile = item % a.n_tiles;
@@ -304,8 +323,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     const uint32_t dstA = p_smem_u32(sA + (size_t)st * PA_STAGE);
                     if (a.conv) {
                         const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
-                        if (PAIR) p_tma_load_5d_pair(dstA, &mapA0, fb, kc * PBK, dz, cy + dy, cx + dx, cb);
-                        else p_tma_load_5d(dstA, &mapA0, fb, kc * PBK, dz, cy + dy, cx + dx, cb);
+                        if (PAIR) p_tma_load_5d_pair(dstA, &mapA0, fb, kc * chk, dz, cy + dy, cx + dx, cb);
+                        else p_tma_load_5d(dstA, &mapA0, fb, kc * chk, dz, cy + dy, cx + dx, cb);
                         if (++kc == a.cin_chunks) {
                             kc = 0;
                             ++tap;
@@ -316,19 +335,19 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                             ++seg;
                         }
                         const CUtensorMap* mp = seg == 0 ? &mapA0 : (seg == 1 ? &mapA1 : &mapA2);
-                        if (PAIR) p_tma_load_2d_pair(dstA, mp, fb, seg_it * PBK, m0);
-                        else p_tma_load_2d(dstA, mp, fb, seg_it * PBK, m0);
+                        if (PAIR) p_tma_load_2d_pair(dstA, mp, fb, seg_it * chk, m0);
+                        else p_tma_load_2d(dstA, mp, fb, seg_it * chk, m0);
                         ++seg_it;
                     }
                     const uint32_t dstB = p_smem_u32(sB + (size_t)st * B_STAGE);
                     if (CL == 1) {
-                        p_tma_load_2d(dstB, &mapB, fb, it * PBK, n0);
+                        p_tma_load_2d(dstB, &mapB, fb, it * chk, n0);
                     } else if (CL == 2) {
                         // this CTA's half of the weight tile goes to both CTAs (same offset), and signals both full barriers
-                        p_tma_load_2d_mc(dstB + rank * (Cfg::B_STAGE / 2), &mapB, fb, it * PBK, n0 + (int)rank * (BN / 2), (uint16_t)0x3);
+                        p_tma_load_2d_mc(dstB + rank * (Cfg::B_STAGE / 2), &mapB, fb, it * chk, n0 + (int)rank * (BN / 2), (uint16_t)0x3);
                     } else {
                         // pair: this CTA keeps only ITS half of the weight rows (the MMA reads the other half from the peer)
-                        p_tma_load_2d_pair(dstB, &mapB, fb, it * PBK, n0 + (int)rank * (BN / 2));
+                        p_tma_load_2d_pair(dstB, &mapB, fb, it * chk, n0 + (int)rank * (BN / 2));
                     }
                     if (++st == stages) {
                         st = 0;
@@ -339,8 +358,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (pair mode: the leader CTA only) =====================
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+        const uint32_t fmt = a.f16 ? 0u : 2u;    // operand format: 0 = f16, 2 = tf32
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)((PAIR ? 2 * PBM : PBM) >> 4) << 24);
+        const bool f16 = a.f16 != 0;
         int st = 0;
         uint32_t ph = 0;
         int li = 0;
@@ -359,8 +380,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                         const uint64_t bd = p_desc_sw128(p_smem_u32(sB + (size_t)st * B_STAGE));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (PAIR) p_umma_tf32_pair(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
-                            else p_umma_tf32(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                            const uint64_t adk = ad + (uint64_t)(k * 2), bdk = bd + (uint64_t)(k * 2);
+                            const uint32_t acc = (uint32_t)((it | k) != 0);
+                            if (PAIR) {
+                                if (f16) p_umma_f16_pair(dcol, adk, bdk, idesc, acc);
+                                else p_umma_tf32_pair(dcol, adk, bdk, idesc, acc);
+                            } else {
+                                if (f16) p_umma_f16(dcol, adk, bdk, idesc, acc);
+                                else p_umma_tf32(dcol, adk, bdk, idesc, acc);
+                            }
                         }
                         if (CL == 1) p_umma_commit(p_smem_u32(&empty_bar[st]));
                         else if (CL == 2) p_umma_commit_mc(p_smem_u32(&empty_bar[st]), (uint16_t)0x3);
@@ -505,7 +533,7 @@ typedef CUresult (*PFN_encodeTiled_p)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int p_make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box)
+               const cuuint32_t* box, bool f16 = false)
 {
     static PFN_encodeTiled_p enc = nullptr;
     if (enc == nullptr) {
@@ -520,7 +548,8 @@ int p_make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
         return P2PB_ERR_CUDA;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+    CUresult rc = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                      const_cast<void*>(base), dims, strides_bytes, box,
                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
@@ -577,9 +606,9 @@ int g_p2pb_gemm_mode = 0;   // bit 1: force the legacy one-tile-per-CTA kernel; 
 // Returns P2PB_ERR_UNSUPPORTED (without setting an error) when the shape is outside this kernel's envelope; the
 // caller then uses the legacy kernel (gemm_tf32.cu).  mapsA: up to 3 prepared A maps (rows mode: box {32,128};
 // conv mode: 5-D box), W: [N, Ktot].
-int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chunks, int conv, int cin_chunks, int tiles_per_sample,
-                          int r, const float* W, int ktot, const float* bias, const float* bias2, int rows_per_sample, float* D,
-                          int ldd, float* stats, float* colmm, int M, int N, cudaStream_t s)
+static int gemm_persist_launch(const CUtensorMap* mapsA, int nseg, const int* seg_chunks, int conv, int cin_chunks, int tiles_per_sample,
+                               int r, const void* W, int ktot, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                               int ldd, float* stats, float* colmm, int M, int N, bool f16, cudaStream_t s)
 {
     if (g_p2pb_gemm_mode & 2) return P2PB_ERR_UNSUPPORTED;
     if (N % 32 != 0) return P2PB_ERR_UNSUPPORTED;
@@ -598,6 +627,7 @@ int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chu
     a.rows_per_sample = rows_per_sample;
     a.store = D != nullptr;
     a.dbg = g_p2pb_gemm_mode;
+    a.f16 = f16 ? 1 : 0;
     a.bias = bias; a.bias2 = bias2; a.stats = stats; a.colmm = colmm;
     // 2-CTA cluster with multicast weights when the weight tile dominates the operand traffic and there is enough work
     // CTA pairs (cta_group::2, M = 256): each SM fetches only half of the weight tile -> for the tensor-bound shapes
@@ -607,9 +637,9 @@ int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chu
     for (int i = 0; i < 3; ++i) maps[i] = mapsA[i < nseg ? i : 0];
     {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
-        cuuint64_t str[1] = {(cuuint64_t)ktot * 4};
-        cuuint32_t box[2] = {PBK, (cuuint32_t)((cl2 || pair) ? bn / 2 : bn)};
-        int rc = p_make_map(&maps[3], W, 2, dims, str, box);
+        cuuint64_t str[1] = {(cuuint64_t)ktot * (f16 ? 2 : 4)};
+        cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)((cl2 || pair) ? bn / 2 : bn)};
+        int rc = p_make_map(&maps[3], W, 2, dims, str, box, f16);
         if (rc != P2PB_OK) return rc;
     }
     if (D != nullptr) {
@@ -641,3 +671,66 @@ int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chu
     }
     return P2PB_ERR_UNSUPPORTED;
 }
+
+int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chunks, int conv, int cin_chunks, int tiles_per_sample,
+                          int r, const float* W, int ktot, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                          int ldd, float* stats, float* colmm, int M, int N, cudaStream_t s)
+{
+    return gemm_persist_launch(mapsA, nseg, seg_chunks, conv, cin_chunks, tiles_per_sample, r, W, ktot, bias, bias2, rows_per_sample, D,
+                               ldd, stats, colmm, M, N, false, s);
+}
+
+// ---- IEEE-half operand entry points (A segments and W are __half; K_i multiples of 64; bias / D / stats fp32) -------------
+// Same contract as p2pb_gemm_rows_ex / p2pb_conv3d_cl otherwise.  Half keeps the 10-bit mantissa a tf32 operand has inside the
+// tensor core; one 128-byte operand row and one MMA carry twice the K of the tf32 path.
+P2PB_API int p2pb_gemm_rows_f16(const void* A0, int K0, int lda0, const void* A1, int K1, int lda1, const void* A2, int K2, int lda2,
+                                const void* W, const float* bias, const float* bias2, int rows_per_sample, float* D, int ldd,
+                                float* stats, float* colmm, int M, int N, void* stream)
+{
+    const void* Ap[3] = {A0, A1, A2};
+    const int Ks[3] = {K0, K1, K2}, lds[3] = {lda0, lda1, lda2};
+    P2PB_CHECK_ARG(M > 0 && N > 0 && N % 32 == 0, "gemm_rows_f16: bad M=%d N=%d (N must be a multiple of 32)", M, N);
+    P2PB_CHECK_ARG(D == nullptr || (ldd % 4 == 0 && ldd >= N && (reinterpret_cast<uintptr_t>(D) & 15) == 0), "gemm_rows_f16: bad D/ldd");
+    P2PB_CHECK_ARG(D != nullptr || stats != nullptr || colmm != nullptr, "gemm_rows_f16: no output requested");
+    P2PB_CHECK_ARG(bias2 == nullptr || rows_per_sample > 0, "gemm_rows_f16: bias2 needs rows_per_sample");
+    CUtensorMap maps[3];
+    int chunks[3] = {0, 0, 0}, ktot = 0, nseg = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (Ap[i] == nullptr || Ks[i] == 0) break;
+        P2PB_CHECK_ARG(Ks[i] % 64 == 0 && lds[i] % 8 == 0 && lds[i] >= Ks[i], "gemm_rows_f16: segment %d K=%d lda=%d (K %% 64, lda %% 8)", i, Ks[i], lds[i]);
+        P2PB_CHECK_ARG((reinterpret_cast<uintptr_t>(Ap[i]) & 15) == 0, "gemm_rows_f16: segment %d not 16-byte aligned", i);
+        cuuint64_t dims[2] = {(cuuint64_t)Ks[i], (cuuint64_t)M};
+        cuuint64_t str[1] = {(cuuint64_t)lds[i] * 2};
+        cuuint32_t box[2] = {64, PBM};
+        int rc = p_make_map(&maps[i], Ap[i], 2, dims, str, box, true);
+        if (rc != P2PB_OK) return rc;
+        chunks[i] = Ks[i] / 64;
+        ktot += Ks[i];
+        ++nseg;
+    }
+    P2PB_CHECK_ARG(nseg > 0, "gemm_rows_f16: no A segment");
+    return gemm_persist_launch(maps, nseg, chunks, 0, 0, 0, 0, W, ktot, bias, bias2, rows_per_sample, D, ldd, stats, colmm, M, N, true,
+                               (cudaStream_t)stream);
+}
+
+// grid [B, r, r, r, Cin] __half channels-last (Cin multiple of 64), W [Cout, 27*Cin] __half -> D [B*r^3, ldd] fp32
+P2PB_API int p2pb_conv3d_cl_f16(const void* grid, const void* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                                int Cin, int Cout, void* stream)
+{
+    P2PB_CHECK_ARG(B > 0 && Cin % 64 == 0 && Cout % 32 == 0, "conv3d_cl_f16: bad B=%d Cin=%d Cout=%d (Cin %% 64, Cout %% 32)", B, Cin, Cout);
+    P2PB_CHECK_ARG(r >= 8 && (r & (r - 1)) == 0 && r <= 128, "conv3d_cl_f16: r=%d must be a power of two in [8,128]", r);
+    P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= Cout && (reinterpret_cast<uintptr_t>(D) & 15) == 0, "conv3d_cl_f16: bad D/ldd");
+    const int r3 = r * r * r;
+    const int bz = r < PBM ? r : PBM;
+    const int by = (PBM / bz) < r ? (PBM / bz) : r;
+    const int bx = PBM / (bz * by);
+    CUtensorMap map;
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * r, (cuuint64_t)Cin * 2 * r * r, (cuuint64_t)Cin * 2 * r3};
+    cuuint32_t box[5] = {64, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
+    int rc = p_make_map(&map, grid, 5, dims, str, box, true);
+    if (rc != P2PB_OK) return rc;
+    return gemm_persist_launch(&map, 1, nullptr, 1, Cin / 64, r3 / PBM, r, W, 27 * Cin, bias, nullptr, 0, D, ldd, stats, nullptr, B * r3,
+                               Cout, true, (cudaStream_t)stream);
+}
+

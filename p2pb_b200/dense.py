@@ -43,12 +43,13 @@ def gemm_rows(segs: Sequence[torch.Tensor], W: torch.Tensor, bias: Optional[torc
     assert 1 <= len(segs) <= 3
     M = segs[0].shape[0]
     N = W.shape[0]
+    f16 = W.dtype == torch.float16          # IEEE-half operands -> p2pb_gemm_rows_f16 (fp32 bias / accumulate / output)
     a = []
     for i in range(3):
         if i < len(segs):
             t = segs[i]
-            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == M):
-                raise P2PBError(f"gemm_rows: segment {i} must be a CUDA fp32 [M,K] tensor with unit inner stride")
+            if not (t.is_cuda and t.dtype == W.dtype and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == M):
+                raise P2PBError(f"gemm_rows: segment {i} must be a CUDA {W.dtype} [M,K] tensor with unit inner stride")
             k = t.shape[1] if ks is None else ks[i]
             a += [_p(t), int(k), int(t.stride(0))]
         else:
@@ -59,7 +60,7 @@ def gemm_rows(segs: Sequence[torch.Tensor], W: torch.Tensor, bias: Optional[torc
         out = None
     assert (out is None or out.stride(1) == 1) and W.is_contiguous()
     with torch.cuda.device(W.device):
-        call("p2pb_gemm_rows_ex", *a, _p(W), _p(bias), _p(bias2), int(rows_per_sample), _p(out),
+        call("p2pb_gemm_rows_f16" if f16 else "p2pb_gemm_rows_ex", *a, _p(W), _p(bias), _p(bias2), int(rows_per_sample), _p(out),
              int(out.stride(0)) if out is not None else 0, _p(stats), _p(colmm), int(M), int(N), _s())
     return out
 
@@ -69,9 +70,9 @@ def conv3d_cl(grid: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
     """3x3x3 / stride 1 / pad 1 conv on a channels-last grid [B, r, r, r, cin] -> rows [B*r^3, cout]."""
     if out is None:
         out = torch.empty((B * r ** 3, cout), dtype=torch.float32, device=grid.device)
-    assert grid.is_contiguous() and W.is_contiguous() and out.stride(1) == 1
+    assert grid.is_contiguous() and W.is_contiguous() and out.stride(1) == 1 and grid.dtype == W.dtype
     with torch.cuda.device(grid.device):
-        call("p2pb_conv3d_cl", _p(grid), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
+        call("p2pb_conv3d_cl_f16" if W.dtype == torch.float16 else "p2pb_conv3d_cl", _p(grid), _p(W), _p(bias), _p(out), int(out.stride(0)), _p(stats), int(B), int(r), int(cin),
              int(cout), _s())
     return out
 

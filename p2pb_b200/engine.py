@@ -52,6 +52,8 @@ def pad64(c: int) -> int:
 # Operands of the large-grid voxel convolutions (conv_halo) are stored as IEEE half: same 10-bit mantissa as the tf32
 # operands the tensor core would otherwise truncate them to, twice the channels per byte and per MMA (conv_halo.cu).
 HALO_F16 = os.environ.get("P2PB_HALO_F16", "1") != "0"
+# ... and likewise the r = 8 voxel convs (per-tap implicit GEMM) and the global PointNet's GEMMs
+GEMM_F16 = os.environ.get("P2PB_GEMM_F16", "1") != "0"
 
 
 class _AdaGN:
@@ -136,6 +138,10 @@ class Engine:
             P["cp"] = cp = pad64(c_in + E)
             P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
             P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
+        elif not halo and GEMM_F16 and cout % 32 == 0:
+            P["cp"] = cp = pad64(c_in + E)
+            P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
+            P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
         else:
             P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full)
             P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad32(cout))
@@ -205,12 +211,16 @@ class Engine:
                 conv, gn = seq[0], seq[1]
                 o, c = conv.weight.shape[:2]
                 L = {"cout": o, "b": self._w(conv.bias), "n": self._norm(gn)}
+                pnet_f16 = GEMM_F16 and self.N % 128 == 0     # (the column max/min epilogue needs whole 128-row tiles per sample)
+                padk = pad64 if pnet_f16 else pad32
                 if j == 2:  # input = cat[point feature (c/2), global max (c/2)]: second half becomes a per-sample bias
                     h = c // 2
-                    L["w"] = self._pack_rows_w(conv.weight, [(0, h, 0)], pad32(h))
+                    L["w"] = self._pack_rows_w(conv.weight, [(0, h, 0)], padk(h))
                     L["w_g"] = self._w(conv.weight).reshape(o, c)[:, h:].contiguous()
                 else:
-                    L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad32(c))
+                    L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], padk(c))
+                if pnet_f16:
+                    L["w"] = L["w"].half()
                 G.append(L)
             W["pnet"] = G
         # SA levels
@@ -343,6 +353,11 @@ class Engine:
         return A, Bc, ym
 
     def act(self, x, A, Bc, rows_per_sample, C, out, act=1, pool=1, gmax=None):
+        if out is not None and out.dtype == torch.float16:      # operand of a half GEMM / conv
+            assert pool == 1 and gmax is None
+            call("p2pb_affine_act_f16", _p(x), int(x.stride(0)), _p(A), _p(Bc), rows_per_sample, x.shape[0], C, act, _p(out),
+                 int(out.stride(0)), _s())
+            return
         call("p2pb_affine_act", _p(x), int(x.stride(0)), _p(A), _p(Bc), rows_per_sample, x.shape[0], C, act, pool,
              _p(out), int(out.stride(0)) if out is not None else 0, _p(gmax), _s())
 
@@ -405,16 +420,19 @@ class Engine:
             dense.conv3d_halo(act1, P["w2"], P["b2"], B, r, c2, cout, out=raw2, stats=st2, cin_valid=cout)
         else:
             tiles = r3 // 32
-            grid = self.buf(f"{name}.grid", B * r3, cp)
-            call("p2pb_voxelize_cl", _p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]),
-                 _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
+            f16 = P["w1"].dtype == torch.float16
+            dt = torch.float16 if f16 else torch.float32
+            c2 = pad64(cout) if f16 else pad32(cout)
+            grid = self.buf(f"{name}.grid", B * r3, cp, dtype=dt)
+            call("p2pb_voxelize_cl_f16" if f16 else "p2pb_voxelize_cl", _p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"],
+                 _p(prep["order"]), _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r, _s())
             st1 = self.buf(f"{name}.st1", B * tiles, cout, 2)
             dense.conv3d_cl(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1)
             A1, B1, _ = self.coef(f"{name}.n1", st1, tiles, P["n1"], cout, r3)
-            act1 = self.buf(f"{name}.act1", B * r3, pad32(cout))
+            act1 = self.buf(f"{name}.act1", B * r3, c2, dtype=dt)
             self.act(raw1, A1, B1, r3, cout, act1, act=1)
             st2 = self.buf(f"{name}.st2", B * tiles, cout, 2)
-            dense.conv3d_cl(act1, P["w2"], P["b2"], B, r, pad32(cout), cout, out=raw2, stats=st2)
+            dense.conv3d_cl(act1, P["w2"], P["b2"], B, r, c2, cout, out=raw2, stats=st2)
         A2, B2, ym = self.coef(f"{name}.n2", st2, tiles, P["n2"], cout, r3, want_mean="se0" in P)
         se = None
         if "se0" in P:
@@ -540,6 +558,12 @@ class Engine:
         if "pnet" in W:
             G = W["pnet"]
             x, kx = X0, 32
+            pdt = torch.float32
+            if G[0]["w"].dtype == torch.float16:       # half operands: coords rows and every activation that feeds a GEMM
+                pdt = torch.float16
+                x, kx = self.buf("X0h", B * N, 64, dtype=pdt), 64
+                call("p2pb_coords_to_rows_f16", _p(xt), _p(x), B, N, 64, 0, _s())
+            padk = pad64 if pdt == torch.float16 else pad32
             g_half = None
             for j, L in enumerate(G):
                 nm = f"pnet{j}"
@@ -560,7 +584,7 @@ class Engine:
                     call("p2pb_gmax_minmax", _p(colmm), tl, B, L["cout"], _p(A), _p(Bc), 1, _p(g), _s())
                     if j == 1:
                         g_half = g
-                        out = self.buf(nm + ".act", B * N, pad32(L["cout"]))
+                        out = self.buf(nm + ".act", B * N, padk(L["cout"]), dtype=pdt)
                         self.act(raw, A, Bc, N, L["cout"], out, act=1)
                     else:
                         out, cond = None, g
@@ -573,9 +597,9 @@ class Engine:
                     cond = self.buf("cond", B, L["cout"])
                     self.act(raw, A, Bc, N, L["cout"], None, act=1, gmax=cond)
                 else:
-                    out = self.buf(nm + ".act", B * N, pad32(L["cout"]))
+                    out = self.buf(nm + ".act", B * N, padk(L["cout"]), dtype=pdt)
                     self.act(raw, A, Bc, N, L["cout"], out, act=1)
-                x, kx = out, pad32(L["cout"])
+                x, kx = out, padk(L["cout"])
             self.emd_all = self.buf("emd_all", B, self._emd_ld)
             dense.gemm_rows([cond], W["emd_w"], W["emd_b"], out=self.emd_all)
         else:

@@ -211,3 +211,49 @@ def test_conv3d_halo_half_operands_vs_fp64(B, r, cin, cin_valid, cout):
     o = out.double().view(B, -1, cout)
     assert torch.allclose(s[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,K,N", [(128 * 301 - 50, 128, 256), (40000, 64, 128), (5000, 192, 96), (131072, 512, 1024)])
+def test_gemm_rows_half_operands(M, K, N):
+    """IEEE-half operand GEMM (kind::f16; single CTAs and cta_group::2 pairs): exact products + fp32 accumulation vs the fp64
+    product of the same half-rounded operands; GroupNorm partials, column max/min, statistics-only variant."""
+    from p2pb_b200 import dense
+
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    T = dense.num_stat_blocks(M)
+    stats = torch.zeros(T, N, 2, device="cuda")
+    colmm = torch.zeros(T, N, 2, device="cuda")
+    out = dense.gemm_rows([A], W, bias, stats=stats, colmm=colmm)
+    ref = A.double() @ W.double().t() + bias.double()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-6, err
+    assert torch.allclose(stats[..., 0].double().sum(0), out.double().sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.equal(colmm[..., 0].max(0).values, out.max(0).values)
+    assert torch.equal(colmm[..., 1].min(0).values, out.min(0).values)
+    stats2, colmm2 = torch.zeros_like(stats), torch.zeros_like(colmm)
+    assert dense.gemm_rows([A], W, bias, stats=stats2, colmm=colmm2, store=False) is None
+    assert torch.equal(stats2, stats) and torch.equal(colmm2, colmm)
+
+
+@pytest.mark.parametrize("B,r,cin,cout", [(3, 8, 256, 256), (64, 8, 128, 128), (2, 16, 64, 64)])
+def test_conv3d_cl_half_operands(B, r, cin, cout):
+    """Per-tap implicit-GEMM conv with IEEE-half grid / weights vs fp64 on the same rounded operands."""
+    import torch.nn.functional as F
+
+    from p2pb_b200 import dense
+
+    g = torch.Generator(device="cuda").manual_seed(r + cin)
+    x = torch.randn(B, cin, r, r, r, device="cuda", generator=g).half()
+    w = (torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5).half()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    grid = x.permute(0, 2, 3, 4, 1).contiguous()
+    stats = torch.zeros(B * r ** 3 // 32, cout, 2, device="cuda")
+    out = dense.conv3d_cl(grid, dense.pack_conv3d_weight(w.float(), cin).half(), bias, B, r, cin, cout, stats=stats)
+    ref = F.conv3d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(B * r ** 3, cout)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-6, err
+    s = stats.double().view(B, -1, cout, 2).sum(1)
+    assert torch.allclose(s[..., 0], out.double().view(B, -1, cout).sum(1), rtol=1e-4, atol=1e-2)
