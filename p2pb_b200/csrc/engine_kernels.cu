@@ -288,6 +288,14 @@ P2PB_API int p2pb_col_stats(const float* x, int ld, int B, int rows, int C, floa
     return P2PB_OK;
 }
 
+static inline int p2pb_log2_exact(long long v)      // log2(v) if v is a power of two, else -1
+{
+    if (v <= 0 || (v & (v - 1)) != 0) return -1;
+    int l = 0;
+    while ((1LL << l) < v) ++l;
+    return l;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // affine_act: out[m, c] = act(x[m, c] * A[b, c] + Bc[b, c]),  b = m / rows_per_sample,  act: 0 none, 1 swish
 //   pool == 1 : out rows [M, ldo]
@@ -312,10 +320,11 @@ __device__ __forceinline__ float4 affine4(float4 x, float4 a, float4 b)
 
 // 4 float4 per thread (all loads issued before the first use): the pass is HBM-bound and one 16-byte load per thread
 // does not keep enough bytes in flight (measured 4.0 TB/s with 1, see profiles/)
+// lC4 / lrps >= 0: C/4 resp. rows_per_sample are powers of two (every layer of the network) -> shifts instead of divisions
 template <int ACT, typename OUT>
 __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                          const float* __restrict__ Bc, int rows_per_sample, int C,
-                                                         OUT* __restrict__ out, int ldo, unsigned total4)
+                                                         OUT* __restrict__ out, int ldo, unsigned total4, int lC4, int lrps)
 {
     const unsigned C4 = C >> 2;
     const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
@@ -326,10 +335,10 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
     for (int k = 0; k < 4; ++k) {
         const unsigned e = e0 + k * blockDim.x;
         if (e < total4) {
-            const unsigned mu = e / C4;
+            const unsigned mu = lC4 >= 0 ? (e >> lC4) : e / C4;
             c[k] = (int)(e - mu * C4) * 4;
             m[k] = mu;
-            const size_t b = mu / (unsigned)rows_per_sample;
+            const size_t b = lrps >= 0 ? (mu >> lrps) : mu / (unsigned)rows_per_sample;
             xv[k] = *reinterpret_cast<const float4*>(x + m[k] * ldx + c[k]);
             a[k] = __ldg(reinterpret_cast<const float4*>(A + b * C + c[k]));
             bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c[k]));
@@ -461,8 +470,8 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     if (pool == 1) {
         const long long total4 = (long long)M * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act");
-        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); affine_act_kernel<1, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
-        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); affine_act_kernel<0, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4); }
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); affine_act_kernel<1, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); affine_act_kernel<0, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
     } else {
         const long long total4 = (long long)(M / pool) * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act(pool)");
@@ -484,8 +493,8 @@ P2PB_API int p2pb_affine_act_f16(const float* x, int ldx, const float* A, const 
     const long long total4 = (long long)M * (C / 4);
     P2PB_CHECK_U32(total4, "affine_act_f16");
     __half* o = reinterpret_cast<__half*>(out);
-    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); affine_act_kernel<1, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4); }
-    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); affine_act_kernel<0, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4); }
+    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); affine_act_kernel<1, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); affine_act_kernel<0, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -956,14 +965,16 @@ P2PB_API int p2pb_voxelize_padded_sparse_f16(const float* feat, int ldf, int Cf,
 }
 
 // y = swish(x*A + B) of dense conv-output rows [B*r^3, ldx] -> zero-bordered padded input rows of the next conv
+// lC4 / lr >= 0: C/4 resp. r are powers of two -> the (sample, x, y, z) split of a voxel row is shifts and masks
 template <typename OUT>
 __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
                                                                 const float* __restrict__ Bc, int C, OUT* __restrict__ out, int ldo,
-                                                                int r, unsigned total4)
+                                                                int r, unsigned total4, int lC4, int lr)
 {
     const unsigned r3 = r * r * r;
     const unsigned C4 = C >> 2;
     const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+    const int P = r + 2;
     float4 xv[4], a[4], bb[4];
     size_t orow[4];
     int c[4];
@@ -971,11 +982,18 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
     for (int k = 0; k < 4; ++k) {      // 4 float4 per thread, loads first (see affine_act_kernel)
         const unsigned e = e0 + k * blockDim.x;
         if (e < total4) {
-            const unsigned vrow = e / C4;
+            const unsigned vrow = lC4 >= 0 ? (e >> lC4) : e / C4;
             c[k] = (int)(e - vrow * C4) * 4;
-            const int b = (int)(vrow / r3);
-            const int v = (int)(vrow - (unsigned)b * r3);
-            orow[k] = padded_row(b, v, r);
+            int b;
+            if (lr >= 0) {
+                b = (int)(vrow >> (3 * lr));
+                const unsigned v = vrow & (r3 - 1);
+                const int vx = (int)(v >> (2 * lr)), vy = (int)((v >> lr) & (unsigned)(r - 1)), vz = (int)(v & (unsigned)(r - 1));
+                orow[k] = (size_t)b * P * P * P + (size_t)(vx + 1) * P * P + (size_t)(vy + 1) * P + (vz + 1);
+            } else {
+                b = (int)(vrow / r3);
+                orow[k] = padded_row(b, (int)(vrow - (unsigned)b * r3), r);
+            }
             xv[k] = *reinterpret_cast<const float4*>(x + (size_t)vrow * ldx + c[k]);
             a[k] = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c[k]));
             bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c[k]));
@@ -996,7 +1014,7 @@ P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, con
     P2PB_CHECK_U32(total4, "affine_act_padded");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<float>);
-    affine_act_padded_kernel<float><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, C, r, total4);
+    affine_act_padded_kernel<float><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, C, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -1012,7 +1030,7 @@ P2PB_API int p2pb_affine_act_padded_f16(const float* x, int ldx, const float* A,
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<__half>);
     affine_act_padded_kernel<__half><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(
-        x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4);
+        x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
