@@ -472,11 +472,22 @@ class Engine:
         return self._side
 
     def _geometry(self, xt):
-        """FPS chain, ball-query indices, 3-NN indices/weights and the voxel CSR of every (level, resolution)."""
+        """FPS chain, ball-query indices, 3-NN indices/weights and the voxel CSR of every (level, resolution).
+        The level-0 voxel CSRs depend on the input coordinates only and come first: an event after them lets the main
+        stream start the first PVConv while the (latency-bound, one CTA per patch) FPS chain is still running."""
         B, N, W = self.B, self.N, self.W
         Ns = self.Ns
         n_levels = len(W["sa"])
         coords = [xt]
+        preps: Dict[tuple, dict] = {}
+        for P in W["sa"][0]["pv"]:
+            self.voxel_prep(preps, 0, xt, P["r"])
+        for L in W["fp"]:
+            if L["lvl"] == 0:
+                for P in L["pv"]:
+                    self.voxel_prep(preps, 0, xt, P["r"])
+        ev_prep0 = torch.cuda.Event()
+        ev_prep0.record(torch.cuda.current_stream())
         for i in range(n_levels):
             M = Ns[i + 1]
             idx = self.buf(f"fps{i}.idx", B, M, dtype=torch.int32)
@@ -495,14 +506,13 @@ class Engine:
             ww = self.buf(f"nn{j}.w", B, 3, Ns[lvl])
             call("p2pb_three_nn", _p(coords[lvl]), _p(coords[lvl + 1]), B, Ns[lvl], Ns[lvl + 1], _p(ix), _p(ww), _s())
             nn3.append((ix, ww))
-        preps: Dict[tuple, dict] = {}
         for i, L in enumerate(W["sa"]):
             for P in L["pv"]:
                 self.voxel_prep(preps, i, coords[i], P["r"])
         for L in W["fp"]:
             for P in L["pv"]:
                 self.voxel_prep(preps, L["lvl"], coords[L["lvl"]], P["r"])
-        return coords, nidx, nn3, preps
+        return coords, nidx, nn3, preps, ev_prep0
 
     # ------------------------------------------------------------------------------------------------ one evaluation
     def prepare_cond(self, x_cond):
@@ -537,7 +547,7 @@ class Engine:
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
-            coords, nidx, nn3, preps = self._geometry(xt)
+            coords, nidx, nn3, preps, ev_prep0 = self._geometry(xt)
             join = torch.cuda.Event()
             join.record(side)
         # ---- point rows of the raw coordinates
@@ -604,16 +614,23 @@ class Engine:
             dense.gemm_rows([cond], W["emd_w"], W["emd_b"], out=self.emd_all)
         else:
             self.emd_all = None
-        main.wait_event(join)       # geometry is needed from here on
+        main.wait_event(ev_prep0)   # level-0 voxel CSRs: all the first PVConv needs from the geometry stream
+        joined = False
         # ---- set abstraction
         feats = F0
         skips = []
         for i, L in enumerate(W["sa"]):
             skips.append(feats)
             n_pts = Ns[i]
+            if i > 0 and not joined:
+                main.wait_event(join)
+                joined = True
             for k, P in enumerate(L["pv"]):
                 prep = self.voxel_prep(preps, i, coords[i], P["r"])
                 feats = self.pvconv(f"sa{i}.pv{k}", P, feats, coords[i], prep, temb, n_pts)
+            if not joined:              # FPS centres / ball-query indices are needed from the first grouping on
+                main.wait_event(join)
+                joined = True
             M, K, cg = Ns[i + 1], L["K"], L["c_grp"]
             grp = self.buf(f"sa{i}.grp", B * M * K, pad32(cg + 3))
             call("p2pb_group_rows", _p(feats), int(feats.stride(0)), cg, _p(coords[i]), _p(coords[i + 1]), _p(nidx[i]), _p(grp),
