@@ -34,6 +34,9 @@ unsigned long long p2pb_launch_count(void);
  * coords [B,3,N] -> idx int32 [B,M]; centers [B,3,M] optional; scratch [B,N] fp32 only needed when N > 16384. */
 int p2pb_furthest_point_sampling(const float* coords, int B, int N, int M, int* idx, float* centers, float* scratch,
                                  void* stream);
+/* development aid: 0 = never use the thread-block-cluster FPS kernel, 1 = for whole clouds N in (16384, 196608] (default),
+ * 2 = also for patches of more than 2048 points */
+int p2pb_fps_set_cluster(int on);
 
 /* replaces gather_features_forward (pvcnn_sampling.cpp:6-24): out[b,c,j] = feat[b,c,idx[b,j]] */
 int p2pb_gather_features(const float* feat, const int* idx, float* out, int B, int C, int N, int M, void* stream);

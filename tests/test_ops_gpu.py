@@ -185,3 +185,25 @@ def test_knn_points_matches_oracle_bitwise(N, K, Q):
     ridx, rdist = OO.knn_points(q, pts, K)
     assert torch.equal(idx.cpu(), ridx)
     assert torch.equal(dist.cpu(), rdist)
+
+
+@pytest.mark.parametrize("B,N,M,snap", [(3, 8192, 2048, None), (2, 4000, 700, 16), (1, 30000, 900, None), (1, 150000, 600, 64),
+                                        (16, 8192, 256, None)])
+def test_fps_cluster_kernel_bit_exact(B, N, M, snap):
+    """Thread-block-cluster FPS (points split over 8 / 16 CTAs, DSMEM candidate exchange): indices identical to the
+    oracle (reference tie-break, heavy ties on the snapped lattices) and to the one-CTA-per-cloud kernels; fused centres."""
+    from oracle import ops as OO
+    from p2pb_b200 import ops
+    from p2pb_b200._lib import lib
+
+    coords = cloud(B, N, seed=N + M, snap=snap)
+    cd = coords.cuda()
+    lib().p2pb_fps_set_cluster(2)          # clusters for the patch sizes too (default: whole clouds only)
+    idx, centers = ops.furthest_point_sampling(cd, M, return_centers=True)
+    assert torch.equal(idx.cpu(), OO.furthest_point_sampling_forward(coords, M))
+    assert torch.equal(centers, torch.gather(cd, 2, idx.long()[:, None, :].expand(-1, 3, -1)))
+    lib().p2pb_fps_set_cluster(0)
+    try:
+        assert torch.equal(ops.furthest_point_sampling(cd, M), idx)
+    finally:
+        lib().p2pb_fps_set_cluster(1)
