@@ -37,7 +37,7 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
 
     r, cin, cout = 32, 64, 64
     if isinstance(getattr(model, "last_engine", None), DualEngine):
-        B = B // 2                       # the engine launches the kernel once per half-batch chain
+        B = B // model.last_engine.n     # the engine launches the kernel once per part-batch chain
     dt = torch.float16 if HALO_F16 else torch.float32
     g = torch.Generator(device=dev).manual_seed(0)
     X = dense.alloc_padded(B, cin, r, dev, dt)

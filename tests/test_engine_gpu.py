@@ -221,19 +221,20 @@ def test_voxelize_sparse_equals_dense_and_clears():
 
 
 def test_dual_chain_engine_equals_single_chain(monkeypatch):
-    """Batches >= 16 run as two half-batch chains on two streams in one CUDA graph (DualEngine).  Patches never
-    interact, every kernel is deterministic and per-sample, so the result must equal the single-chain engine
-    bit for bit, and graph replays must be reproducible."""
+    """With P2PB_CHAINS=2 a batch runs as two half-batch chains on two streams in one CUDA graph (DualEngine).
+    Patches never interact, every kernel is deterministic and per-sample, so the result must equal the single-chain
+    engine bit for bit, and graph replays must be reproducible."""
     from p2pb_b200.engine import DualEngine, Engine
 
     cfg = load_cfg("PVDS_PUNet")
     x = patch_input(16, 1024, seed=21).cuda()
     model, _ = build(cfg, backend="engine", head_scale=0.02)
+    monkeypatch.setenv("P2PB_CHAINS", "2")
     out_dual = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_chain"].clone()
     assert isinstance(model.last_engine, DualEngine)
     again = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_chain"]
     assert torch.equal(out_dual, again)
-    monkeypatch.setenv("P2PB_DUAL", "0")
+    monkeypatch.setenv("P2PB_CHAINS", "1")
     out_single = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_chain"]
     assert isinstance(model.last_engine, Engine)
     assert torch.equal(out_dual, out_single), (out_dual - out_single).abs().max()

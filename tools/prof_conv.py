@@ -1,9 +1,9 @@
-"""Dev tool: run the halo conv as the engine launches it (half operands, CTA pairs, B = 32 per chain) for ncu."""
+"""Dev tool: run the halo conv as the engine launches it (half operands, CTA pairs, B = 64 = the bench batch) for ncu."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from p2pb_b200 import dense
-B = 32
+B = 64
 for r, cin, cout in [(32, 64, 64), (16, 128, 128)]:
     grid = torch.randn(B, r, r, r, cin, device="cuda").half()
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda") / (27 * cin) ** 0.5
