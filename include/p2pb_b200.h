@@ -22,6 +22,8 @@ int p2pb_abi_version(void);
 /* development aid for tools/: bit 0 = rows-GEMM epilogue skips its global stores (timing experiments only) */
 int p2pb_debug_set(int flags);
 int p2pb_device_sm_count(void);
+/* programmatic dependent launch between the hot-path kernels (default 1); 0 = plain stream-ordered launches */
+int p2pb_set_pdl(int on);
 /* dynamic shared memory the persistent tensor-core kernels may use per CTA, KiB in [128, 227] (default 227) */
 int p2pb_set_smem_budget_kb(int kb);
 /* kernels launched (or captured into a CUDA graph) through this library since load */

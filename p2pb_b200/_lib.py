@@ -27,6 +27,8 @@ def lib() -> ctypes.CDLL:
                 "(or __graft_entry__.build()). There is no CPU fallback.")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.p2pb_last_error.restype = ctypes.c_char_p
+        if os.environ.get("P2PB_PDL") is not None:
+            check(_lib.p2pb_set_pdl(int(os.environ["P2PB_PDL"])), "p2pb_set_pdl")
         kb = os.environ.get("P2PB_SMEM_KB")
         if kb:
             check(_lib.p2pb_set_smem_budget_kb(int(kb)), "p2pb_set_smem_budget_kb")

@@ -49,3 +49,11 @@ P2PB_API int p2pb_set_smem_budget_kb(int kb)
     return P2PB_OK;
 }
 
+// programmatic dependent launch on the hot path (see P2PB_PDL_SYNC in common.cuh); 0 = plain stream-ordered launches
+int g_p2pb_pdl = 1;
+P2PB_API int p2pb_set_pdl(int on)
+{
+    g_p2pb_pdl = on ? 1 : 0;
+    return P2PB_OK;
+}
+

@@ -53,6 +53,34 @@ static inline void p2pb_prefer_max_smem(const void* kernel)
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// Programmatic dependent launch: every hot-path kernel starts with P2PB_PDL_SYNC() -- wait until the grids this launch depends
+// on have completed and flushed (a no-op for a plain launch), then allow the NEXT kernel in the stream to be launched --
+// and is launched through p2pb_launch(), which sets programmatic stream serialisation.  The successor's CTAs are then
+// scheduled as soon as SM resources free up and sit in their own griddepcontrol.wait until this grid has completed: the
+// ~2-4 us of launch latency between the ~210 dependent kernels of an evaluation overlaps the predecessor's tail.
+#define P2PB_PDL_SYNC()                                               \
+    do {                                                              \
+        asm volatile("griddepcontrol.wait;" ::: "memory");            \
+    } while (0)
+
+extern int g_p2pb_pdl;      // 1: launches carry the programmatic-serialisation attribute (p2pb_set_pdl)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t p2pb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_p2pb_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int p2pb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 extern int g_p2pb_smem_budget_kb;  // see p2pb_set_smem_budget_kb (abi_common.cu)

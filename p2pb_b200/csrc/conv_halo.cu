@@ -202,6 +202,7 @@ template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const HaloArgs a)
 {
+    P2PB_PDL_SYNC();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NC = PAIR ? 2 : 1;
@@ -631,20 +632,22 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
         cfg.blockDim = dim3(HALO_THREADS, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = s;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = g_p2pb_pdl ? 2 : 1;
         if (f16) P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, true>, mapW, mapX, a));
         else P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, false>, mapW, mapX, a));
     } else {
         int grid = n_sms;
         if (grid > a.total_tiles) grid = a.total_tiles;
-        if (f16) conv_halo_kernel<false, true><<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
-        else conv_halo_kernel<false, false><<<grid, HALO_THREADS, smem, s>>>(mapW, mapX, a);
+        if (f16) (void)p2pb_launch(conv_halo_kernel<false, true>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
+        else (void)p2pb_launch(conv_halo_kernel<false, false>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
     }
     P2PB_LAUNCH_OK();
     return P2PB_OK;

@@ -37,6 +37,7 @@ __device__ __forceinline__ void store4(__half* p, float4 v)
 __global__ void coords_to_rows_kernel(const float* __restrict__ coords, float* __restrict__ rows, int N, int ld, int col0,
                                       long long total)
 {
+    P2PB_PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long b = i / N;
@@ -51,6 +52,7 @@ __global__ void coords_to_rows_kernel(const float* __restrict__ coords, float* _
 __global__ void coords_to_rows_f16_kernel(const float* __restrict__ coords, __half* __restrict__ rows, int N, int ld, int col0,
                                           long long total)
 {
+    P2PB_PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long b = i / N;
@@ -68,7 +70,7 @@ P2PB_API int p2pb_coords_to_rows_f16(const float* coords, void* rows, int B, int
     const long long total = (long long)B * N;
     if (total == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)coords_to_rows_f16_kernel);
-    coords_to_rows_f16_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(coords, reinterpret_cast<__half*>(rows), N, ld,
+    (void)p2pb_launch(coords_to_rows_f16_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, coords, reinterpret_cast<__half*>(rows), N, ld,
                                                                                     col0, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -79,7 +81,7 @@ P2PB_API int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N,
     const long long total = (long long)B * N;
     if (total == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)coords_to_rows_kernel);
-    coords_to_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(coords, rows, N, ld, col0, total);
+    (void)p2pb_launch(coords_to_rows_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, coords, rows, N, ld, col0, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256) voxelize_cl_kernel(const float* __restric
                                                           const int* __restrict__ cnt, OUT* __restrict__ out, int Cp,
                                                           int N, int r3, unsigned total4)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
     const unsigned C4 = Cp >> 2;
@@ -146,7 +149,7 @@ P2PB_API int p2pb_voxelize_cl(const float* feat, int ldf, int Cf, const float* t
     P2PB_CHECK_U32(total4, "voxelize_cl");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)voxelize_cl_kernel<float>);
-    voxelize_cl_kernel<float><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
+    (void)p2pb_launch(voxelize_cl_kernel<float>, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf, temb, E, order, start, cnt, out,
                                                                                       Cp, N, r3, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -162,7 +165,7 @@ P2PB_API int p2pb_voxelize_cl_f16(const float* feat, int ldf, int Cf, const floa
     P2PB_CHECK_U32(total4, "voxelize_cl_f16");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)voxelize_cl_kernel<__half>);
-    voxelize_cl_kernel<__half><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt,
+    (void)p2pb_launch(voxelize_cl_kernel<__half>, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf, temb, E, order, start, cnt,
                                                                                        reinterpret_cast<__half*>(out), Cp, N, r3, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const float* __restrict__ 
                                                       float* __restrict__ coefA, float* __restrict__ coefB,
                                                       float* __restrict__ ymean)
 {
+    P2PB_PDL_SYNC();
     // threads = (channel within group) x (tile slice): every thread sums a strided slice of the tiles for one channel in
     // fp64, slices are combined in a fixed order -> deterministic; the group moments come from the channel sums.
     __shared__ double s_part[256][2];
@@ -255,7 +259,7 @@ P2PB_API int p2pb_gn_coef(const float* stats, int tiles, int B, int C, int group
                    "gn_coef: C=%d groups=%d (group width must be a power of two <= 128)", C, groups);
     if (B == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)gn_coef_kernel);
-    gn_coef_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(stats, tiles, C, groups, (float)rows_per_sample, gamma, beta, emd,
+    (void)p2pb_launch(gn_coef_kernel, dim3(B * groups), dim3(256), (size_t)(0), (cudaStream_t)stream, stats, tiles, C, groups, (float)rows_per_sample, gamma, beta, emd,
                                                                 ld_emd, emd_off, eps, coefA, coefB, ymean);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -265,6 +269,7 @@ P2PB_API int p2pb_gn_coef(const float* stats, int tiles, int B, int C, int group
 // (deep U-Net levels: 8..32 points per patch): out [B, C, 2] == the epilogue format with tiles = 1
 __global__ void col_stats_kernel(const float* __restrict__ x, int ld, int rows, int C, float* __restrict__ out)
 {
+    P2PB_PDL_SYNC();
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -283,7 +288,7 @@ P2PB_API int p2pb_col_stats(const float* x, int ld, int B, int rows, int C, floa
 {
     if (B == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)col_stats_kernel);
-    col_stats_kernel<<<dim3(p2pb_cdiv(C, 128), B), 128, 0, (cudaStream_t)stream>>>(x, ld, rows, C, out);
+    (void)p2pb_launch(col_stats_kernel, dim3(dim3(p2pb_cdiv(C, 128), B)), dim3(128), (size_t)(0), (cudaStream_t)stream, x, ld, rows, C, out);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
                                                          const float* __restrict__ Bc, int rows_per_sample, int C,
                                                          OUT* __restrict__ out, int ldo, unsigned total4, int lC4, int lrps)
 {
+    P2PB_PDL_SYNC();
     const unsigned C4 = C >> 2;
     const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
     float4 xv[4], a[4], bb[4];
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(256) affine_act_pool_kernel(const float* __res
                                                               const float* __restrict__ Bc, int rows_per_sample, int C,
                                                               int pool, float* __restrict__ out, int ldo, unsigned total4)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
     const unsigned C4 = C >> 2;
@@ -381,6 +388,7 @@ __global__ void __launch_bounds__(256) affine_act_gmax_kernel(const float* __res
                                                               int rows_per_cta, float* __restrict__ out, int ldo,
                                                               float* __restrict__ gmax)
 {
+    P2PB_PDL_SYNC();
     const int b = blockIdx.y;
     const int C4 = C >> 2;
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
@@ -409,6 +417,7 @@ __global__ void __launch_bounds__(256) gmax_minmax_kernel(const float* __restric
                                                           const float* __restrict__ A, const float* __restrict__ Bc, int act,
                                                           float* __restrict__ gmax, int total)
 {
+    P2PB_PDL_SYNC();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int b = e / C, c = e - b * C;
@@ -434,13 +443,14 @@ P2PB_API int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const
     if (total == 0) return P2PB_OK;
     P2PB_CHECK_ARG(tiles > 0, "gmax_minmax: tiles must be positive");
     p2pb_prefer_max_smem((const void*)gmax_minmax_kernel);
-    gmax_minmax_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(colmm, tiles, C, A, Bc, act, gmax, total);
+    (void)p2pb_launch(gmax_minmax_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, colmm, tiles, C, A, Bc, act, gmax, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
 
 __global__ void fill_kernel(float* p, float v, long long n)
 {
+    P2PB_PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -456,13 +466,13 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     if (gmax != nullptr) {
         P2PB_CHECK_ARG(pool == 1, "affine_act: gmax and pool are exclusive");
         p2pb_prefer_max_smem((const void*)fill_kernel);
-        fill_kernel<<<p2pb_cdiv((long long)B * C, 256), 256, 0, s>>>(gmax, -INFINITY, (long long)B * C);
+        (void)p2pb_launch(fill_kernel, dim3(p2pb_cdiv((long long)B * C, 256)), dim3(256), (size_t)(0), s, gmax, -INFINITY, (long long)B * C);
         P2PB_LAUNCH_OK();
         int rows_per_cta = p2pb_cdiv(rows_per_sample, p2pb_cdiv(4 * p2pb_num_sms(), B));
         if (rows_per_cta < 8) rows_per_cta = 8;
         dim3 grid(p2pb_cdiv(rows_per_sample, rows_per_cta), B);
-        if (act) { p2pb_prefer_max_smem((const void*)affine_act_gmax_kernel<1>); affine_act_gmax_kernel<1><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax); }
-        else { p2pb_prefer_max_smem((const void*)affine_act_gmax_kernel<0>); affine_act_gmax_kernel<0><<<grid, 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax); }
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_gmax_kernel<1>); (void)p2pb_launch(affine_act_gmax_kernel<1>, dim3(grid), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_gmax_kernel<0>); (void)p2pb_launch(affine_act_gmax_kernel<0>, dim3(grid), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, rows_per_cta, out, ldo, gmax); }
         P2PB_LAUNCH_OK();
         return P2PB_OK;
     }
@@ -470,13 +480,13 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     if (pool == 1) {
         const long long total4 = (long long)M * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act");
-        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); affine_act_kernel<1, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
-        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); affine_act_kernel<0, float><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); (void)p2pb_launch(affine_act_kernel<1, float>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); (void)p2pb_launch(affine_act_kernel<0, float>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
     } else {
         const long long total4 = (long long)(M / pool) * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act(pool)");
-        if (act) { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<1>); affine_act_pool_kernel<1><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
-        else { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<0>); affine_act_pool_kernel<0><<<p2pb_cdiv(total4, 256), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<1>); (void)p2pb_launch(affine_act_pool_kernel<1>, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_pool_kernel<0>); (void)p2pb_launch(affine_act_pool_kernel<0>, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, pool, out, ldo, total4); }
     }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -493,8 +503,8 @@ P2PB_API int p2pb_affine_act_f16(const float* x, int ldx, const float* A, const 
     const long long total4 = (long long)M * (C / 4);
     P2PB_CHECK_U32(total4, "affine_act_f16");
     __half* o = reinterpret_cast<__half*>(out);
-    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); affine_act_kernel<1, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
-    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); affine_act_kernel<0, __half><<<p2pb_cdiv(total4, 1024), 256, 0, s>>>(x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); (void)p2pb_launch(affine_act_kernel<1, __half>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); (void)p2pb_launch(affine_act_kernel<0, __half>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -511,6 +521,7 @@ __global__ void __launch_bounds__(256) devox_cl_kernel(const float* __restrict__
                                                        const float* __restrict__ pA, const float* __restrict__ pB,
                                                        float* __restrict__ out, int ldo, int C, int N, int r, unsigned total4)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
     const unsigned C4 = C >> 2;
@@ -568,7 +579,7 @@ P2PB_API int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, cons
     P2PB_CHECK_U32(total4, "devox_cl");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)devox_cl_kernel);
-    devox_cl_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(ncoords, raw, ldg, A, Bc, se, praw, ldp, pA, pB, out,
+    (void)p2pb_launch(devox_cl_kernel, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, ncoords, raw, ldg, A, Bc, se, praw, ldp, pA, pB, out,
                                                                             ldo, C, N, r, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -584,6 +595,7 @@ __global__ void __launch_bounds__(256) group_rows_kernel(const float* __restrict
                                                          const int* __restrict__ idx, float* __restrict__ out, int ldo, int N,
                                                          int M, int U, unsigned total)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const unsigned C4 = (Cf >> 2) + 1;
@@ -615,7 +627,7 @@ P2PB_API int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* co
     P2PB_CHECK_U32(total, "group_rows");
     if (total == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)group_rows_kernel);
-    group_rows_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
+    (void)p2pb_launch(group_rows_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
                                                                              U, total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -628,6 +640,7 @@ __global__ void __launch_bounds__(256) interp_rows_kernel(const float* __restric
                                                           const float* __restrict__ w, float* __restrict__ out, int ldo, int C,
                                                           int N, int M, unsigned total4)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
     const unsigned C4 = C >> 2;
@@ -660,7 +673,7 @@ P2PB_API int p2pb_interp_rows(const float* f, int ldf, const int* idx, const flo
     P2PB_CHECK_U32(total4, "interp_rows");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)interp_rows_kernel);
-    interp_rows_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(f, ldf, idx, w, out, ldo, C, N, M, total4);
+    (void)p2pb_launch(interp_rows_kernel, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, f, ldf, idx, w, out, ldo, C, N, M, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -674,6 +687,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
                                                            int ldw, const float* __restrict__ bias, int K, int O, int act,
                                                            float* __restrict__ out, int ldo, long long total)
 {
+    P2PB_PDL_SYNC();
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= total) return;
@@ -700,7 +714,7 @@ P2PB_API int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw
     const long long total = (long long)B * O;
     if (total == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)linear_small_kernel);
-    linear_small_kernel<<<p2pb_cdiv(total * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, W, ldw, bias, K, O, act, out, ldo,
+    (void)p2pb_launch(linear_small_kernel, dim3(p2pb_cdiv(total * 32, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, in, ldi, W, ldw, bias, K, O, act, out, ldo,
                                                                                     total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -714,6 +728,7 @@ P2PB_API int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw
 __global__ void __launch_bounds__(1024) attention_small_kernel(const float* __restrict__ qkv, int ldq, int H, int N,
                                                                float* __restrict__ out, int ldo)
 {
+    P2PB_PDL_SYNC();
     __shared__ float sq[32][65], sk[32][65], sv[32][65], sctx[32][33];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 32
@@ -755,7 +770,7 @@ P2PB_API int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N
     P2PB_CHECK_ARG(N > 0 && N <= 64, "attention_small: N=%d tokens (bottleneck only, <= 64)", N);
     if (B == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)attention_small_kernel);
-    attention_small_kernel<<<B * H, dim3(32, 32), 0, (cudaStream_t)stream>>>(qkv, ldq, H, N, out, ldo);
+    (void)p2pb_launch(attention_small_kernel, dim3(B * H), dim3(dim3(32, 32)), (size_t)(0), (cudaStream_t)stream, qkv, ldq, H, N, out, ldo);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -769,6 +784,7 @@ __global__ void bridge_update_kernel(const float* __restrict__ xt, const float* 
                                      const float* __restrict__ coef, int clip, float* __restrict__ xt_next,
                                      float* __restrict__ pred_x0, int N, long long total)
 {
+    P2PB_PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long b = i / N;
@@ -791,7 +807,7 @@ P2PB_API int p2pb_bridge_update(const float* xt, const float* eps, int lde, cons
     const long long total = (long long)B * N;
     if (total == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)bridge_update_kernel);
-    bridge_update_kernel<<<p2pb_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, eps, lde, coef, clip, xt_next, pred_x0, N,
+    (void)p2pb_launch(bridge_update_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, xt, eps, lde, coef, clip, xt_next, pred_x0, N,
                                                                                 total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -815,6 +831,7 @@ __global__ void __launch_bounds__(256) voxelize_padded_kernel(const float* __res
                                                               const int* __restrict__ cnt, float* __restrict__ out, int Cp,
                                                               int N, int r, unsigned total4)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
     const unsigned r3 = r * r * r;
@@ -864,7 +881,7 @@ P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const floa
     P2PB_CHECK_U32(total4, "voxelize_padded");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)voxelize_padded_kernel);
-    voxelize_padded_kernel<<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(feat, ldf, Cf, temb, E, order, start, cnt, out,
+    (void)p2pb_launch(voxelize_padded_kernel, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf, temb, E, order, start, cnt, out,
                                                                                    Cp, N, r, total4);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -883,6 +900,7 @@ __global__ void __launch_bounds__(256) voxelize_sparse_kernel(const float* __res
                                                               OUT* __restrict__ out, int Cp, int N, int r, int clear,
                                                               unsigned total4)
 {
+    P2PB_PDL_SYNC();
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total4) return;
     const unsigned r3 = r * r * r;
@@ -938,11 +956,11 @@ static int voxelize_sparse_impl(const float* feat, int ldf, int Cf, const float*
     if (total4 == 0) return P2PB_OK;
     if (f16) {
         p2pb_prefer_max_smem((const void*)voxelize_sparse_kernel<__half>);
-        voxelize_sparse_kernel<__half><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (void)p2pb_launch(voxelize_sparse_kernel<__half>, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
             feat, ldf, Cf, temb, E, order, ind, start, cnt, reinterpret_cast<__half*>(out), Cp, N, r, clear, total4);
     } else {
         p2pb_prefer_max_smem((const void*)voxelize_sparse_kernel<float>);
-        voxelize_sparse_kernel<float><<<p2pb_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (void)p2pb_launch(voxelize_sparse_kernel<float>, dim3(p2pb_cdiv(total4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
             feat, ldf, Cf, temb, E, order, ind, start, cnt, reinterpret_cast<float*>(out), Cp, N, r, clear, total4);
     }
     P2PB_LAUNCH_OK();
@@ -971,6 +989,7 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
                                                                 const float* __restrict__ Bc, int C, OUT* __restrict__ out, int ldo,
                                                                 int r, unsigned total4, int lC4, int lr)
 {
+    P2PB_PDL_SYNC();
     const unsigned r3 = r * r * r;
     const unsigned C4 = C >> 2;
     const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
@@ -1014,7 +1033,7 @@ P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, con
     P2PB_CHECK_U32(total4, "affine_act_padded");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<float>);
-    affine_act_padded_kernel<float><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(x, ldx, A, Bc, C, out, C, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
+    (void)p2pb_launch(affine_act_padded_kernel<float>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, ldx, A, Bc, C, out, C, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -1029,7 +1048,7 @@ P2PB_API int p2pb_affine_act_padded_f16(const float* x, int ldx, const float* A,
     P2PB_CHECK_U32(total4, "affine_act_padded_f16");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<__half>);
-    affine_act_padded_kernel<__half><<<p2pb_cdiv(total4, 1024), 256, 0, (cudaStream_t)stream>>>(
+    (void)p2pb_launch(affine_act_padded_kernel<__half>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;

@@ -234,6 +234,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ CUtensorMap mapD, const PArgs a)
 {
+    P2PB_PDL_SYNC();
     using Cfg = PCfg<BN>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -586,13 +587,15 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
     cfg.blockDim = dim3(P_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_p2pb_pdl ? 2 : 1;
     P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_persist_kernel<BN, CL>, maps[0], maps[1], maps[2], maps[3], maps[4], a));
     P2PB_LAUNCH_OK();
     return P2PB_OK;

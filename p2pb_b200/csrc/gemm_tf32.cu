@@ -171,6 +171,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                  const GemmArgs args, const int stages)
 {
+    P2PB_PDL_SYNC();
     constexpr int B_STAGE_BYTES = BN * BK * 4;
     constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     constexpr int CW = BN >= 32 ? 32 : 16;  // epilogue chunk width (columns per tcgen05.ld)
@@ -398,7 +399,7 @@ int launch_gemm(const CUtensorMap* maps, const GemmArgs& a, cudaStream_t s)
     dim3 grid(a.n_total / BN, p2pb_cdiv(a.M, BM));
     P2PB_CHECK_ARG(grid.y <= 65535u, "gemm: M=%d needs %u row tiles (> 65535): split the batch", a.M, grid.y);
     p2pb_prefer_max_smem((const void*)gemm_tf32_kernel<BN>);
-    gemm_tf32_kernel<BN><<<grid, GEMM_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], a, stages);
+    (void)p2pb_launch(gemm_tf32_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), s, maps[0], maps[1], maps[2], maps[3], a, stages);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

@@ -34,6 +34,7 @@ template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_reg_kernel(const float* __restrict__ coords, int N, int M,
                                                        int* __restrict__ idx, float* __restrict__ centers)
 {
+    P2PB_PDL_SYNC();
     extern __shared__ float s_xyz[];  // [3][N]
     __shared__ unsigned long long s_slot[2][32];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(T, 1) fps_reg_kernel(const float* __restrict__
 __global__ void __launch_bounds__(1024, 1) fps_global_kernel(const float* __restrict__ coords, int N, int M,
                                                              float* __restrict__ dist, int* __restrict__ idx)
 {
+    P2PB_PDL_SYNC();
     __shared__ unsigned long long s_slot[2][32];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     coords += (size_t)b * 3 * N;
@@ -139,6 +141,7 @@ template <int CL>
 __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(const float* __restrict__ coords, int N, int M, int chunk,
                                                               int* __restrict__ idx, float* __restrict__ centers)
 {
+    P2PB_PDL_SYNC();
     extern __shared__ float s_pts[];                 // [4][chunk]: x, y, z, running min distance
     __shared__ unsigned long long s_warp[32];
     __shared__ int s_warp_loc[32];
@@ -279,7 +282,7 @@ static int launch_fps_reg(const float* coords, int B, int N, int M, int* idx, fl
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(fps_reg_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p2pb_prefer_max_smem((const void*)fps_reg_kernel<P, T>);
-    fps_reg_kernel<P, T><<<B, T, smem, s>>>(coords, N, M, idx, centers);
+    (void)p2pb_launch(fps_reg_kernel<P, T>, dim3(B), dim3(T), (size_t)(smem), s, coords, N, M, idx, centers);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -320,7 +323,7 @@ P2PB_API int p2pb_furthest_point_sampling(const float* coords, int B, int N, int
     P2PB_CHECK_ARG(scratch != nullptr, "fps: N=%d > 16384 needs a B*N float scratch buffer", N);
     P2PB_CHECK_ARG(centers == nullptr, "fps: fused centre gather only for N <= 16384");
     p2pb_prefer_max_smem((const void*)fps_global_kernel);
-    fps_global_kernel<<<B, 1024, 0, s>>>(coords, N, M, scratch, idx);
+    (void)p2pb_launch(fps_global_kernel, dim3(B), dim3(1024), (size_t)(0), s, coords, N, M, scratch, idx);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -333,6 +336,7 @@ P2PB_API int p2pb_furthest_point_sampling(const float* coords, int B, int N, int
 __global__ void gather_cf_kernel(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
                                  int C, int N, int M)
 {
+    P2PB_PDL_SYNC();
     const int b = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= M) return;
@@ -349,7 +353,7 @@ P2PB_API int p2pb_gather_features(const float* feat, const int* idx, float* out,
     if (B == 0 || M == 0) return P2PB_OK;
     dim3 grid(p2pb_cdiv(M, 256), C < 64 ? C : 64, B);
     p2pb_prefer_max_smem((const void*)gather_cf_kernel);
-    gather_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, idx, out, C, N, M);
+    (void)p2pb_launch(gather_cf_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, idx, out, C, N, M);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(WARPS * 32) ball_query_kernel(const float* __r
                                                                 const float* __restrict__ points, int M, int N,
                                                                 float r2, int U, int* __restrict__ out)
 {
+    P2PB_PDL_SYNC();
     extern __shared__ float s_pts[];  // [3][N]
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     points += (size_t)b * 3 * N;
@@ -414,7 +419,7 @@ P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, i
     const int want = p2pb_cdiv(2 * p2pb_num_sms(), B);
     if (gx > want) gx = want < 1 ? 1 : want;
     p2pb_prefer_max_smem((const void*)ball_query_kernel<WARPS>);
-    ball_query_kernel<WARPS><<<dim3(gx, B), WARPS * 32, smem, (cudaStream_t)stream>>>(centers, points, M, N, r2, U, out);
+    (void)p2pb_launch(ball_query_kernel<WARPS>, dim3(dim3(gx, B)), dim3(WARPS * 32), (size_t)(smem), (cudaStream_t)stream, centers, points, M, N, r2, U, out);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -428,6 +433,7 @@ P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, i
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ points, const float* __restrict__ centers,
                                                        int N, int M, int* __restrict__ idx, float* __restrict__ w)
 {
+    P2PB_PDL_SYNC();
     extern __shared__ float s_c[];  // [3][M]
     const int b = blockIdx.y;
     points += (size_t)b * 3 * N;
@@ -465,6 +471,7 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
 __global__ void interp_cf_kernel(const float* __restrict__ cfeat, const int* __restrict__ idx, const float* __restrict__ w,
                                  float* __restrict__ out, int C, int N, int M)
 {
+    P2PB_PDL_SYNC();
     const int b = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
@@ -493,7 +500,7 @@ P2PB_API int p2pb_three_nn(const float* points, const float* centers, int B, int
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p2pb_prefer_max_smem((const void*)three_nn_kernel);
-    three_nn_kernel<<<dim3(p2pb_cdiv(N, 256), B), 256, smem, (cudaStream_t)stream>>>(points, centers, N, M, idx, w);
+    (void)p2pb_launch(three_nn_kernel, dim3(dim3(p2pb_cdiv(N, 256), B)), dim3(256), (size_t)(smem), (cudaStream_t)stream, points, centers, N, M, idx, w);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -506,7 +513,7 @@ P2PB_API int p2pb_three_nn_interpolate(const float* points, const float* centers
     P2PB_CHECK_ARG(C > 0, "three_nn_interpolate: bad C");
     dim3 grid(p2pb_cdiv(N, 256), C < 64 ? C : 64, B);
     p2pb_prefer_max_smem((const void*)interp_cf_kernel);
-    interp_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cfeat, idx, w, out, C, N, M);
+    (void)p2pb_launch(interp_cf_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, cfeat, idx, w, out, C, N, M);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(T, 1) voxel_prep_kernel(const int* __restrict_
                                                           int* __restrict__ order, int* __restrict__ start,
                                                           int* __restrict__ cnt)
 {
+    P2PB_PDL_SYNC();
     extern __shared__ unsigned s_key[];  // [Np2]
     __shared__ double s_red[3][T / 32];
     __shared__ float s_redf[T / 32];
@@ -149,7 +150,7 @@ static int launch_voxel_prep(const int* icoords, const float* fcoords, int B, in
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(voxel_prep_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p2pb_prefer_max_smem((const void*)voxel_prep_kernel<1024>);
-    voxel_prep_kernel<1024><<<B, 1024, smem, s>>>(icoords, fcoords, N, Np2, r, normalize, eps, norm_coords, ind, order,
+    (void)p2pb_launch(voxel_prep_kernel<1024>, dim3(B), dim3(1024), (size_t)(smem), s, icoords, fcoords, N, Np2, r, normalize, eps, norm_coords, ind, order,
                                                   start, cnt);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) voxelize_cf_kernel(const float* __restric
                                                           const int* __restrict__ start, const int* __restrict__ cnt,
                                                           float* __restrict__ out, int C, int N, int r3)
 {
+    P2PB_PDL_SYNC();
     const int b = blockIdx.z;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= r3) return;
@@ -203,7 +205,7 @@ P2PB_API int p2pb_avg_voxelize(const float* feat, const int* coords, int B, int 
     const int r3 = r * r * r;
     dim3 grid(p2pb_cdiv(r3, 256), C < 32 ? C : 32, B);
     p2pb_prefer_max_smem((const void*)voxelize_cf_kernel);
-    voxelize_cf_kernel<<<grid, 256, 0, s>>>(feat, scratch_order, scratch_start, cnt, out, C, N, r3);
+    (void)p2pb_launch(voxelize_cf_kernel, dim3(grid), dim3(256), (size_t)(0), s, feat, scratch_order, scratch_start, cnt, out, C, N, r3);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -247,6 +249,7 @@ __device__ __forceinline__ TriCorners tri_corners(float x, float y, float z, int
 __global__ void __launch_bounds__(256) devox_cf_kernel(const float* __restrict__ coords, const float* __restrict__ grid,
                                                        float* __restrict__ out, int C, int N, int r)
 {
+    P2PB_PDL_SYNC();
     const int b = blockIdx.z;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -274,7 +277,7 @@ P2PB_API int p2pb_trilinear_devoxelize(const float* coords, const float* grid, i
     if (B == 0) return P2PB_OK;
     dim3 g(p2pb_cdiv(N, 256), C < 32 ? C : 32, B);
     p2pb_prefer_max_smem((const void*)devox_cf_kernel);
-    devox_cf_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(coords, grid, out, C, N, r);
+    (void)p2pb_launch(devox_cf_kernel, dim3(g), dim3(256), (size_t)(0), (cudaStream_t)stream, coords, grid, out, C, N, r);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
