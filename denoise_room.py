@@ -4,7 +4,8 @@
 with ``torchrun`` (one process per GPU), the per-point running mean of the reference (:262-289) becomes per-rank
 sums + ONE ``all_reduce`` (NCCL over NVLink) -- see ``p2pb_b200/parallel.py``.
 
-KDTree radius patches (CPU, sklearn) -> pad with jittered duplicates / FPS down to ``npoints`` -> batched
+radius patches (device radius query, ``ops.radius_query``; the reference builds a CPU KD-tree, :454-465) -> pad with
+jittered duplicates / FPS down to ``npoints`` -> batched
 ``P2PB.sample`` -> reassembly -> ``.ply``.  Deviations from the reference, switchable with ``--strict_ref``: the
 reference drops the last patch of every chunk (:498-505) -- here every patch is denoised; ``fpsample`` (absent) is
 replaced by this repo's FPS kernel (start index 0).
@@ -130,15 +131,16 @@ def main(argv=None):
             room_dino = np.load(fp)
             if "arkit" not in str(cfg.data.dataset).lower():
                 room_dino = room_dino.T
-    from sklearn import neighbors
-
-    tree = neighbors.KDTree(room_points, metric="l2")
     npts = cfg.data.npoints
     n_centers = int(np.ceil(room_points.shape[0] / npts) * cfg.k)
-    c = torch.from_numpy(room_points.T.copy()).float().unsqueeze(0).to(cfg.gpu)
-    centers = room_points[ops.furthest_point_sampling(c, n_centers)[0].long().cpu().numpy()]
+    pts_dev = torch.from_numpy(room_points).float().to(cfg.gpu).contiguous()
+    c = pts_dev.t().contiguous().unsqueeze(0)
+    center_idx = ops.furthest_point_sampling(c, n_centers)[0].long()
     radius = 0.3 if "scannet" in str(cfg.data.dataset).lower() else 0.5
-    idx_lists = tree.query_radius(centers, r=radius, return_distance=False)
+    # KDTree.query_radius of the reference (denoise_room.py:454-465) on the device: CSR with ascending indices per centre
+    off, idx = ops.radius_query(pts_dev[center_idx].contiguous(), pts_dev, radius)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+    idx_lists = [idx[off[i]:off[i + 1]] for i in range(n_centers)]
     xyz, rgb, dino, idxs, cuts = create_patches(room_points, npts, idx_lists, room_colors, room_dino, cfg.gpu)
     P = xyz.shape[0]
     lo, hi = shard_range(P, rank, world)

@@ -22,7 +22,7 @@ int p2pb_abi_version(void);
 /* development aid for tools/: bit 0 = rows-GEMM epilogue skips its global stores (timing experiments only) */
 int p2pb_debug_set(int flags);
 int p2pb_device_sm_count(void);
-/* programmatic dependent launch between the hot-path kernels (default 1); 0 = plain stream-ordered launches */
+/* programmatic dependent launch between the hot-path kernels; default 0 = plain stream-ordered launches (measured faster) */
 int p2pb_set_pdl(int on);
 /* dynamic shared memory the persistent tensor-core kernels may use per CTA, KiB in [128, 227] (default 227) */
 int p2pb_set_smem_budget_kb(int kb);
@@ -90,6 +90,15 @@ int p2pb_emd_approx(const float* xyz1, const float* xyz2, int B, int n, int m, f
 /* replaces pytorch3d.ops.knn_points as called at /root/reference/denoise_object.py:90-91 (un-vendored dependency):
  * queries [Q,3], pts [N,3] -> idx int32 [Q,K] ascending squared distance (ties: lower index), dist [Q,K] optional */
 int p2pb_knn_points(const float* queries, const float* pts, int Q, int N, int K, int* idx, float* dist, void* stream);
+
+/* ---- patch creation (denoise_room) --------------------------------------------------------------------------- */
+
+/* replaces sklearn KDTree.query_radius as called at /root/reference/denoise_room.py:454-465: all points within `radius` of
+ * each centre, as CSR with ascending point indices per centre.  centers [P,3], pts [N,3]; pass 1 -> counts int32 [P];
+ * the caller forms offsets int64 [P+1] (exclusive scan); pass 2 -> indices int32 [offsets[P]]. */
+int p2pb_radius_count(const float* centers, const float* pts, int P, int N, float radius, int* counts, void* stream);
+int p2pb_radius_fill(const float* centers, const float* pts, int P, int N, float radius, const long long* offsets, int* indices,
+                     void* stream);
 
 /* ==== fused channels-last engine (rows [M, ld] fp32, ld multiple of 4) ====================== */
 

@@ -189,6 +189,21 @@ def knn_points(queries, points, K):
     return idx, dist
 
 
+def radius_query(centers, points, radius):
+    """KDTree.query_radius contract restated (ascending indices): (offsets int64 [P+1], indices int32)."""
+    centers = centers.contiguous().float()
+    points = points.contiguous().float()
+    P, N = centers.shape[0], points.shape[0]
+    counts = torch.empty((P,), dtype=torch.int32)
+    lib().ora_radius_query(_f(centers), _f(points), P, N, ctypes.c_float(radius), _i(counts), None, None)
+    offsets = torch.zeros((P + 1,), dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts, 0)
+    indices = torch.empty((int(offsets[-1]),), dtype=torch.int32)
+    lib().ora_radius_query(_f(centers), _f(points), P, N, ctypes.c_float(radius), _i(counts),
+                           ctypes.c_void_p(offsets.data_ptr()), _i(indices))
+    return offsets, indices
+
+
 _BACKWARD = ["avg_voxelize_backward", "trilinear_devoxelize_backward", "three_nearest_neighbors_interpolate_backward",
              "grouping_backward", "gather_features_backward"]
 

@@ -477,3 +477,26 @@ ORA_API void ora_knn_points(const float *queries, const float *pts, int Q, int N
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Radius query: sklearn.neighbors.KDTree.query_radius as called by denoise_room.py:454-465 (a dependency, not reference
+ * code; its result ORDER is tree-traversal order, i.e. unspecified -- parity unpinned at this boundary).  Restated contract:
+ * every point with squared distance <= radius^2 (fp32, sqdist3 order), ascending index.  counts [P]; if indices != NULL
+ * they are written at offsets[c] (offsets = exclusive scan of counts).
+ * ------------------------------------------------------------------------------------------- */
+ORA_API void ora_radius_query(const float *centers, const float *pts, int P, int N, float radius, int32_t *counts,
+                              const int64_t *offsets, int32_t *indices)
+{
+    const float r2 = radius * radius;
+    for (int c = 0; c < P; ++c) {
+        int n = 0;
+        for (int i = 0; i < N; ++i) {
+            const float d = sqdist3(pts[i * 3] - centers[c * 3], pts[i * 3 + 1] - centers[c * 3 + 1], pts[i * 3 + 2] - centers[c * 3 + 2]);
+            if (d <= r2) {
+                if (indices) indices[offsets[c] + n] = i;
+                ++n;
+            }
+        }
+        counts[c] = n;
+    }
+}
+

@@ -49,8 +49,10 @@ P2PB_API int p2pb_set_smem_budget_kb(int kb)
     return P2PB_OK;
 }
 
-// programmatic dependent launch on the hot path (see P2PB_PDL_SYNC in common.cuh); 0 = plain stream-ordered launches
-int g_p2pb_pdl = 1;
+// programmatic dependent launch on the hot path (see P2PB_PDL_SYNC in common.cuh); 0 = plain stream-ordered launches.
+// Default off: measured on B200 inside the CUDA graph, early launch_dependents + wait made the evaluation 6 % SLOWER
+// (311 vs 331 patches/s): the successors' CTAs become resident and wait while the persistent kernels still need the SMs.
+int g_p2pb_pdl = 0;
 P2PB_API int p2pb_set_pdl(int on)
 {
     g_p2pb_pdl = on ? 1 : 0;

@@ -349,3 +349,89 @@ P2PB_API int p2pb_knn_points(const float* queries, const float* pts, int Q, int 
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
+
+// =========================================================================================================
+// Radius query for room patch creation: all points of the room within `radius` of each patch centre.
+// Replaces sklearn.neighbors.KDTree(room_points).query_radius(centers, r) (denoise_room.py:454-465), a CPU KD-tree on
+// up to millions of points that left the GPUs idle between chunks.  Result: CSR (offsets, indices)
+// with the indices of every centre in ASCENDING point order (sklearn's order is traversal order, i.e. unspecified; the
+// reference only indexes with it).  Membership: squared distance <= radius^2 in fp32 with the library's sqdist3 order.
+// Two passes of the same brute-force scan (the cloud is L2-resident: 2 M points = 24 MB): count, then -- after an
+// exclusive scan of the counts -- an index-ordered block compaction.  One CTA per centre.
+// =========================================================================================================
+__global__ void __launch_bounds__(1024) radius_count_kernel(const float* __restrict__ centers, const float* __restrict__ pts, int N,
+                                                            float r2, int* __restrict__ counts)
+{
+    __shared__ int s_cnt[32];
+    const int c = blockIdx.x, t = threadIdx.x;
+    const float cx = centers[c * 3], cy = centers[c * 3 + 1], cz = centers[c * 3 + 2];
+    int n = 0;
+    for (int i = t; i < N; i += 1024) n += sqdist3(pts[i * 3] - cx, pts[i * 3 + 1] - cy, pts[i * 3 + 2] - cz) <= r2 ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((t & 31) == 0) s_cnt[t >> 5] = n;
+    __syncthreads();
+    if (t < 32) {
+        int v = s_cnt[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (t == 0) counts[c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(1024) radius_fill_kernel(const float* __restrict__ centers, const float* __restrict__ pts, int N,
+                                                           float r2, const long long* __restrict__ offsets, int* __restrict__ indices)
+{
+    __shared__ int s_scan[32];
+    __shared__ int s_base;
+    const int c = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float cx = centers[c * 3], cy = centers[c * 3 + 1], cz = centers[c * 3 + 2];
+    int* out = indices + offsets[c];
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < N; i0 += 1024) {
+        const int i = i0 + t;
+        const bool in = i < N && sqdist3(pts[i * 3] - cx, pts[i * 3 + 1] - cy, pts[i * 3 + 2] - cz) <= r2;
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        const int within = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_scan[warp] = __popc(m);
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_scan[lane];
+            int inc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += n;
+            }
+            s_scan[lane] = inc - w;
+        }
+        __syncthreads();
+        const int base = s_base;
+        if (in) out[base + s_scan[warp] + within] = i;
+        __syncthreads();
+        if (t == 1023) s_base = base + s_scan[31] + __popc(m);
+        __syncthreads();
+    }
+}
+
+// centers [P,3], pts [N,3] -> counts int32 [P]
+P2PB_API int p2pb_radius_count(const float* centers, const float* pts, int P, int N, float radius, int* counts, void* stream)
+{
+    P2PB_CHECK_ARG(P >= 0 && N > 0 && radius >= 0.f, "radius_count: bad sizes");
+    if (P == 0) return P2PB_OK;
+    radius_count_kernel<<<P, 1024, 0, (cudaStream_t)stream>>>(centers, pts, N, radius * radius, counts);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// offsets int64 [P+1] = exclusive scan of counts (done by the caller); indices int32 [offsets[P]], ascending per centre
+P2PB_API int p2pb_radius_fill(const float* centers, const float* pts, int P, int N, float radius, const long long* offsets,
+                              int* indices, void* stream)
+{
+    P2PB_CHECK_ARG(P >= 0 && N > 0 && radius >= 0.f, "radius_fill: bad sizes");
+    if (P == 0) return P2PB_OK;
+    radius_fill_kernel<<<P, 1024, 0, (cudaStream_t)stream>>>(centers, pts, N, radius * radius, offsets, indices);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}

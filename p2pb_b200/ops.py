@@ -225,3 +225,20 @@ def knn_points(queries: torch.Tensor, points: torch.Tensor, K: int, return_dist:
         call("p2pb_knn_points", _ptr(queries), _ptr(points), Q, N, int(K), _ptr(idx), _ptr(dist), _stream())
     return (idx, dist) if return_dist else idx
 
+
+def radius_query(centers: torch.Tensor, points: torch.Tensor, radius: float):
+    """All ``points [N,3]`` within ``radius`` of each ``centers [P,3]`` row (``KDTree.query_radius`` of
+    denoise_room.py:454-465) -> (offsets int64 [P+1], indices int32 [offsets[-1]]), indices ascending per centre."""
+    _chk(centers, torch.float32, "centers", 2)
+    _chk(points, torch.float32, "points", 2)
+    P, N = centers.shape[0], points.shape[0]
+    dev = points.device
+    counts = torch.empty((P,), dtype=torch.int32, device=dev)
+    offsets = torch.zeros((P + 1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_radius_count", _ptr(centers), _ptr(points), P, N, _f(float(radius)), _ptr(counts), _stream())
+        offsets[1:] = torch.cumsum(counts, 0)
+        indices = torch.empty((int(offsets[-1].item()),), dtype=torch.int32, device=dev)
+        call("p2pb_radius_fill", _ptr(centers), _ptr(points), P, N, _f(float(radius)), _ptr(offsets), _ptr(indices), _stream())
+    return offsets, indices
+

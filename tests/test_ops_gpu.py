@@ -207,3 +207,17 @@ def test_fps_cluster_kernel_bit_exact(B, N, M, snap):
         assert torch.equal(ops.furthest_point_sampling(cd, M), idx)
     finally:
         lib().p2pb_fps_set_cluster(1)
+
+
+@pytest.mark.parametrize("N,P,radius", [(50000, 37, 0.2), (3000, 5, 10.0), (4097, 9, 0.0)])
+def test_radius_query_matches_oracle(N, P, radius):
+    """Device radius query (count + index-ordered fill) == oracle CSR, bit for bit (incl. 'everything' and 'only the centre')."""
+    from oracle import ops as OO
+    from p2pb_b200 import ops
+
+    g = torch.Generator().manual_seed(N)
+    pts = torch.rand(N, 3, generator=g)
+    ctr = pts[torch.randperm(N, generator=g)[:P]].contiguous()
+    off, idx = ops.radius_query(ctr.cuda(), pts.cuda(), radius)
+    roff, ridx = OO.radius_query(ctr, pts, radius)
+    assert torch.equal(off.cpu(), roff) and torch.equal(idx.cpu(), ridx)

@@ -156,3 +156,22 @@ def _sq(q, pts):
     t = (d[:, 1] * d[:, 1]).astype(np.float32)
     t = (d[:, 0].astype(np.float64) * d[:, 0].astype(np.float64) + t.astype(np.float64)).astype(np.float32)
     return (d[:, 2].astype(np.float64) * d[:, 2].astype(np.float64) + t.astype(np.float64)).astype(np.float32)
+
+
+def test_oracle_radius_query_matches_sklearn_sets():
+    """oracle radius query (ascending indices) returns exactly the index SETS of sklearn's KDTree.query_radius -- the call
+    denoise_room.py:454-465 makes -- on a cloud with points near the boundary."""
+    from sklearn import neighbors
+
+    g = torch.Generator().manual_seed(8)
+    pts = torch.rand(4000, 3, generator=g)
+    ctr = pts[::400].contiguous()
+    off, idx = OO.radius_query(ctr, pts, 0.15)
+    ref = neighbors.KDTree(pts.numpy().astype(np.float64), metric="l2").query_radius(ctr.numpy().astype(np.float64), r=0.15)
+    for c in range(ctr.shape[0]):
+        mine = idx[off[c]:off[c + 1]].numpy()
+        assert np.all(np.diff(mine) > 0)
+        # fp32 vs fp64 distance may differ for points within 1e-6 of the sphere: compare modulo that shell
+        d = np.linalg.norm(pts.numpy().astype(np.float64) - ctr[c].numpy().astype(np.float64), axis=1)
+        shell = set(np.nonzero(np.abs(d - 0.15) < 1e-6)[0].tolist())
+        assert set(mine.tolist()) - shell == set(ref[c].tolist()) - shell
