@@ -22,7 +22,7 @@ int p2pb_abi_version(void);
 /* development aid for tools/: bit 0 = rows-GEMM epilogue skips its global stores (timing experiments only) */
 int p2pb_debug_set(int flags);
 int p2pb_device_sm_count(void);
-/* programmatic dependent launch between the hot-path kernels; default 0 = plain stream-ordered launches (measured faster) */
+/* programmatic dependent launch (griddepcontrol.wait, implicit trigger) between the hot-path kernels; default 1 */
 int p2pb_set_pdl(int on);
 /* dynamic shared memory the persistent tensor-core kernels may use per CTA, KiB in [128, 227] (default 227) */
 int p2pb_set_smem_budget_kb(int kb);
@@ -39,6 +39,7 @@ int p2pb_furthest_point_sampling(const float* coords, int B, int N, int M, int* 
 /* development aid: 0 = never use the thread-block-cluster FPS kernel, 1 = for whole clouds N in (16384, 196608] (default),
  * 2 = also for patches of more than 2048 points */
 int p2pb_fps_set_cluster(int on);
+int p2pb_fps_set_shape(int shape);   /* development aid: 0 = default (points per thread, threads) shapes */
 
 /* replaces gather_features_forward (pvcnn_sampling.cpp:6-24): out[b,c,j] = feat[b,c,idx[b,j]] */
 int p2pb_gather_features(const float* feat, const int* idx, float* out, int B, int C, int N, int M, void* stream);

@@ -50,9 +50,10 @@ P2PB_API int p2pb_set_smem_budget_kb(int kb)
 }
 
 // programmatic dependent launch on the hot path (see P2PB_PDL_SYNC in common.cuh); 0 = plain stream-ordered launches.
-// Default off: measured on B200 inside the CUDA graph, early launch_dependents + wait made the evaluation 6 % SLOWER
-// (311 vs 331 patches/s): the successors' CTAs become resident and wait while the persistent kernels still need the SMs.
-int g_p2pb_pdl = 0;
+// Measured on B200 inside the CUDA graph: with an early griddepcontrol.launch_dependents the evaluation got 6 % SLOWER (311 vs
+// 331 patches/s: the successors' CTAs become resident and wait while the persistent kernels still need the SMs); with the
+// implicit trigger at CTA exit (wait only, what P2PB_PDL_SYNC does now) it is 0.5 % faster (338.0 vs 336.3).
+int g_p2pb_pdl = 1;
 P2PB_API int p2pb_set_pdl(int on)
 {
     g_p2pb_pdl = on ? 1 : 0;

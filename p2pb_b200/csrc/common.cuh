@@ -54,10 +54,9 @@ static inline void p2pb_prefer_max_smem(const void* kernel)
 }
 
 // Programmatic dependent launch: every hot-path kernel starts with P2PB_PDL_SYNC() -- wait until the grids this launch depends
-// on have completed and flushed (a no-op for a plain launch), then allow the NEXT kernel in the stream to be launched --
-// and is launched through p2pb_launch(), which sets programmatic stream serialisation.  The successor's CTAs are then
-// scheduled as soon as SM resources free up and sit in their own griddepcontrol.wait until this grid has completed: the
-// ~2-4 us of launch latency between the ~210 dependent kernels of an evaluation overlaps the predecessor's tail.
+// on have completed and flushed (a no-op for a plain launch) -- and is launched through p2pb_launch(), which sets programmatic
+// stream serialisation.  No kernel triggers early (griddepcontrol.launch_dependents measured slower, see abi_common.cu): the
+// implicit trigger at CTA exit lets the successor's launch overlap the predecessor's drain.
 #define P2PB_PDL_SYNC()                                               \
     do {                                                              \
         asm volatile("griddepcontrol.wait;" ::: "memory");            \

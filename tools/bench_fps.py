@@ -15,7 +15,17 @@ def timeit(fn, n=3):
     return e0.elapsed_time(e1) / n
 
 
-for B, N, M in [(8, 8192, 2048), (16, 8192, 2048), (32, 2048, 512), (1, 28672, 10000), (1, 149504, 50000)]:
+for B, N, M in [(16, 8192, 2048), (64, 2048, 512)]:
+    x = torch.randn(B, 3, N, device="cuda")
+    ref = None
+    for shape in (0, 1, 2):
+        lib().p2pb_fps_set_shape(shape)
+        t = timeit(lambda: ops.furthest_point_sampling(x, M))
+        idx = ops.furthest_point_sampling(x, M)
+        ref = idx if ref is None else ref
+        print(f"B={B} N={N} M={M} shape {shape}: {t:8.3f} ms ({t / M * 1e3:5.2f} us/iter) same={bool(torch.equal(idx, ref))}")
+    lib().p2pb_fps_set_shape(0)
+for B, N, M in [(1, 28672, 10000), (1, 149504, 50000)]:
     x = torch.randn(B, 3, N, device="cuda")
     res = []
     for on in (1, 0):
