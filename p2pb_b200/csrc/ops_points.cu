@@ -396,25 +396,50 @@ __global__ void __launch_bounds__(WARPS * 32) ball_query_kernel(const float* __r
     centers += (size_t)b * 3 * M;
     for (int i = threadIdx.x; i < 3 * N; i += WARPS * 32) s_pts[i] = points[i];
     __syncthreads();
-    for (int j = blockIdx.x * WARPS + warp; j < M; j += gridDim.x * WARPS) {
-        const float cx = centers[j], cy = centers[j + M], cz = centers[j + 2 * M];
-        int* o = out + ((size_t)b * M + j) * U;
-        int cnt = 0, first = 0;
-        for (int k0 = 0; k0 < N && cnt < U; k0 += 32) {
+    // Each warp handles CQ = 4 centres per pass: a staged point is read from shared memory once and tested against 4 centres
+    // (the scan is bound by the 3 LDS + loop overhead per 32 points, not by the 6 flops of a distance).
+    constexpr int CQ = 4;
+    for (int j0 = (blockIdx.x * WARPS + warp) * CQ; j0 < M; j0 += gridDim.x * WARPS * CQ) {
+        float cx[CQ], cy[CQ], cz[CQ];
+        int cnt[CQ], first[CQ];
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+            const int j = min(j0 + q, M - 1);
+            cx[q] = centers[j];
+            cy[q] = centers[j + M];
+            cz[q] = centers[j + 2 * M];
+            cnt[q] = j0 + q < M ? 0 : U;      // centres past the end count as finished
+            first[q] = 0;
+        }
+        for (int k0 = 0; k0 < N; k0 += 32) {
+            if (cnt[0] >= U && cnt[1] >= U && cnt[2] >= U && cnt[3] >= U) break;
             const int k = k0 + lane;
-            bool hit = false;
-            if (k < N) hit = sqdist3(cx - s_pts[k], cy - s_pts[k + N], cz - s_pts[k + 2 * N]) < r2;
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                if (cnt == 0) first = k0 + __ffs(m) - 1;
-                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                if (hit && slot < U) o[slot] = k;
-                cnt += __popc(m);
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (k < N) {
+                px = s_pts[k];
+                py = s_pts[k + N];
+                pz = s_pts[k + 2 * N];
+            }
+#pragma unroll
+            for (int q = 0; q < CQ; ++q) {
+                const bool hit = k < N && cnt[q] < U && sqdist3(cx[q] - px, cy[q] - py, cz[q] - pz) < r2;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    if (cnt[q] == 0) first[q] = k0 + __ffs(m) - 1;
+                    const int slot = cnt[q] + __popc(m & ((1u << lane) - 1u));
+                    if (hit && slot < U) out[((size_t)b * M + j0 + q) * U + slot] = k;
+                    cnt[q] += __popc(m);
+                }
             }
         }
-        if (cnt > U) cnt = U;
-        // pad with the first hit (or zeros when empty: reference output is zero-initialised)
-        for (int v = cnt + lane; v < U; v += 32) o[v] = first;
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+            if (j0 + q >= M) continue;
+            int* o = out + ((size_t)b * M + j0 + q) * U;
+            const int c = min(cnt[q], U);
+            // pad with the first hit (or zeros when empty: reference output is zero-initialised)
+            for (int v = c + lane; v < U; v += 32) o[v] = first[q];
+        }
     }
 }
 
@@ -429,7 +454,7 @@ P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, i
     constexpr int WARPS = 8;
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(ball_query_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int gx = p2pb_cdiv(M, WARPS);
+    int gx = p2pb_cdiv(M, WARPS * 4);
     // enough CTAs per patch to fill the chip, but not so many that staging the points dominates
     const int want = p2pb_cdiv(2 * p2pb_num_sms(), B);
     if (gx > want) gx = want < 1 ? 1 : want;

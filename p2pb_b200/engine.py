@@ -488,17 +488,26 @@ class Engine:
                     self.voxel_prep(preps, 0, xt, P["r"])
         ev_prep0 = torch.cuda.Event()
         ev_prep0.record(torch.cuda.current_stream())
-        for i in range(n_levels):
+        # per level: FPS -> ball query -> event, so that set-abstraction level i only waits for ITS centres / neighbour lists
+        # (at N = 8192 the level-0 FPS + ball query take 2.3 ms, the deeper levels another 0.4 ms)
+        nidx, ev_level = [], []
+        for i, L in enumerate(W["sa"]):
             M = Ns[i + 1]
             idx = self.buf(f"fps{i}.idx", B, M, dtype=torch.int32)
             ctr = self.buf(f"fps{i}.ctr", B, 3, M)
             call("p2pb_furthest_point_sampling", _p(coords[i]), B, Ns[i], M, _p(idx), _p(ctr), _vp(0), _s())
             coords.append(ctr)
-        nidx = []
-        for i, L in enumerate(W["sa"]):
-            t = self.buf(f"bq{i}", B, Ns[i + 1], L["K"], dtype=torch.int32)
-            call("p2pb_ball_query", _p(coords[i + 1]), _p(coords[i]), B, Ns[i + 1], Ns[i], _f(L["radius"]), L["K"], _p(t), _s())
+            t = self.buf(f"bq{i}", B, M, L["K"], dtype=torch.int32)
+            call("p2pb_ball_query", _p(coords[i + 1]), _p(coords[i]), B, M, Ns[i], _f(L["radius"]), L["K"], _p(t), _s())
             nidx.append(t)
+            for P in L["pv"]:                       # voxel CSR of this level's PVConvs (level 0 is already cached)
+                self.voxel_prep(preps, i, coords[i], P["r"])
+            if i + 1 < n_levels:
+                for P in W["sa"][i + 1]["pv"]:
+                    self.voxel_prep(preps, i + 1, coords[i + 1], P["r"])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            ev_level.append(ev)
         nn3 = []
         for j, L in enumerate(W["fp"]):
             lvl = L["lvl"]
@@ -512,7 +521,7 @@ class Engine:
         for L in W["fp"]:
             for P in L["pv"]:
                 self.voxel_prep(preps, L["lvl"], coords[L["lvl"]], P["r"])
-        return coords, nidx, nn3, preps, ev_prep0
+        return coords, nidx, nn3, preps, ev_prep0, ev_level
 
     # ------------------------------------------------------------------------------------------------ one evaluation
     def prepare_cond(self, x_cond):
@@ -547,7 +556,7 @@ class Engine:
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
-            coords, nidx, nn3, preps, ev_prep0 = self._geometry(xt)
+            coords, nidx, nn3, preps, ev_prep0, ev_level = self._geometry(xt)
             join = torch.cuda.Event()
             join.record(side)
         # ---- point rows of the raw coordinates
@@ -615,27 +624,22 @@ class Engine:
         else:
             self.emd_all = None
         main.wait_event(ev_prep0)   # level-0 voxel CSRs: all the first PVConv needs from the geometry stream
-        joined = False
         # ---- set abstraction
         feats = F0
         skips = []
         for i, L in enumerate(W["sa"]):
             skips.append(feats)
             n_pts = Ns[i]
-            if i > 0 and not joined:
-                main.wait_event(join)
-                joined = True
             for k, P in enumerate(L["pv"]):
                 prep = self.voxel_prep(preps, i, coords[i], P["r"])
                 feats = self.pvconv(f"sa{i}.pv{k}", P, feats, coords[i], prep, temb, n_pts)
-            if not joined:              # FPS centres / ball-query indices are needed from the first grouping on
-                main.wait_event(join)
-                joined = True
+            main.wait_event(ev_level[i])    # centres + neighbour lists of this level (and the next level's voxel CSRs)
             M, K, cg = Ns[i + 1], L["K"], L["c_grp"]
             grp = self.buf(f"sa{i}.grp", B * M * K, pad32(cg + 3))
             call("p2pb_group_rows", _p(feats), int(feats.stride(0)), cg, _p(coords[i]), _p(coords[i + 1]), _p(nidx[i]), _p(grp),
                  int(grp.stride(0)), B, n_pts, M, K, _s())
             feats = self.mlp_chain(f"sa{i}.mlp", L["mlp"], [grp], [pad32(cg + 3)], M * K, temb, final_pool=K)
+        main.wait_event(join)       # 3-NN tables and the remaining voxel CSRs (feature propagation)
         # ---- bottleneck linear attention (modules.py:165-194; no residual)
         nb = Ns[-1]
         if "att_qkv" in W:
