@@ -51,9 +51,14 @@ def pad64(c: int) -> int:
 
 # Operands of the large-grid voxel convolutions (conv_halo) are stored as IEEE half: same 10-bit mantissa as the tf32
 # operands the tensor core would otherwise truncate them to, twice the channels per byte and per MMA (conv_halo.cu).
-HALO_F16 = os.environ.get("P2PB_HALO_F16", "1") != "0"
-# ... and likewise the r = 8 voxel convs (per-tap implicit GEMM) and the global PointNet's GEMMs
-GEMM_F16 = os.environ.get("P2PB_GEMM_F16", "1") != "0"
+# (P2PB_HALO_F16=0 keeps them fp32 / tf32), and likewise the r = 8 voxel convs (per-tap implicit GEMM) and the global
+# PointNet's GEMMs (P2PB_GEMM_F16=0).  Read when an Engine is built.
+def halo_f16() -> bool:
+    return os.environ.get("P2PB_HALO_F16", "1") != "0"
+
+
+def gemm_f16() -> bool:
+    return os.environ.get("P2PB_GEMM_F16", "1") != "0"
 
 
 class _AdaGN:
@@ -66,7 +71,7 @@ class _AdaGN:
 class Engine:
     # arithmetic of the contractions: 10-bit-mantissa operands (tf32 for the GEMMs / r=8 convs, IEEE half -- the same
     # mantissa -- for the r>=16 voxel convs), fp32 accumulation; everything else fp32
-    dtype_name = "tf32+f16(10-bit mantissa operands), fp32 accumulate" if HALO_F16 else "tf32"
+    dtype_name = "tf32"
 
     def __init__(self, p2pb, net, B: int, N: int, F: int):
         self.p2pb, self.net = p2pb, net
@@ -77,6 +82,9 @@ class Engine:
         assert self.ind == 3
         self.extra = net.extra_feature_channels
         assert F == self.extra, f"x_cond has {F} channels, model expects {self.extra}"
+        self.halo_f16, self.gemm_f16 = halo_f16(), gemm_f16()
+        if self.halo_f16 or self.gemm_f16:
+            self.dtype_name = "tf32+f16(10-bit mantissa operands), fp32 accumulate"
         self._emd_w: List[torch.Tensor] = []
         self._emd_b: List[torch.Tensor] = []
         self._emd_total = 0
@@ -134,11 +142,11 @@ class Engine:
         P = {"cout": cout, "cin": c_in, "E": E, "cp": cp, "r": int(mod.resolution)}
         halo = int(mod.resolution) >= 16 and cout <= 128 and cout % 32 == 0   # large grid / few channels: conv_halo.cu
         P["halo"] = halo
-        if halo and HALO_F16:
+        if halo and self.halo_f16:
             P["cp"] = cp = pad64(c_in + E)
             P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
             P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
-        elif not halo and GEMM_F16 and cout % 32 == 0:
+        elif not halo and self.gemm_f16 and cout % 32 == 0:
             P["cp"] = cp = pad64(c_in + E)
             P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
             P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
@@ -211,7 +219,7 @@ class Engine:
                 conv, gn = seq[0], seq[1]
                 o, c = conv.weight.shape[:2]
                 L = {"cout": o, "b": self._w(conv.bias), "n": self._norm(gn)}
-                pnet_f16 = GEMM_F16 and self.N % 128 == 0     # (the column max/min epilogue needs whole 128-row tiles per sample)
+                pnet_f16 = self.gemm_f16 and self.N % 128 == 0     # (the column max/min epilogue needs whole 128-row tiles per sample)
                 padk = pad64 if pnet_f16 else pad32
                 if j == 2:  # input = cat[point feature (c/2), global max (c/2)]: second half becomes a per-sample bias
                     h = c // 2
@@ -762,14 +770,13 @@ class DualEngine:
     are persistent one-CTA-per-SM kernels that cannot overlap each other.  With several chains the small kernels of one
     part run in the shadow of another part's convolutions / GEMMs."""
 
-    dtype_name = Engine.dtype_name
-
     def __init__(self, p2pb, net, B: int, N: int, F: int, n_chains: int = 2):
         assert B % n_chains == 0
         self.B, self.N, self.F, self.n = B, N, F, n_chains
         self.part = B // n_chains
         self.halves = [Engine(p2pb, net, self.part, N, F) for _ in range(n_chains)]
         self.dev = self.halves[0].dev
+        self.dtype_name = self.halves[0].dtype_name
         self._graphs: Dict[tuple, tuple] = {}
         self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_chains - 1)]
         self.kernels_per_sample = 0

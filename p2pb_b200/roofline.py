@@ -33,7 +33,9 @@ def measured_peaks():
 
 
 def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
-    from .engine import HALO_F16, DualEngine
+    from .engine import DualEngine, halo_f16
+
+    HALO_F16 = halo_f16()
 
     r, cin, cout = 32, 64, 64
     if isinstance(getattr(model, "last_engine", None), DualEngine):

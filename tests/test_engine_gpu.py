@@ -282,3 +282,36 @@ def test_denoise_room_entry_point_end_to_end(tmp_path):
     assert out.shape == pts.shape and np.isfinite(out).all()
     moved = np.linalg.norm(out - pts, axis=1)
     assert moved.max() < 0.2 and 0.25 < (moved > 0).mean() <= 1.0, (moved.max(), (moved > 0).mean())
+
+
+def test_engine_tf32_operand_path_still_matches_golden(golden_dir, monkeypatch):
+    """P2PB_HALO_F16=0 / P2PB_GEMM_F16=0: every contraction with fp32-stored (tf32) operands -- the path the IEEE-half
+    operand storage replaced -- stays available and inside the same tolerance.  Measured on B200 vs the fp32 golden:
+    half operands mean|err| 4.2e-4 / max 5.3e-3, tf32 operands 3.9e-4 / 5.6e-3; between the two 3.4e-4 / 5.5e-3 (both round
+    the operands to 10 mantissa bits, half to nearest, tf32 by truncation)."""
+    from p2pb_b200.engine import get_engine
+
+    z, cfg = _golden(golden_dir, "pvds_b2")
+    x = torch.from_numpy(z["x_start"]).cuda()
+    B, _, N = x.shape
+    nl = float(z["noise_level"][0])
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("P2PB_HALO_F16", flag)
+        monkeypatch.setenv("P2PB_GEMM_F16", flag)
+        model, _ = build(cfg, backend="engine")
+        eng = get_engine(model, model.model, x.shape, None)
+        assert eng.halo_f16 == (flag == "1")
+        with torch.no_grad():
+            sin = eng.time_embedding(nl, None)[None].expand(B, -1).contiguous()
+            th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
+            eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
+            eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
+            eps = eng.evaluate(x.contiguous(), temb)[:, :3].reshape(B, N, 3).permute(0, 2, 1).cpu().numpy()
+        err = np.abs(eps - z["eps"])
+        print(f"operands {'half' if flag == '1' else 'tf32'}: mean|err|={err.mean():.3e} max|err|={err.max():.3e}")
+        assert err.mean() <= 2e-3 and err.max() <= 3e-2
+        outs[flag] = eps
+    d = np.abs(outs["1"] - outs["0"])
+    print(f"half vs tf32 operands: mean|diff|={d.mean():.3e} max|diff|={d.max():.3e}")
+    assert d.mean() <= 1e-3
