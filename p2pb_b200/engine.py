@@ -401,6 +401,26 @@ class Engine:
         B, r, cout, cp = self.B, P["r"], P["cout"], P["cp"]
         r3 = r ** 3
         halo = P["halo"]
+        # point branch (1x1 conv + AdaGN coefficients): independent of the voxel branch until the devoxelisation, so it runs
+        # on a second stream and fills the gaps the voxel branch leaves (conv tails, the HBM-bound activation pass)
+        main = torch.cuda.current_stream()
+        pt_done = None
+        pstream = self._point_stream() if os.environ.get("P2PB_POINT_STREAM", "1") != "0" else None
+        if pstream is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            pstream.wait_event(fork)
+        with torch.cuda.stream(pstream if pstream is not None else main):
+            bias2 = None
+            if P["E"]:
+                bias2 = self.buf(f"{name}.ptb", B, cout)
+                self.linear(temb, P["wp_t"], None, 0, bias2)
+            kp = P["wp"].shape[1]
+            praw, pst, ptiles = self.gemm(f"{name}.pt", [feats], [kp], P["wp"], P["bp"], cout, n_pts, bias2=bias2)
+            pA, pB, _ = self.coef(f"{name}.np", pst, ptiles, P["np"], cout, n_pts)
+            if pstream is not None:
+                pt_done = torch.cuda.Event()
+                pt_done.record(pstream)
         raw1 = self.buf(f"{name}.raw1", B * r3, cout)
         raw2 = self.buf(f"{name}.raw2", B * r3, cout)
         tvox = _p(temb if P["E"] else None)
@@ -448,14 +468,8 @@ class Engine:
             self.linear(ym, P["se0"], None, 2, hid)
             se = self.buf(f"{name}.se", B, cout)
             self.linear(hid, P["se2"], None, 3, se)
-        # point branch
-        bias2 = None
-        if P["E"]:
-            bias2 = self.buf(f"{name}.ptb", B, cout)
-            self.linear(temb, P["wp_t"], None, 0, bias2)
-        kp = P["wp"].shape[1]
-        praw, pst, ptiles = self.gemm(f"{name}.pt", [feats], [kp], P["wp"], P["bp"], cout, n_pts, bias2=bias2)
-        pA, pB, _ = self.coef(f"{name}.np", pst, ptiles, P["np"], cout, n_pts)
+        if pt_done is not None:
+            torch.cuda.current_stream().wait_event(pt_done)
         out = self.buf(f"{name}.out", B * n_pts, cout)
         call("p2pb_devox_cl", _p(prep["norm_coords"]), _p(raw2), cout, _p(A2), _p(B2), _p(se), _p(praw), int(praw.stride(0)),
              _p(pA), _p(pB), _p(out), cout, B, cout, n_pts, r, _s())
@@ -473,6 +487,11 @@ class Engine:
             call("p2pb_voxel_prep", _p(coords), B, n, r, 1, _f(0.0), _p(nc), _p(ind), _p(order), _p(start), _p(cnt), _s())
             cache[key] = {"norm_coords": nc, "order": order, "start": start, "cnt": cnt, "ind": ind}
         return cache[key]
+
+    def _point_stream(self):
+        if getattr(self, "_pstream", None) is None:
+            self._pstream = torch.cuda.Stream(device=self.dev)
+        return self._pstream
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
