@@ -1,29 +1,30 @@
-// conv_halo.cu -- 3x3x3 voxel convolution as a halo-reuse implicit GEMM on tcgen05 (TF32), for the large-grid / small-
-// channel layers (r = 32, 16) where the plain per-tap TMA kernel (gemm_tf32.cu, conv mode) is bound by L2->SM traffic:
-// it re-reads the activation tile once per tap (27x).  Measured on B200 (tools/bench_conv.py): 85-155 TFLOP/s at
-// C<=64 vs 530 TFLOP/s at C=256 for the same kernel.
+// conv_halo.cu -- 3x3x3 voxel convolution as a halo-reuse implicit GEMM on tcgen05, for the large-grid / small-channel layers
+// (r = 32, 16) where a per-tap TMA kernel (gemm_persist.cu, conv mode) re-reads the activation tile once per tap (27x).
+// Replaces cuDNN Conv3d behind models/pvcnn.py:265-284.
 //
 // Idea: store the conv INPUT as a zero-bordered row-major grid  X[b][(r+2)^3][Cin]  indexed by the padded-linear voxel
 // index q = (x+1)P^2 + (y+1)P + (z+1), P = r+2.  In padded-linear space every tap is a CONSTANT row shift
 // d = dx*P^2 + dy*P + dz, so for one dx the 9 taps (dy,dz) of a 128-row output tile read nine overlapping 128-row
-// windows of ONE contiguous run of W = 128 + 2P + 2 rows.  That run is brought into shared memory ONCE per 32-channel
-// chunk by a single TMA box load {32 ch, W rows} (128B swizzle) and the 9 taps are 9 UMMA descriptors into the same
-// buffer: start address advanced by whole 128-byte rows, with the descriptor's base-offset field carrying the swizzle
-// phase ((addr >> 7) & 7) of the un-aligned start.  Activation traffic drops from 27 to 3*(W/128) tile reads (5.8x less
-// at r=32).  Weights are stationary per (dx, 32-channel chunk) slab [9 taps][Cout][32] and shared by G = 512/Cout
-// output tiles whose accumulators all live in TMEM at once.
+// windows of ONE contiguous run of W = 128 + 2P + 2 rows.  That run is brought into shared memory ONCE per 128-byte
+// channel chunk (32 fp32 / 64 half channels) by a single TMA box load {chunk, W rows} (128B swizzle) and the 9 taps are 9
+// UMMA descriptors into the same buffer, start address advanced by whole 128-byte rows (the tensor core applies the 128B
+// swizzle to absolute shared-memory address bits, exactly as TMA did when it wrote the window, so no base-offset
+// correction is needed -- verified against fp64 convolutions).  Activation traffic drops from 27 to 3*(W/128) tile reads.
 //
 // Why 128B-swizzled A and not the un-swizzled core-matrix layout (which takes any 16-byte start): measured with
-// tools/ubench/mma_rate.cu on B200, one tcgen05.mma (M=128, K=32 bytes) costs max(64, N/2) cycles with a SWIZZLE_128B
+// tools/ubench/mma_rate.cu on B200, one tcgen05.mma (M=128, K=32 bytes) costs max(49, N/2) cycles with a SWIZZLE_128B
 // A operand but ~115-125 cycles with an INTERLEAVE (no-swizzle) A operand, independent of the B layout.
 //
-// Mainloop order (v5): weights stream through a ring of SUB-slabs (the 3 dz-taps of one (dx, chunk, dy): 3 x [Cout][32]
-// fp32 = 12..48 KB) while the activation windows of the unit's G tiles stay resident for the whole (dx, chunk) slab:
+// Mainloop: weights stream through a ring of SUB-slabs (the 3 dz-taps of one (dx, chunk, dy)) while the activation
+// windows of the unit's G tiles stay resident for the whole (dx, chunk) slab:
 //   for slab (dx, chunk): for dy: [wait sub-slab] for tile g: [dy == 0: wait window g] 3 taps x 4 MMAs [dy == 2: free window g]
-// A full 9-tap slab is 144 KB at Cout = 128 and could only be single-buffered (every slab change stalled the tensor
-// core for a 144 KB L2 read, r01 profile: 480 TFLOP/s); the sub-slab ring is double/triple buffered in a third of the
-// space, and the freed shared memory holds G + 1..3 windows, so G = 4 tiles share every weight byte (2 before).
-// Separate producer warps feed the two rings so that neither blocks the other.
+// Separate producer warps feed the two rings so that neither blocks the other; one elected thread issues every MMA with
+// 32-bit descriptor arithmetic (at N <= 64 an MMA executes in ~49 cycles, so the issue path is on the critical path);
+// accumulators of consecutive units ping-pong between two 256-column halves of TMEM (epilogue overlaps the next mainloop).
+//
+// Two multipliers on top (template parameters, see the kernel): cta_group::2 CTA pairs (each SM keeps half of the weight
+// rows) and IEEE-half operands (kind::f16: same 10-bit mantissa as tf32, twice the channels per byte and per MMA).
+// History and measurements of every step: profiles/r01_ncu_conv.md.
 //
 // Outputs for border positions inside the tile's linear range are computed but masked (not stored, not counted in the
 // GroupNorm statistics); the result is written in the dense [B*r^3, Cout] row layout the rest of the engine uses.
@@ -34,7 +35,6 @@
 namespace {
 
 constexpr int HBM = 128;
-constexpr int HBK = 32;
 constexpr int HALO_THREADS = 224;   // warp 0: window producer, 1: MMA issuer, 2-5: epilogue, 6: weight producer
 
 struct HaloArgs {

@@ -1,4 +1,7 @@
-// gemm_tf32.cu -- the dense contractions of the PVCNN U-Net as tcgen05 (5th-gen tensor core) tiles fed by TMA.
+// gemm_tf32.cu -- C-ABI entry points of the dense contractions (p2pb_gemm_rows*, p2pb_conv3d_cl) and the FIRST-generation
+// one-tile-per-CTA tcgen05 kernel.  The entry points build the TMA descriptors and hand over to the persistent kernel
+// (gemm_persist.cu) whenever the shape is inside its envelope; this kernel remains for N = 16 (the 128 -> 3 head), for
+// unaligned outputs and as an on-device cross-check (p2pb_debug_set(2)).
 //
 // One kernel family covers every Conv3d / Conv1d / Conv2d(1x1) / Linear of the hot path
 // (reference: cuDNN/cuBLAS library calls behind models/pvcnn.py:174-192,265-284, models/modules.py:337,365-370):
