@@ -199,6 +199,8 @@ int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, const float* 
 /* [features[idx], xyz[idx]-centre] rows for the SA-module MLP (pvcnn_grouping_gpu.cu:18-39 x2 + pvcnn.py:117-126) */
 int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* coords, const float* centers, const int* idx,
                     float* out, int ldo, int B, int N, int M, int U, void* stream);
+int p2pb_group_rows_f16(const float* feat, int ldf, int Cf, const float* coords, const float* centers, const int* idx, void* out,
+                        int ldo, int B, int N, int M, int U, void* stream);   /* IEEE-half rows, ldo in halves */
 
 /* 3-NN weighted gather (pvcnn_neighbor_interpolate_gpu.cu:96-124) on rows */
 int p2pb_interp_rows(const float* f, int ldf, const int* idx, const float* w, float* out, int ldo, int B, int C, int N,

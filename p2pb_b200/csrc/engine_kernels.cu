@@ -590,9 +590,10 @@ P2PB_API int p2pb_devox_cl(const float* ncoords, const float* raw, int ldg, cons
 // (pvcnn_grouping_gpu.cu:18-39 twice + the centre subtraction + torch.cat of pvcnn.py:117-126).  Columns >= Cf+3 are
 // never written (zero from allocation).  One thread per (row, 4-channel chunk); chunk index Cf/4 carries the xyz part.
 // ---------------------------------------------------------------------------------------------------------
+template <typename OUT>
 __global__ void __launch_bounds__(256) group_rows_kernel(const float* __restrict__ feat, int ldf, int Cf,
                                                          const float* __restrict__ coords, const float* __restrict__ centers,
-                                                         const int* __restrict__ idx, float* __restrict__ out, int ldo, int N,
+                                                         const int* __restrict__ idx, OUT* __restrict__ out, int ldo, int N,
                                                          int M, int U, unsigned total)
 {
     P2PB_PDL_SYNC();
@@ -607,15 +608,14 @@ __global__ void __launch_bounds__(256) group_rows_kernel(const float* __restrict
     const int j = (int)(bj - (unsigned)b * (unsigned)M);
     const int src = idx[row];
     if (c4 < (Cf >> 2)) {
-        *reinterpret_cast<float4*>(out + row * ldo + c4 * 4) =
-            __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + src) * ldf + c4 * 4));
+        store4(out + row * ldo + c4 * 4, __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + src) * ldf + c4 * 4)));
     } else {
         const float* co = coords + (size_t)b * 3 * N;
         const float* ce = centers + (size_t)b * 3 * M;
-        float* o = out + row * ldo + Cf;
-        o[0] = co[src] - ce[j];
-        o[1] = co[src + N] - ce[j + M];
-        o[2] = co[src + 2 * N] - ce[j + 2 * M];
+        OUT* o = out + row * ldo + Cf;
+        o[0] = (OUT)(co[src] - ce[j]);
+        o[1] = (OUT)(co[src + N] - ce[j + M]);
+        o[2] = (OUT)(co[src + 2 * N] - ce[j + 2 * M]);
     }
 }
 
@@ -626,9 +626,24 @@ P2PB_API int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* co
     const long long total = (long long)B * M * U * (Cf / 4 + 1);
     P2PB_CHECK_U32(total, "group_rows");
     if (total == 0) return P2PB_OK;
-    p2pb_prefer_max_smem((const void*)group_rows_kernel);
-    (void)p2pb_launch(group_rows_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
+    p2pb_prefer_max_smem((const void*)group_rows_kernel<float>);
+    (void)p2pb_launch(group_rows_kernel<float>, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf, coords, centers, idx, out, ldo, N, M,
                                                                              U, total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// same with IEEE-half output rows (A operand of p2pb_gemm_rows_f16); ldo in halves
+P2PB_API int p2pb_group_rows_f16(const float* feat, int ldf, int Cf, const float* coords, const float* centers, const int* idx,
+                                 void* out, int ldo, int B, int N, int M, int U, void* stream)
+{
+    P2PB_CHECK_ARG(Cf % 4 == 0 && ldf % 4 == 0 && ldo % 4 == 0 && ldo >= Cf + 3, "group_rows_f16: alignment (Cf %% 4, ld %% 4)");
+    const long long total = (long long)B * M * U * (Cf / 4 + 1);
+    P2PB_CHECK_U32(total, "group_rows_f16");
+    if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)group_rows_kernel<__half>);
+    (void)p2pb_launch(group_rows_kernel<__half>, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, feat, ldf, Cf,
+                      coords, centers, idx, reinterpret_cast<__half*>(out), ldo, N, M, U, (unsigned)total);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

@@ -170,8 +170,10 @@ class Engine:
         P["np"] = self._norm(pf[1])
         return P
 
-    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None):
-        """SharedMLP -> list of dicts; first layer's columns remapped by first_cols; optional temb fold block."""
+    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None, half_first=False):
+        """SharedMLP -> list of dicts; first layer's columns remapped by first_cols; optional temb fold block.
+        With gemm_f16 the layers after the first take IEEE-half operands (their input is a GroupNorm+Swish output written
+        by this engine); the first layer too when its input rows are produced as half (half_first: grouped rows)."""
         out = []
         i = 0
         while i < len(layers):
@@ -180,9 +182,13 @@ class Engine:
             L = {"cout": o}
             if i == 0:
                 L["w"] = self._pack_rows_w(conv.weight, first_cols, k_pad_first)
+                if half_first and self.gemm_f16:
+                    L["w"] = L["w"].half()
                 if temb_cols is not None:
                     w = self._w(conv.weight).reshape(o, c)
                     L["w_t"] = w[:, temb_cols[0]:temb_cols[0] + temb_cols[1]].contiguous()
+            elif self.gemm_f16 and o % 32 == 0:
+                L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad64(c)).half()
             else:
                 L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad32(c))
             L["b"] = self._w(conv.bias)
@@ -249,8 +255,10 @@ class Engine:
             if i == 0 and len(pvs) == 0:
                 raise NotImplementedError("level 0 without PVConv")
             assert c_cur % 4 == 0
-            L["mlp"] = self._pack_mlp(sam.mlps[0].layers, [(3, c_cur, 0), (0, 3, c_cur)], pad32(c_cur + 3),
-                                      temb_cols=(3 + c_cur, E) if temb_sa else None)
+            sa_half = self.gemm_f16 and sam.mlps[0].layers[0].weight.shape[0] % 32 == 0
+            L["mlp"] = self._pack_mlp(sam.mlps[0].layers, [(3, c_cur, 0), (0, 3, c_cur)],
+                                      pad64(c_cur + 3) if sa_half else pad32(c_cur + 3),
+                                      temb_cols=(3 + c_cur, E) if temb_sa else None, half_first=sa_half)
             L["centers"], L["radius"], L["K"] = sam.num_centers, float(sam.radius[0]), int(sam.num_neighbors[0])
             L["c_grp"] = c_cur
             sa.append(L)
@@ -390,10 +398,12 @@ class Engine:
                 out = final_out
             elif last and final_pool > 1:
                 out = self.buf(nm + ".pool", raw.shape[0] // final_pool, L["cout"])
+            elif not last and layers[li + 1]["w"].dtype == torch.float16:      # operand of a half GEMM
+                out = self.buf(nm + ".act", raw.shape[0], pad64(L["cout"]), dtype=torch.float16)
             else:
                 out = self.buf(nm + ".act", raw.shape[0], pad32(L["cout"]))
             self.act(raw, A, Bc, rows_per_sample, L["cout"], out, act=1, pool=final_pool if last else 1)
-            x_segs, x_ks = [out], [pad32(L["cout"])] if not last else None
+            x_segs, x_ks = [out], [out.shape[1]] if not last else None
         return out
 
     def pvconv(self, name, P, feats, coords_lvl, prep, temb, n_pts):
@@ -662,10 +672,12 @@ class Engine:
                 feats = self.pvconv(f"sa{i}.pv{k}", P, feats, coords[i], prep, temb, n_pts)
             main.wait_event(ev_level[i])    # centres + neighbour lists of this level (and the next level's voxel CSRs)
             M, K, cg = Ns[i + 1], L["K"], L["c_grp"]
-            grp = self.buf(f"sa{i}.grp", B * M * K, pad32(cg + 3))
-            call("p2pb_group_rows", _p(feats), int(feats.stride(0)), cg, _p(coords[i]), _p(coords[i + 1]), _p(nidx[i]), _p(grp),
-                 int(grp.stride(0)), B, n_pts, M, K, _s())
-            feats = self.mlp_chain(f"sa{i}.mlp", L["mlp"], [grp], [pad32(cg + 3)], M * K, temb, final_pool=K)
+            g16 = L["mlp"][0]["w"].dtype == torch.float16
+            kg = pad64(cg + 3) if g16 else pad32(cg + 3)
+            grp = self.buf(f"sa{i}.grp", B * M * K, kg, dtype=torch.float16 if g16 else torch.float32)
+            call("p2pb_group_rows_f16" if g16 else "p2pb_group_rows", _p(feats), int(feats.stride(0)), cg, _p(coords[i]),
+                 _p(coords[i + 1]), _p(nidx[i]), _p(grp), int(grp.stride(0)), B, n_pts, M, K, _s())
+            feats = self.mlp_chain(f"sa{i}.mlp", L["mlp"], [grp], [kg], M * K, temb, final_pool=K)
         main.wait_event(join)       # 3-NN tables and the remaining voxel CSRs (feature propagation)
         # ---- bottleneck linear attention (modules.py:165-194; no residual)
         nb = Ns[-1]
