@@ -141,7 +141,8 @@ int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* 
                    int Cin, int Cout, void* stream);
 
 /* same convolution, halo-reuse kernel for large grids / few channels (r in [8,62], Cout <= 128):
- * X = zero-bordered padded-linear rows [B*(r+2)^3 + slack, Cin] (p2pb_conv_halo_layout gives rows/slack/tiles) */
+ * X = zero-padded padded-linear rows [B*(r+1)^3 + slack, Cin] with SHARED padding: voxel (x,y,z) at row
+ * (x+1)P^2 + (y+1)P + (z+1), P = r+1 (p2pb_conv_halo_layout gives rows/slack/tiles) */
 int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int* tiles_per_sample_out);
 int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
                      int Cin, int Cout, void* stream);

@@ -835,7 +835,7 @@ P2PB_API int p2pb_bridge_update(const float* xt, const float* eps, int lde, cons
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ size_t padded_row(int b, int v, int r)
 {
-    const int P = r + 2;
+    const int P = r + 1;     // shared-padding layout, see p2pb_conv_halo_layout (conv_halo.cu)
     const int x = v / (r * r), y = (v / r) % r, z = v % r;
     return (size_t)b * P * P * P + (size_t)(x + 1) * P * P + (size_t)(y + 1) * P + (z + 1);
 }
@@ -1008,7 +1008,7 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
     const unsigned r3 = r * r * r;
     const unsigned C4 = C >> 2;
     const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
-    const int P = r + 2;
+    const int P = r + 1;
     float4 xv[4], a[4], bb[4];
     size_t orow[4];
     int c[4];

@@ -105,9 +105,9 @@ def alloc_padded(B: int, C: int, r: int, device, dtype=torch.float32) -> torch.T
 def dense_to_padded(grid: torch.Tensor, r: int) -> torch.Tensor:
     """Test helper (torch ops): channels-last dense grid [B, r, r, r, C] -> padded row-major layout (dtype kept)."""
     B, C = grid.shape[0], grid.shape[-1]
-    P = r + 2
+    P = r + 1
     X = alloc_padded(B, C, r, grid.device, grid.dtype)
-    X[: B * P ** 3].view(B, P, P, P, C)[:, 1:-1, 1:-1, 1:-1, :] = grid
+    X[: B * P ** 3].view(B, P, P, P, C)[:, 1:, 1:, 1:, :] = grid
     return X
 
 

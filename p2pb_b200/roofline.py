@@ -43,8 +43,8 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
     dt = torch.float16 if HALO_F16 else torch.float32
     g = torch.Generator(device=dev).manual_seed(0)
     X = dense.alloc_padded(B, cin, r, dev, dt)
-    P = r + 2
-    X[: B * P ** 3].view(B, P, P, P, cin)[:, 1:-1, 1:-1, 1:-1, :] = torch.randn(B, r, r, r, cin, device=dev, generator=g).to(dt)
+    P = r + 1
+    X[: B * P ** 3].view(B, P, P, P, cin)[:, 1:, 1:, 1:, :] = torch.randn(B, r, r, r, cin, device=dev, generator=g).to(dt)
     w = (torch.randn(cout, 27 * cin, device=dev, generator=g) / (27 * cin) ** 0.5).to(dt)
     bias = torch.zeros(cout, device=dev)
     out = torch.empty(B * r ** 3, cout, device=dev)
@@ -78,5 +78,5 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
                                          "fp32 accumulate, cta_group::2 tcgen05)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "ms_per_launch": ms, "flops_per_launch": flops,
-            "algorithmic_bytes_per_launch": B * (esz * (r + 2) ** 3 * cin + 4.0 * r ** 3 * cout),
+            "algorithmic_bytes_per_launch": B * (esz * (r + 1) ** 3 * cin + 4.0 * r ** 3 * cout),
             "peak_source": f"{how}: dense 16-bit rate {bf16_peak:.1f} TFLOP/s" + ("" if HALO_F16 else " / 2 for TF32")}
