@@ -176,21 +176,6 @@ __device__ __forceinline__ void h_tmem_ld32(uint32_t taddr, float* v)
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float h_colsum32(float (&v)[32], int lane)
-{
-#pragma unroll
-    for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int j = 0; j < n / 2; ++j) {
-            const float send = up ? v[j] : v[j + n / 2];
-            const float keep = up ? v[j + n / 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0];
-}
-
 // PAIR: two CTAs of a cluster form a cta_group::2 pair.  Each MMA has M = 256 = one 128-row tile per CTA against the SAME
 // weights; CTA r keeps only weight rows [Cout/2 r, Cout/2 (r+1)) of every tap in its shared memory (the tensor core reads
 // the other half from the peer), so per SM the weight bytes fetched from L2, written to and read from shared memory halve.
@@ -223,6 +208,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][cout][2]
+    // epilogue staging tiles: 4 warps x (32 rows x 128 B), 1024-byte aligned for the XOR swizzle
+    uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stats + 4 * a.cout * 2) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank = 0;
@@ -447,27 +434,48 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 const int x = q / a.P2, rem = q - x * a.P2, y = rem / a.P, z = rem - y * a.P;
                 const bool ok = tile_ok && q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
                 const size_t v = (size_t)b * r3 + (size_t)(x - 1) * r * r + (size_t)(y - 1) * r + (size_t)(z - 1);
-                float* drow = a.D + v * a.ldd;
+                // The valid rows of a tile are CONSECUTIVE dense voxel rows (v enumerates the interior voxels in the same order
+                // as q, pads skipped), so the warp's valid rows are compacted into a 128B-swizzled staging tile and leave as
+                // full 128-byte row segments (4 rows per store instruction instead of 32 different cache lines), and the
+                // GroupNorm partials are read back column-wise from the staging tile instead of two 31-shuffle butterflies.
+                const unsigned vmask = __ballot_sync(0xffffffffu, ok);
+                const int nv = __popc(vmask);
+                const int pos = __popc(vmask & ((1u << lane) - 1u));
+                const unsigned long long v0 = __shfl_sync(0xffffffffu, (unsigned long long)v, vmask ? (__ffs(vmask) - 1) : 0);
+                float* dbase = a.D + (size_t)v0 * a.ldd;
+                uint8_t* stg = sStage + (size_t)qd * 4096;
                 for (int c = 0; c < a.cout / 32; ++c) {
                     float vv[32];
                     h_tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * half_cols + g * a.cout + c * 32), vv);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = vv[j];
-                        if (a.bias != nullptr) t += __ldg(a.bias + c * 32 + j);
-                        vv[j] = ok ? t : 0.f;
-                    }
+                    __syncwarp();              // the previous chunk's readers are done with the staging tile
                     if (ok) {
+                        uint8_t* rowp = stg + pos * 128;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(drow + c * 32 + j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+                        for (int j = 0; j < 8; ++j) {
+                            float4 t = make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
+                            if (a.bias != nullptr) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + 4 * j));
+                                t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+                            }
+                            *reinterpret_cast<float4*>(rowp + ((j ^ (pos & 7)) << 4)) = t;
+                        }
+                    }
+                    __syncwarp();
+                    // rows [0, nv) of the staging tile -> nv consecutive dense rows, 8 lanes per 128-byte row segment
+                    for (int i = lane; i < nv * 8; i += 32) {
+                        const int rr = i >> 3, j = i & 7;
+                        const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
+                        *reinterpret_cast<float4*>(dbase + (size_t)rr * a.ldd + c * 32 + j * 4) = t;
                     }
                     if (a.stats != nullptr) {
-                        float sq[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sq[j] = vv[j] * vv[j];
-                        const float s1 = h_colsum32(vv, lane);
-                        const float s2 = h_colsum32(sq, lane);
+                        // column `lane`: element (rr, lane) sits at rr*128 + (((lane>>2) ^ (rr&7))<<4) + (lane&3)*4 (conflict-free)
+                        float s1 = 0.f, s2 = 0.f;
+                        const uint8_t* colp = stg + (lane & 3) * 4;
+                        for (int rr = 0; rr < nv; ++rr) {
+                            const float xx = *reinterpret_cast<const float*>(colp + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4));
+                            s1 += xx;
+                            s2 = fmaf(xx, xx, s2);
+                        }
                         s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
                         s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
                     }
@@ -577,7 +585,8 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     const bool pair = g_halo_pair && a.total_tiles >= 2 * n_sms && n_sms >= 2;
     const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * 128;     // per CTA: pair mode keeps half of the output channels
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
-    const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 4 * Cout * 2 * 4;
+    const int stage_bytes = 4 * 4096 + 1024;      // epilogue staging tiles (+ alignment)
+    const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 4 * Cout * 2 * 4 - stage_bytes;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
     a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
     if (g_halo_w_stages >= 2) {
@@ -587,7 +596,7 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     if (a.a_stages > 2 * a.G) a.a_stages = 2 * a.G;
     if (g_halo_a_stages > 0 && g_halo_a_stages < a.a_stages) a.a_stages = g_halo_a_stages;
     P2PB_CHECK_ARG(a.a_stages >= a.G + 1, "conv3d_halo: shared memory budget exceeded (Cout=%d r=%d)", Cout, r);
-    const size_t smem = 1024 + (size_t)a.w_stages * sub_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)4 * Cout * 2 * 4;
+    const size_t smem = 1024 + (size_t)a.w_stages * sub_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)4 * Cout * 2 * 4 + stage_bytes;
     CUtensorMap mapW, mapX;
     {
         static PFN_encodeTiled_h enc = nullptr;
