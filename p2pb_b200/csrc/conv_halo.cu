@@ -35,7 +35,7 @@
 namespace {
 
 constexpr int HBM = 128;
-constexpr int HALO_THREADS = 224;   // warp 0: window producer, 1: MMA issuer, 2-5: epilogue, 6: weight producer
+constexpr int HALO_THREADS = 352;   // warp 0: window producer, 1: MMA issuer, 2-5: epilogue set 0, 6: weight producer, 7-10: epilogue set 1
 
 struct HaloArgs {
     int B, r, P, P2, P3;      // P = r+1 (shared padding, see p2pb_conv_halo_layout)
@@ -207,9 +207,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     uint64_t* tmem_full = w_empty + a.w_stages;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [4][cout][2]
+    float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [2 sets][4][cout][2]
     // epilogue staging tiles: 4 warps x (32 rows x 128 B), 1024-byte aligned for the XOR swizzle
-    uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stats + 4 * a.cout * 2) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stats + 2 * 4 * a.cout * 2) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank = 0;
@@ -231,7 +231,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         }
         for (int h = 0; h < 2; ++h) {
             h_mbar_init(h_smem_u32(&tmem_full[h]), 1);
-            h_mbar_init(h_smem_u32(&tmem_empty[h]), 4 * NC);   // one arrival per epilogue warp (of both CTAs in pair mode)
+            h_mbar_init(h_smem_u32(&tmem_empty[h]), 8 * NC);   // one arrival per epilogue warp (of both CTAs in pair mode)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -417,7 +417,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         }
     } else {
         // ===================== epilogue =====================
+        // two sets of 4 warps (warp w reads TMEM lanes 32*(w%4)..+31); set 0 takes the even tiles of a unit, set 1 the odd ones
         const int qd = warp & 3;
+        const int eset = warp >= 7 ? 1 : 0;
+        float* s_stats_set = s_stats + (size_t)eset * 4 * a.cout * 2;
         const int r = a.r, r3 = r * r * r;
         int it_unit = 0;
         for (int tile0 = tile_begin; tile0 < tile_end; tile0 += NC * a.G, ++it_unit) {
@@ -426,7 +429,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
             const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
             h_mbar_wait(h_smem_u32(&tmem_full[h]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int g = 0; g < ntiles; ++g) {
+            for (int g = eset; g < ntiles; g += 2) {
                 const int tile = tile0 + NC * g + (int)rank;
                 const bool tile_ok = tile < tile_end;         // false only for the dummy slot of an odd range (pair mode)
                 const int b = tile / a.tiles_per_sample;
@@ -443,7 +446,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 const int pos = __popc(vmask & ((1u << lane) - 1u));
                 const unsigned long long v0 = __shfl_sync(0xffffffffu, (unsigned long long)v, vmask ? (__ffs(vmask) - 1) : 0);
                 float* dbase = a.D + (size_t)v0 * a.ldd;
-                uint8_t* stg = sStage + (size_t)qd * 4096;
+                uint8_t* stg = sStage + (size_t)(eset * 4 + qd) * 4096;
                 for (int c = 0; c < a.cout / 32; ++c) {
                     float vv[32];
                     h_tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * half_cols + g * a.cout + c * 32), vv);
@@ -476,25 +479,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                             s1 += xx;
                             s2 = fmaf(xx, xx, s2);
                         }
-                        s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
-                        s_stats[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
+                        s_stats_set[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
+                        s_stats_set[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
                     }
                 }
                 if (a.stats != nullptr) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const int t = threadIdx.x - 64;
+                    if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else asm volatile("bar.sync 2, 128;" ::: "memory");
+                    const int t = qd * 32 + lane;
                     for (int n = t; tile_ok && n < a.cout; n += 128) {
                         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
-                            s1 += s_stats[((w * a.cout) + n) * 2 + 0];
-                            s2 += s_stats[((w * a.cout) + n) * 2 + 1];
+                            s1 += s_stats_set[((w * a.cout) + n) * 2 + 0];
+                            s2 += s_stats_set[((w * a.cout) + n) * 2 + 1];
                         }
                         float* o = a.stats + ((size_t)tile * a.cout + n) * 2;
                         o[0] = s1;
                         o[1] = s2;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else asm volatile("bar.sync 2, 128;" ::: "memory");
                 }
             }
             // this half of TMEM may be overwritten by the MMA warp again
@@ -585,8 +590,8 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     const bool pair = g_halo_pair && a.total_tiles >= 2 * n_sms && n_sms >= 2;
     const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * 128;     // per CTA: pair mode keeps half of the output channels
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
-    const int stage_bytes = 4 * 4096 + 1024;      // epilogue staging tiles (+ alignment)
-    const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 4 * Cout * 2 * 4 - stage_bytes;
+    const int stage_bytes = 8 * 4096 + 1024;      // epilogue staging tiles (+ alignment)
+    const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 8 * Cout * 2 * 4 - stage_bytes;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
     a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
     if (g_halo_w_stages >= 2) {
@@ -596,7 +601,7 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     if (a.a_stages > 2 * a.G) a.a_stages = 2 * a.G;
     if (g_halo_a_stages > 0 && g_halo_a_stages < a.a_stages) a.a_stages = g_halo_a_stages;
     P2PB_CHECK_ARG(a.a_stages >= a.G + 1, "conv3d_halo: shared memory budget exceeded (Cout=%d r=%d)", Cout, r);
-    const size_t smem = 1024 + (size_t)a.w_stages * sub_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)4 * Cout * 2 * 4 + stage_bytes;
+    const size_t smem = 1024 + (size_t)a.w_stages * sub_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)8 * Cout * 2 * 4 + stage_bytes;
     CUtensorMap mapW, mapX;
     {
         static PFN_encodeTiled_h enc = nullptr;
