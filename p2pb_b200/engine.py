@@ -853,9 +853,9 @@ class DualEngine:
 
 def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False):
     """Engine for (net, B, N, F), built once.  allow_dual (the sampling loop): with P2PB_CHAINS=n the batch is split into n
-    independent part-batch chains (DualEngine).  Default 1: measured on B200 (PVDS, 64 patches) one chain 336 patches/s,
-    two chains 330, four 312 -- since the small kernels were rewritten, batch efficiency of the big kernels outweighs the
-    overlap; at 128 patches two chains of 64 reach 355."""
+    independent part-batch chains (DualEngine).  Default 1: measured on B200 (PVDS) one chain 366 patches/s, two chains 361
+    at 64 patches, 390 vs 384 at 128 -- since the small kernels were rewritten, batch efficiency of the big kernels
+    outweighs the overlap."""
     B, _, N = x_shape
     F = 0 if cond_shape is None else cond_shape[1]
     n = int(os.environ.get("P2PB_CHAINS", "1"))
