@@ -120,6 +120,10 @@ int p2pb_gemm_rows_ex(const float* A0, int K0, int lda0, const float* A1, int K1
                       float* stats, float* colmm, int M, int N, void* stream);
 int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const float* A, const float* Bc, int act, float* gmax,
                      void* stream);
+/* neighbourhood max-pool (K = 32 grouped rows per centre, /root/reference/models/pvcnn.py:414) of act(x*A + Bc) from the column
+ * (max, min) per 32-row block of p2pb_gemm_rows_ex/_f16: colmm [B*M, C, 2], A / Bc [B, C] -> out rows [B*M, ldo] */
+int p2pb_pool32_minmax(const float* colmm, int B, int M, int C, const float* A, const float* Bc, int act, float* out, int ldo,
+                       void* stream);
 
 /* IEEE-half operand variants of the two entry points above: A segments / grid and W are __half (K_i resp. Cin multiples
  * of 64, lda multiples of 8), bias / accumulation / D / stats / colmm fp32.  Half keeps the 10-bit mantissa a tf32 operand

@@ -448,6 +448,44 @@ P2PB_API int p2pb_gmax_minmax(const float* colmm, int tiles, int B, int C, const
     return P2PB_OK;
 }
 
+// Neighbourhood max-pool (max over the K = 32 grouped rows of a centre, pvcnn.py:414) of act(x*A + Bc) from the GEMM
+// epilogue's column (max, min) per 32-row block -- one block IS one neighbourhood -- by the same argument as
+// gmax_minmax_kernel (monotone affine map, unimodal Swish): the [B*M*32, C] pre-activation of the last shared-MLP layer is
+// never written and the pooling pass over it disappears.  colmm [B*M, C, 2]; A, Bc [B, C]; out rows [B*M, ldo].
+__global__ void __launch_bounds__(256) pool32_minmax_kernel(const float* __restrict__ colmm, int M, int C,
+                                                            const float* __restrict__ A, const float* __restrict__ Bc, int act,
+                                                            float* __restrict__ out, int ldo, unsigned total)
+{
+    P2PB_PDL_SYNC();
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const unsigned row = e / (unsigned)C;        // b*M + j
+    const int c = (int)(e - row * (unsigned)C);
+    const unsigned b = row / (unsigned)M;
+    const float2 p = *reinterpret_cast<const float2*>(colmm + (size_t)e * 2);
+    const float a = A[(size_t)b * C + c], bb = Bc[(size_t)b * C + c];
+    float y0 = fmaf(p.x, a, bb), y1 = fmaf(p.y, a, bb);
+    if (act == 1) {
+        y0 = swishf(y0);
+        y1 = swishf(y1);
+    }
+    out[(size_t)row * ldo + c] = fmaxf(y0, y1);
+}
+
+P2PB_API int p2pb_pool32_minmax(const float* colmm, int B, int M, int C, const float* A, const float* Bc, int act, float* out,
+                                int ldo, void* stream)
+{
+    const long long total = (long long)B * M * C;
+    P2PB_CHECK_U32(total, "pool32_minmax");
+    if (total == 0) return P2PB_OK;
+    P2PB_CHECK_ARG(ldo >= C, "pool32_minmax: ldo < C");
+    p2pb_prefer_max_smem((const void*)pool32_minmax_kernel);
+    (void)p2pb_launch(pool32_minmax_kernel, dim3(p2pb_cdiv(total, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, colmm, M, C, A, Bc,
+                      act, out, ldo, (unsigned)total);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
 __global__ void fill_kernel(float* p, float v, long long n)
 {
     P2PB_PDL_SYNC();

@@ -391,9 +391,20 @@ class Engine:
             if li == 0 and "w_t" in L:
                 bias2 = self.buf(nm + ".tb", B, L["cout"])
                 self.linear(temb, L["w_t"], None, 0, bias2)
-            raw, stats, tiles = self.gemm(nm, x_segs, x_ks, L["w"], L["b"], L["cout"], rows_per_sample, bias2=bias2)
-            A, Bc, _ = self.coef(nm, stats, tiles, L["n"], L["cout"], rows_per_sample)
             last = li == len(layers) - 1
+            # neighbourhood max-pool over K = 32 grouped rows == one 32-row block of the GEMM epilogue's column (max, min):
+            # the last layer's [B*M*32, C] output is never written and the pooling pass disappears (p2pb_pool32_minmax)
+            pool_mm = (last and final_pool == 32 and final_out is None and rows_per_sample % 128 == 0 and L["cout"] % 32 == 0
+                       and os.environ.get("P2PB_POOL_MINMAX", "1") != "0")
+            raw, stats, tiles = self.gemm(nm, x_segs, x_ks, L["w"], L["b"], L["cout"], rows_per_sample, bias2=bias2,
+                                          minmax=pool_mm, store=not pool_mm)
+            colmm = self.last_colmm
+            A, Bc, _ = self.coef(nm, stats, tiles, L["n"], L["cout"], rows_per_sample)
+            if pool_mm:
+                M_rows = (x_segs[0].shape[0]) // 32
+                out = self.buf(nm + ".pool", M_rows, L["cout"])
+                call("p2pb_pool32_minmax", _p(colmm), B, M_rows // B, L["cout"], _p(A), _p(Bc), 1, _p(out), int(out.stride(0)), _s())
+                return out
             if last and final_out is not None:
                 out = final_out
             elif last and final_pool > 1:
