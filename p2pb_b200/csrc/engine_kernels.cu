@@ -187,20 +187,32 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const float* __restrict__ 
 {
     P2PB_PDL_SYNC();
     // threads = (channel within group) x (tile slice): every thread sums a strided slice of the tiles for one channel in
-    // fp64, slices are combined in a fixed order -> deterministic; the group moments come from the channel sums.
+    // fp64; slices, then channels, are combined by fixed binary trees in shared memory -> deterministic.  The kernel is
+    // pure latency (48 launches per evaluation): the affine parameters are fetched before the reduction, the tile loop is
+    // unrolled so that its loads are in flight together, and no thread walks a serial list.
     __shared__ double s_part[256][2];
     __shared__ double s_ch[128][2];
-    __shared__ double s_g[2];
     const int b = blockIdx.x / groups, g = blockIdx.x % groups;
     const int cpg = C / groups;
     const int t = threadIdx.x;
     const int slices = 256 / cpg;              // cpg is a power of two <= 128 for every layer of the network
     const int c = t % cpg, sl = t / cpg;
     const int ch = g * cpg + c;
+    float p_gamma = 0.f, p_beta = 0.f, p_f = 1.f, p_eb = 0.f;
+    if (t < cpg) {
+        p_gamma = gamma[ch];
+        p_beta = beta[ch];
+        if (emd != nullptr) {
+            p_f = emd[(size_t)b * ld_emd + emd_off + ch];
+            p_eb = emd[(size_t)b * ld_emd + emd_off + C + ch];
+        }
+    }
     double s = 0.0, q = 0.0;
-    if (sl < slices) {
+    {
+        const float* sp = stats + ((size_t)b * tiles * C + ch) * 2;
+#pragma unroll 4
         for (int tl = sl; tl < tiles; tl += slices) {
-            const float2 p = *reinterpret_cast<const float2*>(stats + (((size_t)b * tiles + tl) * C + ch) * 2);
+            const float2 p = *reinterpret_cast<const float2*>(sp + (size_t)tl * C * 2);
             s += (double)p.x;
             q += (double)p.y;
         }
@@ -208,41 +220,39 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const float* __restrict__ 
     s_part[t][0] = s;
     s_part[t][1] = q;
     __syncthreads();
+    for (int stride = slices >> 1; stride > 0; stride >>= 1) {       // slices -> channel sums (rows 0..cpg-1)
+        if (sl < stride) {
+            s_part[t][0] += s_part[t + stride * cpg][0];
+            s_part[t][1] += s_part[t + stride * cpg][1];
+        }
+        __syncthreads();
+    }
     if (t < cpg) {
-        double cs = 0.0, cq = 0.0;
-        for (int k = 0; k < slices; ++k) {
-            cs += s_part[k * cpg + t][0];
-            cq += s_part[k * cpg + t][1];
-        }
-        s_ch[t][0] = cs;
-        s_ch[t][1] = cq;
+        s_ch[t][0] = s_part[t][0];
+        s_ch[t][1] = s_part[t][1];
     }
     __syncthreads();
-    if (t == 0) {
-        double gs = 0.0, gq = 0.0;
-        for (int k = 0; k < cpg; ++k) {
-            gs += s_ch[k][0];
-            gq += s_ch[k][1];
+    for (int stride = cpg >> 1; stride > 0; stride >>= 1) {          // channel sums -> group sums (row 0)
+        if (t < stride) {
+            s_part[t][0] += s_part[t + stride][0];
+            s_part[t][1] += s_part[t + stride][1];
         }
-        s_g[0] = gs;
-        s_g[1] = gq;
+        __syncthreads();
     }
-    __syncthreads();
+    const double gsum = s_part[0][0], gsq = s_part[0][1];
     if (t < cpg) {
         const double n = (double)count * cpg;
-        const double mean = s_g[0] / n;
-        double var = s_g[1] / n - mean * mean;
+        const double mean = gsum / n;
+        double var = gsq / n - mean * mean;
         if (var < 0.0) var = 0.0;
         const float rstd = (float)(1.0 / sqrt(var + (double)eps));
         const float meanf = (float)mean;
         const int chn = g * cpg + t;
-        float a = rstd * gamma[chn];
-        float bb = beta[chn] - meanf * a;
+        float a = rstd * p_gamma;
+        float bb = p_beta - meanf * a;
         if (emd != nullptr) {
-            const float f = emd[(size_t)b * ld_emd + emd_off + chn];
-            const float eb = emd[(size_t)b * ld_emd + emd_off + C + chn];
-            a *= f;
-            bb = bb * f + eb;
+            a *= p_f;
+            bb = bb * p_f + p_eb;
         }
         coefA[(size_t)b * C + chn] = a;
         coefB[(size_t)b * C + chn] = bb;
