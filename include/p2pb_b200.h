@@ -24,6 +24,7 @@ int p2pb_debug_set(int flags);
 int p2pb_device_sm_count(void);
 /* programmatic dependent launch (griddepcontrol.wait, implicit trigger) between the hot-path kernels; default 1 */
 int p2pb_set_pdl(int on);
+int p2pb_set_act_grid(int ctas_per_sm);   /* development aid: persistent grid of the activation passes (0 = one CTA per tile) */
 /* dynamic shared memory the persistent tensor-core kernels may use per CTA, KiB in [128, 227] (default 227) */
 int p2pb_set_smem_budget_kb(int kb);
 /* kernels launched (or captured into a CUDA graph) through this library since load */

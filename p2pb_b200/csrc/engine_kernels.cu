@@ -303,6 +303,20 @@ P2PB_API int p2pb_col_stats(const float* x, int ld, int B, int rows, int C, floa
     return P2PB_OK;
 }
 
+int g_p2pb_act_grid = 0;     // development aid: CTAs per SM of the activation passes' persistent grid (0 = one CTA per 1024 float4)
+P2PB_API int p2pb_set_act_grid(int ctas_per_sm)
+{
+    g_p2pb_act_grid = ctas_per_sm;
+    return P2PB_OK;
+}
+static inline unsigned p2pb_act_grid(long long total4)
+{
+    const long long full = (total4 + 1023) / 1024;
+    if (g_p2pb_act_grid <= 0) return (unsigned)full;
+    const long long cap = (long long)p2pb_num_sms() * g_p2pb_act_grid;
+    return (unsigned)(full < cap ? full : cap);
+}
+
 static inline int p2pb_log2_exact(long long v)      // log2(v) if v is a power of two, else -1
 {
     if (v <= 0 || (v & (v - 1)) != 0) return -1;
@@ -343,27 +357,30 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
 {
     P2PB_PDL_SYNC();
     const unsigned C4 = C >> 2;
-    const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
-    float4 xv[4], a[4], bb[4];
-    size_t m[4];
-    int c[4];
+    // grid-stride over blocks of 4 x blockDim float4 (the launcher picks a persistent grid for large tensors)
+    for (unsigned base = blockIdx.x * (blockDim.x * 4); base < total4; base += gridDim.x * (blockDim.x * 4)) {
+        const unsigned e0 = base + threadIdx.x;
+        float4 xv[4], a[4], bb[4];
+        size_t m[4];
+        int c[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const unsigned e = e0 + k * blockDim.x;
-        if (e < total4) {
-            const unsigned mu = lC4 >= 0 ? (e >> lC4) : e / C4;
-            c[k] = (int)(e - mu * C4) * 4;
-            m[k] = mu;
-            const size_t b = lrps >= 0 ? (mu >> lrps) : mu / (unsigned)rows_per_sample;
-            xv[k] = *reinterpret_cast<const float4*>(x + m[k] * ldx + c[k]);
-            a[k] = __ldg(reinterpret_cast<const float4*>(A + b * C + c[k]));
-            bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c[k]));
+        for (int k = 0; k < 4; ++k) {
+            const unsigned e = e0 + k * blockDim.x;
+            if (e < total4) {
+                const unsigned mu = lC4 >= 0 ? (e >> lC4) : e / C4;
+                c[k] = (int)(e - mu * C4) * 4;
+                m[k] = mu;
+                const size_t b = lrps >= 0 ? (mu >> lrps) : mu / (unsigned)rows_per_sample;
+                xv[k] = *reinterpret_cast<const float4*>(x + m[k] * ldx + c[k]);
+                a[k] = __ldg(reinterpret_cast<const float4*>(A + b * C + c[k]));
+                bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c[k]));
+            }
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const unsigned e = e0 + k * blockDim.x;
-        if (e < total4) store4(out + m[k] * ldo + c[k], affine4<ACT>(xv[k], a[k], bb[k]));
+        for (int k = 0; k < 4; ++k) {
+            const unsigned e = e0 + k * blockDim.x;
+            if (e < total4) store4(out + m[k] * ldo + c[k], affine4<ACT>(xv[k], a[k], bb[k]));
+        }
     }
 }
 
@@ -528,8 +545,8 @@ P2PB_API int p2pb_affine_act(const float* x, int ldx, const float* A, const floa
     if (pool == 1) {
         const long long total4 = (long long)M * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act");
-        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); (void)p2pb_launch(affine_act_kernel<1, float>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
-        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); (void)p2pb_launch(affine_act_kernel<0, float>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+        if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, float>); (void)p2pb_launch(affine_act_kernel<1, float>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+        else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, float>); (void)p2pb_launch(affine_act_kernel<0, float>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, out, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
     } else {
         const long long total4 = (long long)(M / pool) * (C / 4);
         P2PB_CHECK_U32(total4, "affine_act(pool)");
@@ -551,8 +568,8 @@ P2PB_API int p2pb_affine_act_f16(const float* x, int ldx, const float* A, const 
     const long long total4 = (long long)M * (C / 4);
     P2PB_CHECK_U32(total4, "affine_act_f16");
     __half* o = reinterpret_cast<__half*>(out);
-    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); (void)p2pb_launch(affine_act_kernel<1, __half>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
-    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); (void)p2pb_launch(affine_act_kernel<0, __half>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+    if (act) { p2pb_prefer_max_smem((const void*)affine_act_kernel<1, __half>); (void)p2pb_launch(affine_act_kernel<1, __half>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
+    else { p2pb_prefer_max_smem((const void*)affine_act_kernel<0, __half>); (void)p2pb_launch(affine_act_kernel<0, __half>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), s, x, ldx, A, Bc, rows_per_sample, C, o, ldo, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(rows_per_sample)); }
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -1055,8 +1072,9 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
     P2PB_PDL_SYNC();
     const unsigned r3 = r * r * r;
     const unsigned C4 = C >> 2;
-    const unsigned e0 = blockIdx.x * (blockDim.x * 4) + threadIdx.x;
     const int P = r + 1;
+    for (unsigned base = blockIdx.x * (blockDim.x * 4); base < total4; base += gridDim.x * (blockDim.x * 4)) {
+    const unsigned e0 = base + threadIdx.x;
     float4 xv[4], a[4], bb[4];
     size_t orow[4];
     int c[4];
@@ -1086,6 +1104,7 @@ __global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __r
         const unsigned e = e0 + k * blockDim.x;
         if (e < total4) store4(out + orow[k] * ldo + c[k], affine4<1>(xv[k], a[k], bb[k]));
     }
+    }
 }
 
 P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, const float* Bc, int B, int C, int r, float* out,
@@ -1096,7 +1115,7 @@ P2PB_API int p2pb_affine_act_padded(const float* x, int ldx, const float* A, con
     P2PB_CHECK_U32(total4, "affine_act_padded");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<float>);
-    (void)p2pb_launch(affine_act_padded_kernel<float>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, ldx, A, Bc, C, out, C, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
+    (void)p2pb_launch(affine_act_padded_kernel<float>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, ldx, A, Bc, C, out, C, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }
@@ -1111,7 +1130,7 @@ P2PB_API int p2pb_affine_act_padded_f16(const float* x, int ldx, const float* A,
     P2PB_CHECK_U32(total4, "affine_act_padded_f16");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<__half>);
-    (void)p2pb_launch(affine_act_padded_kernel<__half>, dim3(p2pb_cdiv(total4, 1024)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+    (void)p2pb_launch(affine_act_padded_kernel<__half>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;
