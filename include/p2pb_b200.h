@@ -207,6 +207,12 @@ int p2pb_group_rows(const float* feat, int ldf, int Cf, const float* coords, con
                     float* out, int ldo, int B, int N, int M, int U, void* stream);
 int p2pb_group_rows_f16(const float* feat, int ldf, int Cf, const float* coords, const float* centers, const int* idx, void* out,
                         int ldo, int B, int N, int M, int U, void* stream);   /* IEEE-half rows, ldo in halves */
+/* first shared-MLP layer of a set-abstraction module without the grouped tensor (linear in [features[idx], xyz[idx]-centre],
+ * /root/reference/models/pvcnn.py:117-126,174-192): v = Pf[idx] + Wx.(xyz[idx]-centre), Pf = features @ Wf^T + bias per POINT.
+ * mode 0: GroupNorm partials per centre -> stats [B*M, C, 2]; mode 1: swish(v*A+Bc) -> half rows [B*M*32, ldo] */
+int p2pb_group_project(const float* Pf, int ldp, const float* Wx, const float* coords, const float* centers, const int* idx,
+                       const float* A, const float* Bc, float* stats, void* out, int ldo, int B, int C, int N, int M, int U,
+                       int mode, void* stream);
 
 /* 3-NN weighted gather (pvcnn_neighbor_interpolate_gpu.cu:96-124) on rows */
 int p2pb_interp_rows(const float* f, int ldf, const int* idx, const float* w, float* out, int ldo, int B, int C, int N,

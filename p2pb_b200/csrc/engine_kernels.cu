@@ -714,6 +714,85 @@ P2PB_API int p2pb_group_rows_f16(const float* feat, int ldf, int Cf, const float
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// group_project: first shared-MLP layer of a set-abstraction module WITHOUT materialising the grouped tensor.
+// The layer is linear in its grouped input [features[idx], xyz[idx] - centre] (pvcnn.py:117-126, 174-192), so
+//   v[b, j, k, c] = Pf[b, idx[b,j,k], c] + Wx[c] . (xyz[b, idx] - centre[b, j])
+// with Pf = features @ Wf^T + bias (+ time-embedding fold) computed ONCE per point by the GEMM (N rows instead of M*32),
+// and the 3-channel coordinate part evaluated here in fp32 from the fp32 difference (more accurate than rounding it to a
+// tensor-core operand).  One warp per centre, lanes over channels.
+//   mode 0: GroupNorm partials (sum, sum^2) over the centre's 32 rows -> stats [B*M, C, 2]   (the 32-row-block format)
+//   mode 1: y = swish(v*A + Bc) -> IEEE-half rows [B*M*32, ldo] (A operand of the next layer's GEMM)
+// Replaces group_rows + the [B*M*32, C_in] grouped buffer + the first GEMM's [B*M*32, C] output + its activation pass.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) group_project_kernel(const float* __restrict__ Pf, int ldp, const float* __restrict__ Wx,
+                                                            const float* __restrict__ coords, const float* __restrict__ centers,
+                                                            const int* __restrict__ idx, const float* __restrict__ A,
+                                                            const float* __restrict__ Bc, float* __restrict__ stats,
+                                                            __half* __restrict__ out, int ldo, int C, int N, int M, int total_centers)
+{
+    P2PB_PDL_SYNC();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= total_centers) return;
+    const int b = warp / M, j = warp - b * M;
+    const float* co = coords + (size_t)b * 3 * N;
+    const float cx = centers[((size_t)b * 3 + 0) * M + j], cy = centers[((size_t)b * 3 + 1) * M + j], cz = centers[((size_t)b * 3 + 2) * M + j];
+    const int my_src = idx[(size_t)warp * 32 + lane];
+    const float mdx = co[my_src] - cx, mdy = co[my_src + N] - cy, mdz = co[my_src + 2 * N] - cz;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const float wx = Wx[c * 3], wy = Wx[c * 3 + 1], wz = Wx[c * 3 + 2];
+        float a = 0.f, bb = 0.f;
+        if (MODE == 1) {
+            a = A[(size_t)b * C + c];
+            bb = Bc[(size_t)b * C + c];
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const int src = __shfl_sync(0xffffffffu, my_src, k);
+            const float dx = __shfl_sync(0xffffffffu, mdx, k), dy = __shfl_sync(0xffffffffu, mdy, k), dz = __shfl_sync(0xffffffffu, mdz, k);
+            float v = Pf[((size_t)b * N + src) * ldp + c];
+            v = fmaf(wx, dx, v);
+            v = fmaf(wy, dy, v);
+            v = fmaf(wz, dz, v);
+            if (MODE == 0) {
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+            } else {
+                out[((size_t)warp * 32 + k) * ldo + c] = __float2half_rn(swishf(fmaf(v, a, bb)));
+            }
+        }
+        if (MODE == 0) *reinterpret_cast<float2*>(stats + ((size_t)warp * C + c) * 2) = make_float2(s1, s2);
+    }
+}
+
+// Pf [B*N, ldp] fp32, Wx [C, 3], coords [B,3,N], centers [B,3,M], idx [B,M,32]; mode 0 -> stats [B*M, C, 2];
+// mode 1 (A, Bc [B, C]) -> out half rows [B*M*32, ldo]
+P2PB_API int p2pb_group_project(const float* Pf, int ldp, const float* Wx, const float* coords, const float* centers, const int* idx,
+                                const float* A, const float* Bc, float* stats, void* out, int ldo, int B, int C, int N, int M, int U,
+                                int mode, void* stream)
+{
+    P2PB_CHECK_ARG(U == 32 && C % 32 == 0 && C > 0, "group_project: needs 32 neighbours per centre and C %% 32 == 0 (U=%d C=%d)", U, C);
+    P2PB_CHECK_ARG(mode == 0 ? stats != nullptr : (out != nullptr && A != nullptr && Bc != nullptr && ldo >= C), "group_project: bad outputs for mode %d", mode);
+    const long long total = (long long)B * M;
+    if (total == 0) return P2PB_OK;
+    P2PB_CHECK_U32(total * 32, "group_project");
+    const dim3 grid(p2pb_cdiv(total * 32, 256)), block(256);
+    if (mode == 0) {
+        p2pb_prefer_max_smem((const void*)group_project_kernel<0>);
+        (void)p2pb_launch(group_project_kernel<0>, grid, block, (size_t)0, (cudaStream_t)stream, Pf, ldp, Wx, coords, centers, idx, A, Bc,
+                          stats, reinterpret_cast<__half*>(out), ldo, C, N, M, (int)total);
+    } else {
+        p2pb_prefer_max_smem((const void*)group_project_kernel<1>);
+        (void)p2pb_launch(group_project_kernel<1>, grid, block, (size_t)0, (cudaStream_t)stream, Pf, ldp, Wx, coords, centers, idx, A, Bc,
+                          stats, reinterpret_cast<__half*>(out), ldo, C, N, M, (int)total);
+    }
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // interp_rows: out[b*N + n, 0:C] = f[i2]*w2 + f[i1]*w1 + f[i3]*w3 (reference contraction order) from rows [B*M, ldf]
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) interp_rows_kernel(const float* __restrict__ f, int ldf, const int* __restrict__ idx,

@@ -259,6 +259,17 @@ class Engine:
             L["mlp"] = self._pack_mlp(sam.mlps[0].layers, [(3, c_cur, 0), (0, 3, c_cur)],
                                       pad64(c_cur + 3) if sa_half else pad32(c_cur + 3),
                                       temb_cols=(3 + c_cur, E) if temb_sa else None, half_first=sa_half)
+            # gather-after-GEMM form of the first layer (p2pb_group_project): feature part per point, coordinate part in fp32
+            conv0 = sam.mlps[0].layers[0]
+            o0 = conv0.weight.shape[0]
+            w0 = self._w(conv0.weight).reshape(o0, -1)
+            L["proj"] = (self.gemm_f16 and o0 % 32 == 0 and int(sam.num_neighbors[0]) == 32 and len(L["mlp"]) > 1
+                         and L["mlp"][1]["w"].dtype == torch.float16 and os.environ.get("P2PB_GROUP_PROJECT", "1") != "0")
+            if L["proj"]:
+                L["w_f"] = self.zeros(o0, pad32(c_cur))
+                L["w_f"][:, :c_cur] = w0[:, 3:3 + c_cur]
+                L["w_f"] = L["w_f"].contiguous()
+                L["w_x"] = w0[:, 0:3].contiguous()
             L["centers"], L["radius"], L["K"] = sam.num_centers, float(sam.radius[0]), int(sam.num_neighbors[0])
             L["c_grp"] = c_cur
             sa.append(L)
@@ -381,12 +392,12 @@ class Engine:
         call("p2pb_linear_small", _p(x), int(x.stride(0)), _p(w), int(w.stride(0)), _p(bias), x.shape[0], K or w.shape[1],
              O or w.shape[0], act, _p(out), int(out.stride(0)), _s())
 
-    def mlp_chain(self, name, layers, segs, ks, rows_per_sample, temb, final_pool=1, final_out=None):
+    def mlp_chain(self, name, layers, segs, ks, rows_per_sample, temb, final_pool=1, final_out=None, li0=0):
         """(GEMM -> GN/AdaGN coef -> Swish)* ; the last layer's activation optionally max-pools `final_pool` rows."""
         B = self.B
         x_segs, x_ks = segs, ks
         for li, L in enumerate(layers):
-            nm = f"{name}.{li}"
+            nm = f"{name}.{li + li0}"
             bias2 = None
             if li == 0 and "w_t" in L:
                 bias2 = self.buf(nm + ".tb", B, L["cout"])
@@ -416,6 +427,27 @@ class Engine:
             self.act(raw, A, Bc, rows_per_sample, L["cout"], out, act=1, pool=final_pool if last else 1)
             x_segs, x_ks = [out], [out.shape[1]] if not last else None
         return out
+
+    def sa_projected(self, name, L, feats, coords_pts, coords_ctr, nidx, temb, n_pts, M, K, cg):
+        """Set-abstraction shared MLP with the first layer in gather-after-GEMM form (no grouped tensor, no first-layer output):
+        Pf = features @ Wf^T + bias (+ temb fold) per point; statistics and activation of v = Pf[idx] + Wx.(xyz[idx]-centre)
+        are two passes of p2pb_group_project; the remaining layers run as usual on the half activation rows."""
+        B = self.B
+        L0 = L["mlp"][0]
+        c0 = L0["cout"]
+        nm = f"{name}.mlp.0"
+        bias2 = None
+        if "w_t" in L0:
+            bias2 = self.buf(nm + ".tb", B, c0)
+            self.linear(temb, L0["w_t"], None, 0, bias2)
+        pf, _, _ = self.gemm(nm + ".pf", [feats], [pad32(cg)], L["w_f"], L0["b"], c0, n_pts, bias2=bias2, want_stats=False)
+        stats = self.buf(nm + ".stats", B * M, c0, 2)
+        args = (_p(pf), int(pf.stride(0)), _p(L["w_x"]), _p(coords_pts), _p(coords_ctr), _p(nidx))
+        call("p2pb_group_project", *args, _vp(0), _vp(0), _p(stats), _vp(0), 0, B, c0, n_pts, M, K, 0, _s())
+        A, Bc, _ = self.coef(nm, stats, M, L0["n"], c0, M * K)
+        act0 = self.buf(nm + ".act", B * M * K, pad64(c0), dtype=torch.float16)
+        call("p2pb_group_project", *args, _p(A), _p(Bc), _vp(0), _p(act0), int(act0.stride(0)), B, c0, n_pts, M, K, 1, _s())
+        return self.mlp_chain(f"{name}.mlp", L["mlp"][1:], [act0], [act0.shape[1]], M * K, temb, final_pool=K, li0=1)
 
     def pvconv(self, name, P, feats, coords_lvl, prep, temb, n_pts):
         """PVConv (pvcnn.py:306-334): voxel branch + point branch -> rows [B*n_pts, cout]."""
@@ -683,6 +715,9 @@ class Engine:
                 feats = self.pvconv(f"sa{i}.pv{k}", P, feats, coords[i], prep, temb, n_pts)
             main.wait_event(ev_level[i])    # centres + neighbour lists of this level (and the next level's voxel CSRs)
             M, K, cg = Ns[i + 1], L["K"], L["c_grp"]
+            if L["proj"]:
+                feats = self.sa_projected(f"sa{i}", L, feats, coords[i], coords[i + 1], nidx[i], temb, n_pts, M, K, cg)
+                continue
             g16 = L["mlp"][0]["w"].dtype == torch.float16
             kg = pad64(cg + 3) if g16 else pad32(cg + 3)
             grp = self.buf(f"sa{i}.grp", B * M * K, kg, dtype=torch.float16 if g16 else torch.float32)
