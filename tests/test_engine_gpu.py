@@ -50,13 +50,38 @@ def test_engine_single_evaluation_vs_reference_golden(golden_dir, name):
     assert err.mean() <= 2e-3 and err.max() <= 3e-2, (err.mean(), err.max())
 
 
-@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_t30_damped"])
-def test_engine_teacher_forced_steps_vs_reference_golden(golden_dir, name):
-    """Every step of the loop (T=5 on config 1 = first 1024 points of the reference's test.xyz; T=30 on 2 x 2048
-    points), teacher-forced: the engine advances the REFERENCE's state x_t (golden chain) by one bridge step and must
-    land on the reference's x_{t-1}.  (Free-running with un-damped random weights is chaotic -- see DESIGN.md.)"""
-    from p2pb_b200.engine import get_engine
+def _teacher_forced(eng, x_start, chain, T, rel_bound, tag):
+    """Advance the REFERENCE's state x_t by one engine step and compare with the reference's x_{t-1}, for every step.
+    The bound is RELATIVE to that step's displacement (mean|err| <= rel_bound * mean|x_{t-1} - x_t|): a step that returned its
+    input has relative error 1 and fails, whatever the size of the step."""
     from p2pb_b200.p2pb import space_indices
+
+    rev = space_indices(1000, T + 1)[::-1]
+    worst = 0.0
+    for s, (prev, step) in enumerate(zip(rev[1:], rev[:-1])):
+        before = x_start if s == 0 else chain[:, T - s]
+        after_ref = chain[:, T - 1 - s]
+        xs, _ = eng.sample(before.contiguous(), None, [(prev, step)], [prev], False)
+        err = (xs[:, 0] - after_ref).abs().mean().item()
+        disp = (after_ref - before).abs().mean().item()
+        worst = max(worst, err / disp)
+        assert err <= rel_bound * disp, (tag, s, err, disp, err / disp)
+    print(f"{tag} teacher-forced: worst per-step mean|err| / mean|dx| over {T} steps = {worst:.3e} (bound {rel_bound})")
+    return worst
+
+
+# Measured on B200 (profiles/r02_rgpu_report.json): the reference's OWN GPU path (cuDNN TF32 convolutions, its compiled
+# kernels) differs from its fp32 CPU run by 0.18 % (mean over steps) / 0.25 % (worst step) of the step displacement; its fp32
+# GPU run by 3e-6.  The engine (10-bit-mantissa operands everywhere a contraction runs, not only in the convolutions) is held
+# to 1 %: four times the reference's own TF32 spread, two orders of magnitude below "did nothing".
+TEACHER_FORCED_REL = 0.01
+
+
+@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_t30", "pvds_t30_damped"])
+def test_engine_teacher_forced_steps_vs_reference_golden(golden_dir, name):
+    """Every step of the loop (T=5 on config 1 = first 1024 points of the reference's test.xyz; T=30 on 2 x 2048 points with
+    the UN-damped and the damped seeded checkpoint), teacher-forced against the chain of the reference's real model code."""
+    from p2pb_b200.engine import get_engine
 
     z, cfg = _golden(golden_dir, name)
     model, _ = build(cfg, backend="engine", head_scale=float(z["head_scale"]))
@@ -64,25 +89,86 @@ def test_engine_teacher_forced_steps_vs_reference_golden(golden_dir, name):
     chain = torch.from_numpy(z["x_chain"]).cuda()          # [B, T, 3, N], index 0 = final state
     x = torch.from_numpy(z["x_start"]).cuda()
     eng = get_engine(model, model.model, x.shape, None)
-    rev = space_indices(1000, T + 1)[::-1]
-    worst = 0.0
-    for s, (prev, step) in enumerate(zip(rev[1:], rev[:-1])):
-        before = x if s == 0 else chain[:, T - s]
-        after_ref = chain[:, T - 1 - s]
-        xs, _ = eng.sample(before.contiguous(), None, [(prev, step)], [prev], False)
-        d = (xs[:, 0] - after_ref).abs()
-        worst = max(worst, d.max().item())
-        assert d.mean().item() < 5e-4 and d.max().item() < 1e-2, (s, d.mean().item(), d.max().item())
-    print(f"{name} teacher-forced: worst max|diff| over {T} steps = {worst:.3e}")
+    _teacher_forced(eng, x, chain, T, TEACHER_FORCED_REL, name)
+
+
+def test_engine_teacher_forced_pvdl_8192_vs_rgpu(golden_dir):
+    """PVDL at N = 8192 (BASELINE configs 3-4), T = 5 loop, against the chain of the UNMODIFIED reference run on a B200
+    (fp32; oracle/gen_golden_rgpu.py), plus one evaluation against its eps."""
+    from p2pb_b200.engine import get_engine
+
+    z = np.load(os.path.join(golden_dir, "rgpu_golden.npz"))
+    cfg = load_cfg("PVDL_SNPP", **{"data.npoints": 8192, "model.extra_feature_channels": 0})
+    model, _ = build(cfg, backend="engine")
+    x = torch.from_numpy(z["pvdl8192_x_start"]).cuda()
+    chain = torch.from_numpy(z["pvdl8192_x_chain"]).cuda()
+    eng = get_engine(model, model.model, x.shape, None)
+    _teacher_forced(eng, x, chain, 5, TEACHER_FORCED_REL, "pvdl8192")
+    eps = _one_evaluation(eng, x, float(z["pvdl8192_noise_level"][0]))
+    err = (eps - torch.from_numpy(z["pvdl8192_eps_fp32"]).cuda()).abs()
+    print(f"PVDL N=8192 engine vs R-GPU fp32 eps: mean|err|={err.mean():.3e} max|err|={err.max():.3e}")
+    assert err.mean().item() <= 2e-3 and err.max().item() <= 5e-2
+
+
+def _one_evaluation(eng, x, noise_level):
+    B, _, N = x.shape
+    with torch.no_grad():
+        sin = eng.time_embedding(noise_level, None)[None].expand(B, -1).contiguous()
+        th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
+        eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
+        eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
+        eps_rows = eng.evaluate(x.contiguous(), temb)
+    torch.cuda.synchronize()
+    return eps_rows[:, :3].reshape(B, N, 3).permute(0, 2, 1)
+
+
+def test_engine_bench_config_vs_rgpu(golden_dir):
+    """The BENCHMARKED configuration itself (bench.py: 64 synthetic 2048-point patches, PVDS, T = 30) against the UNMODIFIED
+    reference run on a B200 (oracle/gen_golden_rgpu.py -> tests/golden/rgpu_golden.npz).  At 64 patches the kernels take
+    the CTA-pair / balanced-tile-range code paths the small goldens do not reach.
+      (1) one evaluation, un-damped weights, continuous compare with the reference's fp32 eps (same tolerance as the small
+          goldens; the reference's own TF32 path differs from it by 2.9e-4 mean / 2.3e-3 max, 1.5e-3 max run to run);
+      (2) free-running T = 30 on the damped-head checkpoint: Chamfer(engine, R-GPU fp32) per patch within
+          max(1e-5, 2 x the reference's own Chamfer(TF32, fp32)) -- mean and worst patch.  The reference's floor, measured:
+          mean 1.9e-6 / worst patch 7.3e-6 (TF32 vs fp32), 1.1e-6 / 6.6e-6 (run to run, fp32 atomics).
+    Un-damped free-running T = 30 is not comparable for ANY implementation: the reference's own two runs differ by Chamfer
+    1.2e-2 (mean over patches; do-nothing 7.5e-2), profiles/r02_rgpu_report.json."""
+    import bench
+    from p2pb_b200 import ops
+    from p2pb_b200.engine import get_engine
+
+    z = np.load(os.path.join(golden_dir, "rgpu_golden.npz"))
+    B = int(z["cfg2_B"])
+    cfg = load_cfg("PVDS_PUNet")
+    x = bench.synth_patches(64, 2048, seed=1000)[:B].cuda()
+    model, _ = build(cfg, backend="engine")
+    eng = get_engine(model, model.model, x.shape, None)
+    eps = _one_evaluation(eng, x, float(z["cfg2_noise_level"][0]))
+    err = (eps - torch.from_numpy(z["cfg2_eps_fp32"]).cuda()).abs()
+    print(f"B={B} engine vs R-GPU fp32 eps: mean|err|={err.mean():.3e} max|err|={err.max():.3e}")
+    assert err.mean().item() <= 2e-3 and err.max().item() <= 3e-2
+    model, _ = build(cfg, backend="engine", head_scale=0.02)
+    out = model.sample(x_start=x, steps=30, log_count=1, verbose=False)["x_pred"]
+    ref = torch.from_numpy(z["cfg2_damped_x_pred_fp32"]).cuda()
+    cd = torch.tensor(ops.calculate_cd(out, ref))
+    cd0 = torch.tensor(ops.calculate_cd(x, ref))
+    b_mean = max(1e-5, 2 * float(z["floor_cd_tf32_vs_fp32_mean"]))
+    b_max = max(1e-5, 2 * float(z["floor_cd_tf32_vs_fp32_max"]))
+    print(f"B={B} T=30 damped: chamfer(engine, R-GPU fp32) mean={cd.mean():.3e} max={cd.max():.3e} (bounds {b_mean:.2e} / {b_max:.2e}; "
+          f"reference TF32-vs-fp32 floor {float(z['floor_cd_tf32_vs_fp32_mean']):.2e} / {float(z['floor_cd_tf32_vs_fp32_max']):.2e}; "
+          f"do-nothing {cd0.mean():.3e})")
+    assert cd.mean().item() <= b_mean and cd.max().item() <= b_max, (cd.mean().item(), cd.max().item())
 
 
 @pytest.mark.parametrize("name", ["pvds_cfg1_damped", "pvds_t30_damped"])
 def test_engine_free_running_loop_vs_reference_golden(golden_dir, name):
     """Free-running T-step loop through P2PB.sample (engine, one CUDA graph) on the damped-head checkpoint vs the
-    reference's real P2PB.sample: Chamfer (calculate_cd_cuda definition) within the north-star bound 1e-5."""
+    reference's real P2PB.sample (fp32 CPU).  Bound: max(1e-5, 2 x the reference's own TF32-vs-fp32 Chamfer on a B200 for a
+    T = 30 loop of this checkpoint, worst patch 7.3e-6 -- tests/golden/rgpu_golden.npz) = 1.47e-5; T = 5: the north-star 1e-5."""
     from p2pb_b200 import ops
 
     z, cfg = _golden(golden_dir, name)
+    fl = np.load(os.path.join(golden_dir, "rgpu_golden.npz"))
     model, _ = build(cfg, backend="engine", head_scale=float(z["head_scale"]))
     x = torch.from_numpy(z["x_start"]).cuda()
     T = int(z["T"])
@@ -94,10 +180,10 @@ def test_engine_free_running_loop_vs_reference_golden(golden_dir, name):
     cd = ops.calculate_cd(out["x_pred"], ref)
     diff = (out["x_pred"] - ref).abs()
     moved = (ref - x).abs().mean().item()
-    print(f"{name}: T={T} chamfer={max(cd):.3e} mean|diff|={diff.mean():.3e} max|diff|={diff.max():.3e} (mean |x_pred-x_start|={moved:.3e})")
-    # T=5 (the reference scripts' default step count): the north-star bound.  T=30: rounding-level differences (TF32
-    # vs the fp32 golden) are amplified step after step by the discrete ops; bound 5e-5, measured value printed above.
-    assert max(cd) < (1e-5 if T <= 5 else 5e-5), cd
+    bound = 1e-5 if T <= 5 else max(1e-5, 2 * float(fl["floor_cd_tf32_vs_fp32_max"]))
+    print(f"{name}: T={T} chamfer={max(cd):.3e} (bound {bound:.2e}) mean|diff|={diff.mean():.3e} max|diff|={diff.max():.3e} "
+          f"(mean |x_pred-x_start|={moved:.3e})")
+    assert max(cd) <= bound, cd
     assert diff.mean().item() < 0.1 * moved + 1e-4
 
 
