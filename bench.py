@@ -40,7 +40,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--backend", default=os.environ.get("P2PB_BACKEND", "engine"), choices=["engine", "eager"])
+    ap.add_argument("--backend", default="engine", choices=["engine", "eager"],
+                    help="eager = the validation path (torch library layers); the bench line of record is the engine")
+    ap.add_argument("--no-graph", action="store_true", help="profiling aid: enqueue kernels directly (ncu launch lists)")
+    ap.add_argument("--chains", type=int, default=1, help="development aid: part-batch chains inside the graph")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patches per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -181,6 +184,10 @@ def run_b200(args):
     from p2pb_b200.p2pb import P2PB
     from p2pb_b200.unet_pvc import PVCNN2Unet
 
+    from p2pb_b200 import engine as ENG
+
+    ENG.OPTIONS.no_graph = bool(args.no_graph)
+    ENG.OPTIONS.chains = int(args.chains)
     cfg_dict = load_cfg_dict()
     cfg = Config.wrap(cfg_dict)
     cfg.gpu = str(dev)

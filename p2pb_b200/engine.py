@@ -49,16 +49,39 @@ def pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
-# Operands of the large-grid voxel convolutions (conv_halo) are stored as IEEE half: same 10-bit mantissa as the tf32
-# operands the tensor core would otherwise truncate them to, twice the channels per byte and per MMA (conv_halo.cu).
-# (P2PB_HALO_F16=0 keeps them fp32 / tf32), and likewise the r = 8 voxel convs (per-tap implicit GEMM) and the global
-# PointNet's GEMMs (P2PB_GEMM_F16=0).  Read when an Engine is built.
+class Options:
+    """Build-time knobs of the engine.  There is ONE product path: these defaults.  The process environment does not change
+    the arithmetic or the kernels that run; tests and the profiling tools under ``tools/`` flip a knob by assigning to
+    ``engine.OPTIONS`` before an Engine is built (tests/test_engine_gpu.py shows each alternative is still correct).
+
+    halo_f16 / gemm_f16: operands of the large-grid voxel convolutions (conv_halo) resp. of the r = 8 convs, the global
+        PointNet and the shared-MLP chains are stored as IEEE half -- the same 10-bit mantissa a tf32 operand keeps inside
+        the tensor core, twice the channels per byte and per MMA.  False keeps fp32 storage / kind::tf32 (also what a layer
+        falls back to when its weights do not fit half's exponent range, see Engine._half_ok).
+    group_project: first set-abstraction layer in gather-after-GEMM form;  pool_minmax: neighbourhood max-pool from the GEMM
+        epilogue's column (max, min);  point_stream: PVConv point branch on a second stream;  chains: independent part-batch
+        chains inside one graph (DualEngine);  no_graph: enqueue the kernels directly instead of replaying the captured
+        CUDA graph (profilers that cannot see inside graphs)."""
+
+    def __init__(self):
+        self.halo_f16 = True
+        self.gemm_f16 = True
+        self.group_project = True
+        self.pool_minmax = True
+        self.point_stream = True
+        self.chains = 1
+        self.no_graph = False
+
+
+OPTIONS = Options()
+
+
 def halo_f16() -> bool:
-    return os.environ.get("P2PB_HALO_F16", "1") != "0"
+    return OPTIONS.halo_f16
 
 
 def gemm_f16() -> bool:
-    return os.environ.get("P2PB_GEMM_F16", "1") != "0"
+    return OPTIONS.gemm_f16
 
 
 class _AdaGN:
@@ -128,6 +151,9 @@ class Engine:
         """c_in = valid channels of the incoming rows (features[, xyz]); temb_in: 64 time channels follow in the
         reference's channel order.  coords_first: reference input order is [xyz, feats] (level 0) -> ours [feats, xyz]."""
         E = self.E if temb_in else 0
+        if getattr(mod, "attn", None) is not None:
+            raise NotImplementedError("PVConv with attention=True: no shipped config builds one (pvcnn.py:692,709 shadow "
+                                      "`fp_blocks`), the fused engine does not implement it")
         conv1, n1, conv2, n2 = mod.voxel_layers[0], mod.voxel_layers[1], mod.voxel_layers[4], mod.voxel_layers[5]
         se = mod.voxel_layers[6] if len(mod.voxel_layers) > 6 else None
         cout = conv1.out_channels
@@ -264,7 +290,7 @@ class Engine:
             o0 = conv0.weight.shape[0]
             w0 = self._w(conv0.weight).reshape(o0, -1)
             L["proj"] = (self.gemm_f16 and o0 % 32 == 0 and int(sam.num_neighbors[0]) == 32 and len(L["mlp"]) > 1
-                         and L["mlp"][1]["w"].dtype == torch.float16 and os.environ.get("P2PB_GROUP_PROJECT", "1") != "0")
+                         and L["mlp"][1]["w"].dtype == torch.float16 and OPTIONS.group_project)
             if L["proj"]:
                 L["w_f"] = self.zeros(o0, pad32(c_cur))
                 L["w_f"][:, :c_cur] = w0[:, 3:3 + c_cur]
@@ -406,7 +432,7 @@ class Engine:
             # neighbourhood max-pool over K = 32 grouped rows == one 32-row block of the GEMM epilogue's column (max, min):
             # the last layer's [B*M*32, C] output is never written and the pooling pass disappears (p2pb_pool32_minmax)
             pool_mm = (last and final_pool == 32 and final_out is None and rows_per_sample % 128 == 0 and L["cout"] % 32 == 0
-                       and os.environ.get("P2PB_POOL_MINMAX", "1") != "0")
+                       and OPTIONS.pool_minmax)
             raw, stats, tiles = self.gemm(nm, x_segs, x_ks, L["w"], L["b"], L["cout"], rows_per_sample, bias2=bias2,
                                           minmax=pool_mm, store=not pool_mm)
             colmm = self.last_colmm
@@ -458,7 +484,7 @@ class Engine:
         # on a second stream and fills the gaps the voxel branch leaves (conv tails, the HBM-bound activation pass)
         main = torch.cuda.current_stream()
         pt_done = None
-        pstream = self._point_stream() if os.environ.get("P2PB_POINT_STREAM", "1") != "0" else None
+        pstream = self._point_stream() if OPTIONS.point_stream else None
         if pstream is not None:
             fork = torch.cuda.Event()
             fork.record(main)
@@ -772,7 +798,7 @@ class Engine:
         xt = self.buf("xt", B, 3, N)
         li = 0
         for s, (prev, step) in enumerate(pairs):
-            sin = self.buf("temb.sin", len(pairs), E)
+            sin = self.buf(f"temb.sin{len(pairs)}", len(pairs), E)
             th = self.buf("temb.h", B, E)
             temb = self.buf("temb", B, E)
             row = sin[s:s + 1].expand(B, E)       # stride-0 view: every sample shares the noise level in sampling
@@ -781,7 +807,7 @@ class Engine:
             eps = self.evaluate(xt, temb)
             logged = prev in log_set
             x0 = x0_buf[li] if logged else None
-            call("p2pb_bridge_update", _p(xt), _p(eps), 16, _p(self.buf("coef", len(pairs), 3)[s]), int(bool(clip)), _p(xt),
+            call("p2pb_bridge_update", _p(xt), _p(eps), 16, _p(self.buf(f"coef{len(pairs)}", len(pairs), 3)[s]), int(bool(clip)), _p(xt),
                  _p(x0), B, N, _s())
             if logged:
                 xs_buf[li].copy_(xt)
@@ -795,8 +821,8 @@ class Engine:
         log_set = set(log_steps)
         n_log = sum(1 for prev, _ in pairs if prev in log_set)
         # per-step host tables: sinusoid of the noise level, posterior scalars (fp32, same op order as p_posterior)
-        sin = self.buf("temb.sin", T, E)
-        coef = self.buf("coef", T, 3)
+        sin = self.buf(f"temb.sin{T}", T, E)       # keyed by T: sample(steps=...) may change between calls
+        coef = self.buf(f"coef{T}", T, 3)
         sin_h = torch.stack([self.time_embedding(float(p.noise_levels[step].item()), None) for _, step in pairs])
         coef_h = torch.tensor([p.posterior_coefs(prev, step) for prev, step in pairs], dtype=torch.float32)
         sin.copy_(sin_h)
@@ -810,11 +836,16 @@ class Engine:
 
     def sample(self, x1, x_cond, pairs, log_steps, clip):
         """pairs = [(prev_step, step)] in sampling order -> (xs, pred_x0s) [B, log_count, 3, N], logged steps flipped
-        to ascending time like ``sample_ddpm`` (p2pb.py:215-262)."""
+        to ascending time like ``sample_ddpm`` (p2pb.py:215-262).  Runs on the engine's own device whatever the caller's
+        current device is (denoise_object.py --gpu cuda:1)."""
+        with torch.cuda.device(self.dev):
+            return self._sample(x1, x_cond, pairs, log_steps, clip)
+
+    def _sample(self, x1, x_cond, pairs, log_steps, clip):
         log_set, xs_buf, x0_buf = self.prepare(x1, x_cond, pairs, log_steps)
         xt = self.buf("xt", self.B, 3, self.N)
         key = (tuple(pairs), tuple(sorted(log_set)), bool(clip))
-        if os.environ.get("P2PB_NO_GRAPH"):     # debugging aid: same kernels, no graph capture
+        if OPTIONS.no_graph:     # profiling aid: same kernels, no graph capture
             self._run_loop(pairs, log_set, clip, xs_buf, x0_buf)
             xs = torch.flip(xs_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
             return xs, torch.flip(x0_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
@@ -871,11 +902,15 @@ class DualEngine:
             cur.wait_stream(st)
 
     def sample(self, x1, x_cond, pairs, log_steps, clip):
+        with torch.cuda.device(self.dev):
+            return self._sample(x1, x_cond, pairs, log_steps, clip)
+
+    def _sample(self, x1, x_cond, pairs, log_steps, clip):
         h = self.part
         parts = [(x1[i * h:(i + 1) * h], None if x_cond is None else x_cond[i * h:(i + 1) * h]) for i in range(self.n)]
         prep = [e.prepare(x, c, pairs, log_steps) for e, (x, c) in zip(self.halves, parts)]
         key = (tuple(pairs), tuple(sorted(prep[0][0])), bool(clip))
-        if os.environ.get("P2PB_NO_GRAPH"):
+        if OPTIONS.no_graph:
             self._run_all(pairs, prep, clip)
         else:
             if key not in self._graphs:
@@ -904,14 +939,25 @@ def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False):
     outweighs the overlap."""
     B, _, N = x_shape
     F = 0 if cond_shape is None else cond_shape[1]
-    n = int(os.environ.get("P2PB_CHAINS", "1"))
+    n = int(OPTIONS.chains)
     while n > 1 and (B % n != 0 or B // n < 8):
         n -= 1
     dual = allow_dual and n > 1
+    # the packed weights are a snapshot: key them by the parameters' in-place version counters, so that a
+    # load_state_dict / optimizer step after the first sample() rebuilds the engine instead of running stale weights
+    version = sum(int(p._version) for p in net.parameters()) + sum(int(b._version) for b in net.buffers())
     key = (id(net), B, N, F, n if dual else 1)
-    eng = p2pb._engines.get(key)
-    if eng is None:
-        eng = DualEngine(p2pb, net, B, N, F, n) if dual else Engine(p2pb, net, B, N, F)
-        p2pb._engines[key] = eng
+    entry = p2pb._engines.get(key)
+    if entry is not None and entry[0] != version:
+        for k in [k for k in p2pb._engines if k[0] == id(net)]:
+            del p2pb._engines[k]            # every shape's engine of this net is stale: free their buffers
+        entry = None
+    if entry is None:
+        dev = next(net.parameters()).device
+        with torch.cuda.device(dev):
+            eng = DualEngine(p2pb, net, B, N, F, n) if dual else Engine(p2pb, net, B, N, F)
+        entry = (version, eng)
+        p2pb._engines[key] = entry
+    eng = entry[1]
     p2pb.last_engine = eng
     return eng

@@ -307,7 +307,7 @@ def test_voxelize_sparse_equals_dense_and_clears():
 
 
 def test_dual_chain_engine_equals_single_chain(monkeypatch):
-    """With P2PB_CHAINS=2 a batch runs as two half-batch chains on two streams in one CUDA graph (DualEngine).
+    """With engine.OPTIONS.chains = 2 a batch runs as two half-batch chains on two streams in one CUDA graph (DualEngine).
     Patches never interact, every kernel is deterministic and per-sample, so the result must equal the single-chain
     engine bit for bit, and graph replays must be reproducible."""
     from p2pb_b200.engine import DualEngine, Engine
@@ -315,12 +315,14 @@ def test_dual_chain_engine_equals_single_chain(monkeypatch):
     cfg = load_cfg("PVDS_PUNet")
     x = patch_input(16, 1024, seed=21).cuda()
     model, _ = build(cfg, backend="engine", head_scale=0.02)
-    monkeypatch.setenv("P2PB_CHAINS", "2")
+    from p2pb_b200 import engine as E
+
+    monkeypatch.setattr(E.OPTIONS, "chains", 2)
     out_dual = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_chain"].clone()
     assert isinstance(model.last_engine, DualEngine)
     again = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_chain"]
     assert torch.equal(out_dual, again)
-    monkeypatch.setenv("P2PB_CHAINS", "1")
+    monkeypatch.setattr(E.OPTIONS, "chains", 1)
     out_single = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_chain"]
     assert isinstance(model.last_engine, Engine)
     assert torch.equal(out_dual, out_single), (out_dual - out_single).abs().max()
@@ -371,10 +373,11 @@ def test_denoise_room_entry_point_end_to_end(tmp_path):
 
 
 def test_engine_tf32_operand_path_still_matches_golden(golden_dir, monkeypatch):
-    """P2PB_HALO_F16=0 / P2PB_GEMM_F16=0: every contraction with fp32-stored (tf32) operands -- the path the IEEE-half
+    """engine.OPTIONS.halo_f16 = gemm_f16 = False: every contraction with fp32-stored (tf32) operands -- the path the IEEE-half
     operand storage replaced -- stays available and inside the same tolerance.  Measured on B200 vs the fp32 golden:
     half operands mean|err| 4.2e-4 / max 5.3e-3, tf32 operands 3.9e-4 / 5.6e-3; between the two 3.4e-4 / 5.5e-3 (both round
     the operands to 10 mantissa bits, half to nearest, tf32 by truncation)."""
+    from p2pb_b200 import engine as E
     from p2pb_b200.engine import get_engine
 
     z, cfg = _golden(golden_dir, "pvds_b2")
@@ -383,8 +386,8 @@ def test_engine_tf32_operand_path_still_matches_golden(golden_dir, monkeypatch):
     nl = float(z["noise_level"][0])
     outs = {}
     for flag in ("1", "0"):
-        monkeypatch.setenv("P2PB_HALO_F16", flag)
-        monkeypatch.setenv("P2PB_GEMM_F16", flag)
+        monkeypatch.setattr(E.OPTIONS, "halo_f16", flag == "1")
+        monkeypatch.setattr(E.OPTIONS, "gemm_f16", flag == "1")
         model, _ = build(cfg, backend="engine")
         eng = get_engine(model, model.model, x.shape, None)
         assert eng.halo_f16 == (flag == "1")
@@ -401,3 +404,33 @@ def test_engine_tf32_operand_path_still_matches_golden(golden_dir, monkeypatch):
     d = np.abs(outs["1"] - outs["0"])
     print(f"half vs tf32 operands: mean|diff|={d.mean():.3e} max|diff|={d.max():.3e}")
     assert d.mean() <= 1e-3
+
+
+def test_sample_with_two_step_counts_and_reloaded_weights():
+    """One model, sample(steps=3) then sample(steps=5) (the reference takes `steps` per call, p2pb.py:337-363), then a
+    load_state_dict: the engine must be rebuilt from the new weights (packed weights are a snapshot), and reloading the old
+    weights must reproduce the first result bit for bit."""
+    from p2pb_b200.model_loader import seeded_state_dict
+
+    cfg = load_cfg("PVDS_PUNet")
+    model, _ = build(cfg, backend="engine", head_scale=0.02)
+    x = patch_input(2, 1024, seed=3).cuda()
+    a3 = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_pred"].clone()
+    a5 = model.sample(x_start=x, steps=5, log_count=5, verbose=False)["x_pred"].clone()
+    assert not torch.equal(a3, a5)
+    assert torch.equal(a3, model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_pred"])
+    sd0 = {k: v.clone() for k, v in model.model.state_dict().items()}
+    model.model.load_state_dict(seeded_state_dict(model.model, seed=1, head_scale=0.02))
+    b3 = model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_pred"].clone()
+    assert not torch.equal(a3, b3), "engine kept the packed weights of the previous state dict"
+    model.model.load_state_dict(sd0)
+    assert torch.equal(a3, model.sample(x_start=x, steps=3, log_count=3, verbose=False)["x_pred"])
+
+
+def test_engine_refuses_configs_it_does_not_implement():
+    """No silent dispatch to the library-layer path: a stochastic (ot_ode=false) sampler raises with a clear message."""
+    cfg = load_cfg("PVDS_PUNet", **{"diffusion.ot_ode": False})
+    model, _ = build(cfg, backend="engine", head_scale=0.02)
+    x = patch_input(1, 1024, seed=3).cuda()
+    with pytest.raises(NotImplementedError, match="ot_ode"):
+        model.sample(x_start=x, steps=2, log_count=1, verbose=False)

@@ -1,5 +1,5 @@
 """Dev tool: PVDL (configs 3-4 of BASELINE.json: N=8192, data.npoints=8192) throughput of the engine, T steps.
-usage: python tools/bench_pvdl.py [batch] [T] [extra_channels]"""
+usage: python tools/bench_pvdl.py [batch] [T] [extra_channels] [nograph]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, yaml
@@ -12,6 +12,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 extra = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 N = 8192
+if len(sys.argv) > 4 and sys.argv[4] == "nograph":      # ncu launch lists cannot see inside a CUDA graph
+    from p2pb_b200 import engine as _E
+    _E.OPTIONS.no_graph = True
 cfg_dict = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "..", "p2pb_b200", "configs", "PVDL_SNPP.yaml")))
 cfg_dict["data"]["npoints"] = N
 cfg_dict["model"]["extra_feature_channels"] = extra
