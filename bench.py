@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patches per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (R-GPU arm, PVDL configs 3-5) and `parity`")
     return ap.parse_args()
 
 
@@ -124,6 +125,108 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def sustained_peak_tflops():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16 sustained"
+    except Exception:
+        return 1408.0, "fallback (BASELINE.md)"
+
+
+PVDL_GFLOP_PER_EVAL = {0: 332.99, 3: 332.99, 387: 333.39}       # SURVEY.md 8(d), per patch per network evaluation at N = 8192
+PVDL_B_PER_GPU, PVDL_N = 32, 8192
+
+
+def pvdl_configs(dev, rank, world, timed_fn):
+    """BASELINE configs 3-5 on the engine: PVDL (data.npoints = 8192), 32 patches of 8192 points per GPU, T = 30; xyz only /
+    xyz+RGB (x_cond 3 ch) / xyz+RGB+DINOv2 (x_cond 387 ch).  Same timing rules as the headline (CUDA events, max over ranks,
+    patches sharded over ranks, no data-path collective).  -> {name: {...}}"""
+    import torch
+    import yaml
+
+    from p2pb_b200.config import Config
+    from p2pb_b200.model_loader import seeded_state_dict
+    from p2pb_b200.p2pb import P2PB
+    from p2pb_b200.unet_pvc import PVCNN2Unet
+    from tests.helpers import patch_input
+
+    peak, peak_src = sustained_peak_tflops()
+    out = {}
+    for name, extra in (("pvdl_8192_xyz", 0), ("pvdl_8192_rgb", 3), ("pvdl_8192_rgb_dino", 387)):
+        cfg_dict = yaml.safe_load(open(os.path.join(ROOT, "p2pb_b200", "configs", "PVDL_SNPP.yaml")))
+        cfg_dict["data"]["npoints"] = PVDL_N
+        cfg_dict["model"]["extra_feature_channels"] = extra
+        cfg = Config.wrap(cfg_dict)
+        cfg.gpu = str(dev)
+        cfg.model.ema = False
+        net = PVCNN2Unet(cfg)
+        net.load_state_dict(seeded_state_dict(net, seed=0), strict=True)
+        model = P2PB(cfg, net.to(dev)).eval()
+        x = patch_input(PVDL_B_PER_GPU, PVDL_N, seed=7 + rank).to(dev)
+        xc = None
+        if extra:
+            g = torch.Generator().manual_seed(1 if extra == 3 else 2)
+            xc = torch.rand(PVDL_B_PER_GPU, 3, PVDL_N, generator=g)
+            if extra > 3:
+                xc = torch.cat([xc, torch.randn(PVDL_B_PER_GPU, extra - 3, PVDL_N, generator=g)], 1)
+            xc = xc.to(dev)
+        ms, _ = timed_fn(lambda: model.sample(x_start=x, x_cond=xc, steps=TSTEPS, log_count=1, verbose=False, use_ema=False), 2, 3)
+        rate = PVDL_B_PER_GPU * world / (ms / 1e3)
+        ceiling = peak * 1e12 / (PVDL_GFLOP_PER_EVAL[extra] * 1e9 * TSTEPS)
+        out[name] = {"value": rate, "unit": UNIT, "ms_per_step": ms, "patches_per_gpu": PVDL_B_PER_GPU, "npoints": PVDL_N, "T": TSTEPS,
+                     "x_cond_channels": extra, "algorithmic_tflops": rate * PVDL_GFLOP_PER_EVAL[extra] * TSTEPS / 1e3,
+                     "ceiling_patches_s_per_gpu": ceiling, "frac_of_ceiling": rate / world / ceiling,
+                     "ceiling": f"{peak_src} {peak:.1f} TFLOP/s / ({PVDL_GFLOP_PER_EVAL[extra]} GFLOP x T={TSTEPS})"}
+        del model, net
+        torch.cuda.empty_cache()
+    return out
+
+
+def rgpu_arm(local):
+    """The reference's own GPU path (oracle/rgpu_bench.py) in a separate process on this rank's GPU."""
+    try:
+        o = subprocess.run([sys.executable, "-m", "oracle.rgpu_bench", "--device", f"cuda:{local}", "--pvdl"], cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        lines = [l for l in o.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"available": False, "why": (o.stderr or "no output")[-300:]}
+    except Exception as ex:
+        return {"available": False, "why": repr(ex)[:300]}
+
+
+def parity_live(dev):
+    """Chamfer (calculate_cd_cuda definition) between THIS run's engine and the committed output of the unmodified reference
+    on a B200 (tests/golden/rgpu_golden.npz, fp32), on the bench's own 64 patches, T = 30, damped-head seeded checkpoint --
+    next to the reference's own TF32-vs-fp32 floor measured in the same golden run."""
+    import numpy as np
+    import torch
+
+    from p2pb_b200 import ops
+    from p2pb_b200.config import Config
+    from p2pb_b200.model_loader import seeded_state_dict
+    from p2pb_b200.p2pb import P2PB
+    from p2pb_b200.unet_pvc import PVCNN2Unet
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rgpu_golden.npz"))
+    cfg = Config.wrap(load_cfg_dict())
+    cfg.gpu = str(dev)
+    cfg.model.ema = False
+    net = PVCNN2Unet(cfg)
+    net.load_state_dict(seeded_state_dict(net, seed=0, head_scale=0.02), strict=True)
+    model = P2PB(cfg, net.to(dev)).eval()
+    x = synth_patches(B_PER_GPU, NPTS, seed=1000).to(dev)
+    out = model.sample(x_start=x, steps=TSTEPS, log_count=1, verbose=False, use_ema=False)["x_pred"]
+    ref = torch.from_numpy(z["cfg2_damped_x_pred_fp32"]).to(dev)
+    cd = torch.tensor(ops.calculate_cd(out, ref))
+    cd0 = torch.tensor(ops.calculate_cd(x, ref))
+    fm, fx = float(z["floor_cd_tf32_vs_fp32_mean"]), float(z["floor_cd_tf32_vs_fp32_max"])
+    return {"what": "Chamfer(engine, unmodified reference on B200 fp32), 64 bench patches, T=30, damped-head seeded checkpoint",
+            "chamfer_mean": float(cd.mean()), "chamfer_max": float(cd.max()), "chamfer_do_nothing_mean": float(cd0.mean()),
+            "reference_floor_tf32_vs_fp32": {"mean": fm, "max": fx},
+            "reference_floor_run_to_run": {"mean": float(z["floor_cd_run_to_run_mean"]), "max": float(z["floor_cd_run_to_run_max"])},
+            "bound": {"mean": max(1e-5, 2 * fm), "max": max(1e-5, 2 * fx)},
+            "ok": bool(cd.mean() <= max(1e-5, 2 * fm) and cd.max() <= max(1e-5, 2 * fx))}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -258,6 +361,29 @@ def run_b200(args):
             roofline = RL.dominant_kernel_roofline(model, B, dev)
         except Exception as ex:  # keep the bench line even if the micro-timing fails
             roofline = {"error": repr(ex)}
+    dtype_name = getattr(eng, "dtype_name", "tf32") if eng is not None else "tf32"
+    extra, parity = None, None
+    if not args.no_extra and args.backend == "engine":
+        del model, net, eng                                   # free the headline engine's buffers before the PVDL engines
+        torch.cuda.empty_cache()
+        try:
+            extra = pvdl_configs(dev, rank, world, timed)
+        except Exception as ex:
+            extra = {"error": repr(ex)[:300]}
+        if rank == 0:
+            try:
+                parity = parity_live(dev)
+            except Exception as ex:
+                parity = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
+            if world == 1:
+                rg = rgpu_arm(local)
+                extra["rgpu"] = rg
+                if rg.get("available"):
+                    extra["rgpu_patches_s"] = rg["pvds_2048"]["patches_per_s"]
+                    extra["speedup_vs_rgpu"] = value / rg["pvds_2048"]["patches_per_s"]
+                    if "pvdl_8192_xyz" in rg and "pvdl_8192_xyz" in extra:
+                        extra["pvdl_8192_xyz"]["rgpu_patches_s"] = rg["pvdl_8192_xyz"]["patches_per_s"]
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, cores, sample = cpu_port_rate(cfg_dict)
@@ -266,7 +392,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": getattr(eng, "dtype_name", "tf32") if eng is not None else "tf32", "data": "synthetic",
+            "dtype": dtype_name, "data": "synthetic",
             "config": {"workload": WORKLOAD, "backend": args.backend, "patches_per_gpu": B, "npoints": NPTS, "T": TSTEPS,
                        "weights": "seeded random-init, reference checkpoint layout",
                        "l2": "256 MiB L2 flush between timed iterations; per-step working set >> 126 MB L2",
@@ -275,7 +401,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": host_x.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
-"""Room denoising entry point: same CLI / ``opt.yaml`` discovery / ``.ply`` output as the reference's ``denoise_room.py``
-(flags :292-312, flow :424-570), running the B200 hot path; patches shard data-parallel across GPUs when launched
-with ``torchrun`` (one process per GPU), the per-point running mean of the reference (:262-289) becomes per-rank
-sums + ONE ``all_reduce`` (NCCL over NVLink) -- see ``p2pb_b200/parallel.py``.
+"""Room denoising entry point: same CLI / ``opt.yaml`` discovery / output naming / ``.ply`` output as the reference's
+``denoise_room.py`` (flags :292-312, flow :424-570), running the B200 hot path.  Patch creation, normalisation and reassembly
+run on the device (``p2pb_b200/room.py``, ``csrc/room.cu``); launched with ``torchrun`` (one process per GPU) every rank
+creates and denoises its own shard of the patch jobs and the per-point running mean of the reference (:262-289) becomes
+per-rank fixed-point sums + ONE ``all_reduce`` (NCCL over NVLink).
 
-radius patches (device radius query, ``ops.radius_query``; the reference builds a CPU KD-tree, :454-465) -> pad with
-jittered duplicates / FPS down to ``npoints`` -> batched
-``P2PB.sample`` -> reassembly -> ``.ply``.  Deviations from the reference, switchable with ``--strict_ref``: the
-reference drops the last patch of every chunk (:498-505) -- here every patch is denoised; ``fpsample`` (absent) is
-replaced by this repo's FPS kernel (start index 0).
+All reference flags are honoured: ``--average_predictions False`` (FPS of all denoised patches, :523-531, 552-556),
+``--intermediate`` (one ``*_step_i.ply`` per sampling step, :475-478, 512-521, 566-570), the fill of points no patch touched
+(:540-550).  ``--strict_ref`` additionally reproduces the reference's dropped last patch per chunk (:492-505) and draws the
+padding randoms from np.random in its order (the default is a counter-based device RNG, rank-count independent).
 """
 from __future__ import annotations
 
@@ -19,11 +19,16 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from p2pb_b200 import ops
+from p2pb_b200 import room as R
 from p2pb_b200.config import load_yaml
 from p2pb_b200.io_ply import read_ply, write_ply
 from p2pb_b200.model_loader import load_diffusion, logger
-from p2pb_b200.parallel import RoomAccumulator, shard_range
+
+
+def _bool(v):
+    """argparse ``type=bool`` of the reference (any non-empty string is True, denoise_room.py:298,303) -- plus the literal
+    spellings of False, so that ``--average_predictions False`` does what it says."""
+    return bool(v) and str(v).lower() not in ("false", "0", "no")
 
 
 def parse_args(argv=None):
@@ -31,11 +36,11 @@ def parse_args(argv=None):
     p.add_argument("--room_path", type=str, required=True, help="Path to the room point cloud.")
     p.add_argument("--model_path", type=str, required=True, help="Path to the model.")
     p.add_argument("--seed", type=int, default=42, help="Random seed.")
-    p.add_argument("--use_ema", type=bool, default=True, help="Use EMA model for prediction.")
+    p.add_argument("--use_ema", type=_bool, default=True, help="Use EMA model for prediction.")
     p.add_argument("--feature_name", type=str, default="dino_iphone")
     p.add_argument("--out_path", type=str, default=None, help="Path to save the denoised room.")
     p.add_argument("--overwrite", action="store_true", help="Overwrite existing predictions.")
-    p.add_argument("--average_predictions", type=bool, default=True, help="Average out predictions.")
+    p.add_argument("--average_predictions", type=_bool, default=True, help="Average out predictions.")
     p.add_argument("--steps", type=int, default=5, help="Number of steps for the diffusion.")
     p.add_argument("--k", type=int, default=4, help="Number of patches to sample.")
     p.add_argument("--intermediate", action="store_true", help="Save intermediate steps.")
@@ -43,7 +48,7 @@ def parse_args(argv=None):
     p.add_argument("--local_rank", type=int, default=int(os.environ.get("LOCAL_RANK", 0)), help="Local rank.")
     p.add_argument("--gpu", type=str, default=None, help="GPU to use.")
     p.add_argument("--distribution_type", default="none")
-    p.add_argument("--strict_ref", action="store_true", help="reproduce the reference's dropped last patch per chunk")
+    p.add_argument("--strict_ref", action="store_true", help="reproduce the reference's dropped last patch per chunk and np.random padding")
     args = p.parse_args(argv)
     cfg = load_yaml(os.path.join(os.path.dirname(args.model_path), "opt.yaml"))
     cfg.merge(vars(args))
@@ -53,118 +58,87 @@ def parse_args(argv=None):
     return cfg
 
 
-def create_patches(room_points, patch_size, idx_lists, room_colors=None, room_dino=None, device="cuda"):
-    """denoise_room.py:352-421 -> (xyz [P,n,3], rgb, dino, idx [P,n], cut [P])."""
-    xyz, rgb, dino, idxs, cuts = [], [], [], [], []
-    for mapping in idx_lists:
-        pts = room_points[mapping]
-        n = len(pts)
-        if n == 0:
-            continue
-        if n < patch_size:                                   # pad with jittered random duplicates (:369-395)
-            extra = np.random.randint(0, n, patch_size - n)
-            noise = np.linalg.norm(pts.max(0) - pts.min(0)) * 1e-2
-            add = pts[extra] + np.random.normal(0, noise, (patch_size - n, 3))
-            sel = np.concatenate([np.arange(n), extra])
-            xyz.append(np.concatenate([pts, add], 0))
-            idxs.append(mapping[sel])
-            cuts.append(n)
-            if room_colors is not None:
-                rgb.append(room_colors[mapping][sel])
-            if room_dino is not None:
-                dino.append(room_dino[mapping][sel])
-        else:                                                # FPS down to patch_size (:400-419), n//patch_size+1 times
-            c = torch.from_numpy(pts.T.copy()).float().unsqueeze(0).to(device)
-            sel = ops.furthest_point_sampling(c, patch_size)[0].long().cpu().numpy()
-            for _ in range(n // patch_size + 1):
-                xyz.append(pts[sel])
-                idxs.append(mapping[sel])
-                cuts.append(patch_size)
-                if room_colors is not None:
-                    rgb.append(room_colors[mapping][sel])
-                if room_dino is not None:
-                    dino.append(room_dino[mapping][sel])
-    st = lambda l: np.stack(l) if l else None
-    return st(xyz), st(rgb), st(dino), st(idxs), np.array(cuts)
+def default_out_path(cfg) -> str:
+    """denoise_room.py:430-445."""
+    model_training_steps = cfg.model_path.split("_")[-1].split(".")[0]
+    model_config = cfg.model_path.split("/")[-2]
+    ema = "_ema" if cfg.use_ema else ""
+    room_source = cfg.room_path.split("/")[-1].split(".")[0]
+    return os.path.join(os.path.dirname(cfg.room_path), "..", "predictions", "P2SB",
+                        f"{model_config.replace('_', '-')}_{room_source.replace('_', '-')}_{model_training_steps}_{cfg.steps}{ema}.ply")
 
 
-@torch.no_grad()
-def denoise_patch_batch(xyz, model, cfg, rgb=None, dino=None):
-    """denoise_room.py:115-178: per-patch centre / max-norm scale, sample, de-normalise."""
-    x = torch.from_numpy(xyz).float().to(cfg.gpu)
-    center = x.mean(dim=1, keepdim=True)
-    x = x - center
-    scale = x.norm(dim=2).amax(dim=1)[:, None, None]
-    x = (x / scale).transpose(1, 2).contiguous()
-    cond = None
-    if cfg.data.get("use_rgb_features") and rgb is not None:
-        cond = torch.from_numpy(rgb).float().to(cfg.gpu).transpose(1, 2)
-    if cfg.data.get("point_features") == "dino" and dino is not None:
-        d = torch.from_numpy(dino).float().to(cfg.gpu).transpose(1, 2)
-        cond = d if cond is None else torch.cat([cond, d], dim=1)
-    out = model.sample(x_start=x, x_cond=None if cond is None else cond.contiguous(), verbose=False, steps=cfg.steps,
-                       use_ema=cfg.use_ema, log_count=1)["x_pred"]
-    return out.transpose(1, 2) * scale + center
+def load_room_files(cfg):
+    """denoise_room.py:324-349."""
+    room_points, room_colors = read_ply(cfg.room_path)
+    if room_colors is not None and len(room_colors) != len(room_points):
+        logger.warning("Color array has different length than point array. Setting colors to None.")
+        room_colors = None
+    room_dino = None
+    if cfg.data.get("point_features") == "dino":
+        fp = os.path.join(os.path.dirname(cfg.room_path), "..", "features", f"{cfg.feature_name}.npy")
+        try:
+            room_dino = np.load(fp)
+            if "arkit" not in str(cfg.data.dataset).lower():
+                room_dino = room_dino.T
+        except Exception:
+            logger.warning("No dino features found")
+    return room_points, room_colors, room_dino
 
 
 def main(argv=None):
     cfg = parse_args(argv)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(cfg.gpu)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(cfg.local_rank)
         dist.init_process_group("nccl")
     torch.manual_seed(cfg.seed)
-    np.random.seed(cfg.seed)          # same seed on every rank: identical patch lists, then sharded
-    out_path = os.path.abspath(cfg.out_path) if cfg.out_path else os.path.join(
-        os.path.dirname(cfg.room_path), "..", "predictions", "P2SB", os.path.basename(cfg.room_path))
+    np.random.seed(cfg.seed)
+    out_path = os.path.abspath(cfg.out_path) if cfg.out_path else default_out_path(cfg)
     if os.path.exists(out_path) and not cfg.overwrite:
         logger.info(f"Prediction already exists at {out_path}")
         return
     model, _ = load_diffusion(cfg)
-    room_points, room_colors = read_ply(cfg.room_path)
-    room_dino = None
-    if cfg.data.get("point_features") == "dino":
-        fp = os.path.join(os.path.dirname(cfg.room_path), "..", "features", f"{cfg.feature_name}.npy")
-        if os.path.exists(fp):
-            room_dino = np.load(fp)
-            if "arkit" not in str(cfg.data.dataset).lower():
-                room_dino = room_dino.T
-    npts = cfg.data.npoints
-    n_centers = int(np.ceil(room_points.shape[0] / npts) * cfg.k)
-    pts_dev = torch.from_numpy(room_points).float().to(cfg.gpu).contiguous()
-    c = pts_dev.t().contiguous().unsqueeze(0)
-    center_idx = ops.furthest_point_sampling(c, n_centers)[0].long()
+    room_points, room_colors, room_dino = load_room_files(cfg)
+    dev = torch.device(cfg.gpu)
+    room = torch.from_numpy(np.ascontiguousarray(room_points)).float().to(dev).contiguous()
+    feats = None                                   # x_cond channels in the reference's order: rgb, then dino (:149-153)
+    if cfg.data.get("use_rgb_features") and room_colors is not None:
+        rgb = room_colors.astype(np.float32) / (255.0 if room_colors.dtype == np.uint8 else 1.0)
+        feats = torch.from_numpy(rgb).float().to(dev)
+    if cfg.data.get("point_features") == "dino" and room_dino is not None:
+        d = torch.from_numpy(np.ascontiguousarray(room_dino)).float().to(dev)
+        feats = d if feats is None else torch.cat([feats, d], dim=1)
     radius = 0.3 if "scannet" in str(cfg.data.dataset).lower() else 0.5
-    # KDTree.query_radius of the reference (denoise_room.py:454-465) on the device: CSR with ascending indices per centre
-    off, idx = ops.radius_query(pts_dev[center_idx].contiguous(), pts_dev, radius)
-    off, idx = off.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
-    idx_lists = [idx[off[i]:off[i + 1]] for i in range(n_centers)]
-    xyz, rgb, dino, idxs, cuts = create_patches(room_points, npts, idx_lists, room_colors, room_dino, cfg.gpu)
-    P = xyz.shape[0]
-    lo, hi = shard_range(P, rank, world)
-    acc = RoomAccumulator(room_points.shape[0], device=cfg.gpu)
-    bs = cfg.batch_size
-    for s in range(lo, hi, bs):
-        e = min(s + bs, hi)
-        sl = np.arange(s, e)
-        if cfg.strict_ref and len(sl) > 1:
-            sl = sl[:-1]                                     # the reference's [start:end] with end = last index
-        pad = bs - len(sl)                                   # static batch shape for the captured graph
-        take = np.concatenate([sl, np.repeat(sl[-1:], pad)]) if pad else sl
-        den = denoise_patch_batch(xyz[take], model, cfg, None if rgb is None else rgb[take], None if dino is None else dino[take])
-        for j, p in enumerate(sl):
-            acc.add(torch.from_numpy(idxs[p][: cuts[p]]), den[j, : cuts[p]])
-    mean, count = acc.reduce()
+    logger.info(f"Detected dataset: {cfg.data.dataset}, denoising in radius {radius}")
+    res = R.sweep(model, room, int(cfg.data.npoints), int(cfg.k), radius, int(cfg.steps), int(cfg.batch_size), int(cfg.seed),
+                  feats=None if feats is None else feats.contiguous(), use_ema=bool(cfg.use_ema),
+                  average_predictions=bool(cfg.average_predictions), intermediate=bool(cfg.intermediate),
+                  strict_ref=bool(cfg.strict_ref), rank=rank, world=world)
     if rank == 0:
-        out = room_points.copy()
-        m = count.cpu().numpy() > 0
-        out[m] = mean.cpu().numpy()[m]
         os.makedirs(os.path.dirname(out_path), exist_ok=True)
-        write_ply(out_path, out, room_colors)
-        logger.info(f"wrote {out_path} ({int(m.sum())} of {len(m)} points updated)")
+        if cfg.average_predictions:
+            out = res.denoised.cpu().numpy()
+            cnt = res.count.cpu().numpy()
+            missing = R.fill_not_updated(out, cnt)
+            if missing:
+                logger.warning(f"There are {missing} points that did not get updated.")
+            write_ply(out_path, out, room_colors)
+            logger.info(f"wrote {out_path} ({int((cnt > 0).sum())} of {len(cnt)} points updated, {res.n_jobs} patch jobs)")
+            if res.steps is not None:
+                for i, st in enumerate(res.steps):
+                    s = st.cpu().numpy()
+                    R.fill_not_updated(s, cnt)
+                    # the reference names these f"{out_path.split('.')[0]}_step_{i}.ply" (:569), which cuts at the FIRST dot of the path
+                    # -- inside the "/../" of its own default out_path; the intended stem is used here
+                    write_ply(f"{os.path.splitext(out_path)[0]}_step_{i}.ply", s, room_colors)
+        else:
+            write_ply(out_path, res.denoised.cpu().numpy().astype(np.float64), room_colors)
+            logger.info(f"wrote {out_path} (FPS of {res.n_jobs} denoised patches, no averaging)")
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

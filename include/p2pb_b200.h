@@ -230,6 +230,34 @@ int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N, float* 
 int p2pb_bridge_update(const float* xt, const float* eps, int lde, const float* coef, int clip, float* xt_next,
                        float* pred_x0, int B, int N, void* stream);
 
+/* ---- room sweep: device-side patch creation and reassembly (/root/reference/denoise_room.py) ---------------------------------
+ * All work on the radius-query CSR of the room: room [N,3] fp32 row-major, off int64 [P+1], csr int32 [off[P]] (p2pb_radius_fill). */
+
+/* replaces the under-full branch of create_patches (denoise_room.py:369-395): rows 0..n-1 = the patch, rows n..M-1 = random
+ * duplicates + N(0, (1e-2 |bbox diagonal|)^2) jitter, cut = n.  job_patch int32 [n_jobs] = CSR patch of each job; job_key int32
+ * [n_jobs] (optional) = the number its random draws are keyed by (global patch number when the CSR is one rank's shard).  RNG:
+ * counter-based on (seed, key, slot), or -- all three of pre_off int64 [n_jobs+1], pre_idx int32, pre_noise fp32 [.,3] given --
+ * host-drawn randoms (the reference's np.random sequence).  -> xyz_out [n_jobs,M,3], idx_out int32 [n_jobs,M], cut_out int32 [n_jobs] */
+int p2pb_room_pad_patches(const float* room, const long long* off, const int* csr, const int* job_patch, const int* job_key,
+                          int n_jobs, int M, unsigned long long seed, const long long* pre_off, const int* pre_idx, const float* pre_noise,
+                          float* xyz_out, int* idx_out, int* cut_out, void* stream);
+
+/* replaces the over-full branch (denoise_room.py:396-419, fpsample.bucket_fps_kdline_sampling per replica): exact FPS of M points
+ * from LOCAL start index job_start[j] for every (patch, replica) job, one 8-CTA cluster per job; n_max = largest patch among the
+ * jobs (<= 102400).  -> xyz_out [n_jobs,M,3] in FPS order, idx_out int32 [n_jobs,M] */
+int p2pb_room_fps_patches(const float* room, const long long* off, const int* csr, const int* job_patch, const int* job_start,
+                          int n_jobs, int n_max, int M, float* xyz_out, int* idx_out, void* stream);
+
+/* replaces the normalisation of denoise_patch_batch (denoise_room.py:141-146), fp64 statistics:
+ * xyz [P,M,3] -> x_start [P,3,M] fp32, center f64 [P,3], scale f64 [P] */
+int p2pb_patch_normalize(const float* xyz, int P, int M, float* x_start, double* center, double* scale, void* stream);
+
+/* replaces update_prediction_noisy_batches (denoise_room.py:262-289) + the de-normalisation (:176): x_pred [P,3,M] -> per-point
+ * fixed-point sums int64 [N,3] (units of 2^-40) and counts int32 [N], ACCUMULATED with integer atomics (order-independent, so
+ * bit-identical for any patch order / batch split / rank count); only rows < cut[p] contribute */
+int p2pb_room_accumulate(const float* x_pred, const double* center, const double* scale, const int* idx, const int* cut, int P,
+                         int M, long long* sum_fixed, int* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

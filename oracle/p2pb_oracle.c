@@ -226,50 +226,58 @@ ORA_API void ora_gather_features_forward(const float *feat, const int32_t *idx, 
  * the 9-level tree keeps the LOWER slot on ties (:170).  So the winner is the maximum of d2 with the
  * lexicographically smallest key (k mod 512, k); threads with no point contribute (best=-1, besti=0).
  * ------------------------------------------------------------------------------------------- */
-ORA_API void ora_furthest_point_sampling(const float *coords, int B, int N, int M, int32_t *idx)
+static void fps_one(const float *c, int N, int M, int start, int32_t *ix)
 {
     const int BS = 512;
+    float *dist = (float *)malloc(sizeof(float) * (size_t)N);
+    float tb[512];
+    int ti[512];
+    for (int i = 0; i < N; ++i) dist[i] = 1e38f;
+    int old = start;
+    ix[0] = start;
+    for (int j = 1; j < M; ++j) {
+        const float x1 = c[old], y1 = c[old + N], z1 = c[old + 2 * N];
+        for (int t = 0; t < BS; ++t) {
+            tb[t] = -1.f;
+            ti[t] = 0;
+        }
+        for (int k = 0; k < N; ++k) {
+            const float d = sqdist3(c[k] - x1, c[k + N] - y1, c[k + 2 * N] - z1);
+            const float d2 = fminf(d, dist[k]);
+            dist[k] = d2;
+            const int t = k % BS;
+            if (d2 > tb[t]) {
+                tb[t] = d2;
+                ti[t] = k;
+            }
+        }
+        /* tree reduction, lower slot wins ties (strict <) */
+        float best = tb[0];
+        int besti = ti[0];
+        for (int t = 1; t < BS; ++t)
+            if (best < tb[t]) {
+                best = tb[t];
+                besti = ti[t];
+            }
+        old = besti;
+        ix[j] = old;
+    }
+    free(dist);
+}
+
+ORA_API void ora_furthest_point_sampling(const float *coords, int B, int N, int M, int32_t *idx)
+{
     memset(idx, 0, sizeof(int32_t) * (size_t)B * (M > 0 ? M : 0));
     if (M <= 0) return;
 #pragma omp parallel for schedule(static)
-    for (int b = 0; b < B; ++b) {
-        const float *c = coords + (size_t)b * 3 * N;
-        int32_t *ix = idx + (size_t)b * M;
-        float *dist = (float *)malloc(sizeof(float) * (size_t)N);
-        float tb[512];
-        int ti[512];
-        for (int i = 0; i < N; ++i) dist[i] = 1e38f;
-        int old = 0;
-        ix[0] = 0;
-        for (int j = 1; j < M; ++j) {
-            const float x1 = c[old], y1 = c[old + N], z1 = c[old + 2 * N];
-            for (int t = 0; t < BS; ++t) {
-                tb[t] = -1.f;
-                ti[t] = 0;
-            }
-            for (int k = 0; k < N; ++k) {
-                const float d = sqdist3(c[k] - x1, c[k + N] - y1, c[k + 2 * N] - z1);
-                const float d2 = fminf(d, dist[k]);
-                dist[k] = d2;
-                const int t = k % BS;
-                if (d2 > tb[t]) {
-                    tb[t] = d2;
-                    ti[t] = k;
-                }
-            }
-            /* tree reduction, lower slot wins ties (strict <) */
-            float best = tb[0];
-            int besti = ti[0];
-            for (int t = 1; t < BS; ++t)
-                if (best < tb[t]) {
-                    best = tb[t];
-                    besti = ti[t];
-                }
-            old = besti;
-            ix[j] = old;
-        }
-        free(dist);
-    }
+    for (int b = 0; b < B; ++b) fps_one(coords + (size_t)b * 3 * N, N, M, 0, idx + (size_t)b * M);
+}
+
+/* The same selection rule from an arbitrary start index: the over-full branch of create_patches (denoise_room.py:396-419)
+ * draws a fresh start per replica (fpsample.bucket_fps_kdline_sampling, start_idx=None -> random; un-vendored, parity unpinned). */
+ORA_API void ora_fps_from_start(const float *coords, int N, int M, int start, int32_t *idx)
+{
+    if (M > 0) fps_one(coords, N, M, start, idx);
 }
 
 /* ---------------------------------------------------------------------------------------------

@@ -226,6 +226,16 @@ def knn_points(queries: torch.Tensor, points: torch.Tensor, K: int, return_dist:
     return (idx, dist) if return_dist else idx
 
 
+def radius_count(centers: torch.Tensor, points: torch.Tensor, radius: float) -> torch.Tensor:
+    """Number of ``points [N,3]`` within ``radius`` of each ``centers [P,3]`` row -> int32 [P] (first pass of radius_query)."""
+    _chk(centers, torch.float32, "centers", 2)
+    _chk(points, torch.float32, "points", 2)
+    counts = torch.empty((centers.shape[0],), dtype=torch.int32, device=points.device)
+    with torch.cuda.device(points.device):
+        call("p2pb_radius_count", _ptr(centers), _ptr(points), centers.shape[0], points.shape[0], _f(float(radius)), _ptr(counts), _stream())
+    return counts
+
+
 def radius_query(centers: torch.Tensor, points: torch.Tensor, radius: float):
     """All ``points [N,3]`` within ``radius`` of each ``centers [P,3]`` row (``KDTree.query_radius`` of
     denoise_room.py:454-465) -> (offsets int64 [P+1], indices int32 [offsets[-1]]), indices ascending per centre."""
@@ -242,3 +252,71 @@ def radius_query(centers: torch.Tensor, points: torch.Tensor, radius: float):
         call("p2pb_radius_fill", _ptr(centers), _ptr(points), P, N, _f(float(radius)), _ptr(offsets), _ptr(indices), _stream())
     return offsets, indices
 
+
+
+# ---- room sweep: device-side patch creation and reassembly (csrc/room.cu; denoise_room.py:352-421, 141-146, 262-289) ---------
+def room_pad_patches(room: torch.Tensor, off: torch.Tensor, csr: torch.Tensor, job_patch: torch.Tensor, M: int, seed: int,
+                     pre=None, job_key: torch.Tensor = None):
+    """Under-full radius patches (n < M) -> (xyz [J,M,3], idx int32 [J,M], cut int32 [J]).  ``pre`` = (pre_off int64 [J+1],
+    pre_idx int32, pre_noise fp32 [.,3]) replaces the counter-based RNG by host-drawn randoms (``--strict_ref``); ``job_key``
+    int32 [J] = the numbers the counter RNG is keyed by (global patch numbers; default ``job_patch``)."""
+    _chk(room, torch.float32, "room", 2)
+    _chk(off, torch.int64, "off", 1)
+    _chk(csr, torch.int32, "csr", 1)
+    _chk(job_patch, torch.int32, "job_patch", 1)
+    J, dev = job_patch.shape[0], room.device
+    xyz = torch.empty((J, M, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((J, M), dtype=torch.int32, device=dev)
+    cut = torch.empty((J,), dtype=torch.int32, device=dev)
+    po, pi, pn = (None, None, None) if pre is None else pre
+    with torch.cuda.device(dev):
+        call("p2pb_room_pad_patches", _ptr(room), _ptr(off), _ptr(csr), _ptr(job_patch), _ptr(job_key), J, int(M), ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)),
+             _ptr(po), _ptr(pi), _ptr(pn), _ptr(xyz), _ptr(idx), _ptr(cut), _stream())
+    return xyz, idx, cut
+
+
+def room_fps_patches(room: torch.Tensor, off: torch.Tensor, csr: torch.Tensor, job_patch: torch.Tensor, job_start: torch.Tensor,
+                     n_max: int, M: int):
+    """Over-full radius patches (n >= M): exact FPS of M points from local start index ``job_start`` per (patch, replica) job
+    -> (xyz [J,M,3] in FPS order, idx int32 [J,M])."""
+    _chk(room, torch.float32, "room", 2)
+    _chk(off, torch.int64, "off", 1)
+    _chk(csr, torch.int32, "csr", 1)
+    _chk(job_patch, torch.int32, "job_patch", 1)
+    _chk(job_start, torch.int32, "job_start", 1)
+    J, dev = job_patch.shape[0], room.device
+    xyz = torch.empty((J, M, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((J, M), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_room_fps_patches", _ptr(room), _ptr(off), _ptr(csr), _ptr(job_patch), _ptr(job_start), J, int(n_max), int(M),
+             _ptr(xyz), _ptr(idx), _stream())
+    return xyz, idx
+
+
+def patch_normalize(xyz: torch.Tensor):
+    """xyz [P,M,3] -> (x_start [P,3,M] fp32 centred / max-norm scaled, center f64 [P,3], scale f64 [P])."""
+    _chk(xyz, torch.float32, "xyz", 3)
+    P, M, _ = xyz.shape
+    dev = xyz.device
+    x = torch.empty((P, 3, M), dtype=torch.float32, device=dev)
+    c = torch.empty((P, 3), dtype=torch.float64, device=dev)
+    s = torch.empty((P,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        call("p2pb_patch_normalize", _ptr(xyz), P, M, _ptr(x), _ptr(c), _ptr(s), _stream())
+    return x, c, s
+
+
+def room_accumulate(x_pred: torch.Tensor, center: torch.Tensor, scale: torch.Tensor, idx: torch.Tensor, cut: torch.Tensor,
+                    sum_fixed: torch.Tensor, count: torch.Tensor) -> None:
+    """Add the de-normalised predictions of P patches into ``sum_fixed int64 [N,3]`` (2^-40 units) / ``count int32 [N]``."""
+    _chk(x_pred, torch.float32, "x_pred", 3)
+    _chk(center, torch.float64, "center", 2)
+    _chk(scale, torch.float64, "scale", 1)
+    _chk(idx, torch.int32, "idx", 2)
+    _chk(cut, torch.int32, "cut", 1)
+    _chk(sum_fixed, torch.int64, "sum_fixed", 2)
+    _chk(count, torch.int32, "count", 1)
+    P, _, M = x_pred.shape
+    with torch.cuda.device(x_pred.device):
+        call("p2pb_room_accumulate", _ptr(x_pred), _ptr(center), _ptr(scale), _ptr(idx), _ptr(cut), P, M, _ptr(sum_fixed), _ptr(count),
+             _stream())
