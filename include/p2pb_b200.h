@@ -27,6 +27,9 @@ int p2pb_set_pdl(int on);
 int p2pb_set_act_grid(int ctas_per_sm);   /* development aid: persistent grid of the activation passes (0 = one CTA per tile) */
 /* dynamic shared memory the persistent tensor-core kernels may use per CTA, KiB in [128, 227] (default 227) */
 int p2pb_set_smem_budget_kb(int kb);
+/* range guard of the IEEE-half operand storage: number of values that exceeded half's largest finite value (65504) in any
+ * half-producing kernel since the last reset; *host_count is a HOST pointer; synchronises `stream` */
+int p2pb_half_overflow_count(int reset, unsigned int* host_count, void* stream);
 /* kernels launched (or captured into a CUDA graph) through this library since load */
 unsigned long long p2pb_launch_count(void);
 
@@ -224,6 +227,10 @@ int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw, const f
 
 /* LinearAttention core on the bottleneck tokens (/root/reference/models/modules.py:186-192) */
 int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N, float* out, int ldo, void* stream);
+
+/* softmax attention core on the bottleneck tokens: modules.Attention / Attend (/root/reference/models/modules.py:197-264, 77-162),
+ * `attention_type: flash`; qkv rows [B*N, 3*H*32] = [to_q | to_kv] outputs */
+int p2pb_attention_softmax_small(const float* qkv, int ldq, int B, int H, int N, float* out, int ldo, void* stream);
 
 /* pred_x0 = xt - std*eps ; xt_next = mu_x0*pred_x0 + mu_xn*xt  (/root/reference/models/p2pb.py:155-165, 190-213);
  * coef = device pointer to {std_fwd[n], mu_x0, mu_xn} */

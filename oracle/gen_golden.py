@@ -73,6 +73,10 @@ CASES = [
     # un-damped T=30 chain: the teacher-forced test advances the reference's state one step at a time, so chaos does not
     # matter and the per-step displacement is large enough for a RELATIVE bound (an identity step fails)
     ("pvds_t30", "PVDS_PUNet", {}, "synth", 2, 2048, 30, 0, 1.0),
+    # attention_type: flash -> modules.Attention / Attend at the bottleneck (unet_pvc.py:98-99, 238-241)
+    ("pvds_flash", "PVDS_PUNet", {"model.PVD.attention_type": "flash"}, "synth", 2, 1024, 2, 0, 1.0),
+    ("pvdl_flash", "PVDL_SNPP", {"data.npoints": 512, "model.extra_feature_channels": 0, "model.PVD.attention_type": "flash"},
+     "synth", 1, 512, 1, 0, 1.0),
 ]
 
 

@@ -124,6 +124,19 @@ def linear_attention(sd, key, x, heads):
     return _pw(sd, key + ".to_out", out)
 
 
+def softmax_attention(sd, key, x, heads):
+    """modules.py:197-264 (Attention with norm=False, no time_cond, no qk_norm) around Attend (:77-162, scaled dot-product softmax),
+    with the transposes of unet_pvc.py:239-241: x [B,C,N] -> [B,C,N]."""
+    B, C, N = x.shape
+    t = x.transpose(1, 2)
+    q = F.linear(t, sd[key + ".to_q.weight"])
+    k, v = F.linear(t, sd[key + ".to_kv.weight"]).chunk(2, dim=-1)
+    q, k, v = (z.reshape(B, N, heads, -1).transpose(1, 2) for z in (q, k, v))
+    attn = (torch.einsum("bhid,bhjd->bhij", q, k) * (q.shape[-1] ** -0.5)).softmax(dim=-1)
+    out = torch.einsum("bhij,bhjd->bhid", attn, v).transpose(1, 2).reshape(B, N, -1)
+    return F.linear(out, sd[key + ".to_out.weight"]).transpose(1, 2)
+
+
 def timestep_embedding(t, dim):
     """unet_pvc.py:156-169."""
     half = dim // 2
@@ -255,6 +268,8 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x, t, x_cond=None, taps
             taps[f"sa{i}"] = feats
     if "global_att.to_qkv.weight" in sd:
         feats = linear_attention(sd, "global_att", feats, plan["heads"])
+    elif "global_att.to_q.weight" in sd:
+        feats = softmax_attention(sd, "global_att", feats, plan["heads"])
     for j, lv in enumerate(plan["fp"]):
         skip, up_coords = skips[-1 - j], coords_list[-1 - j]
         nseq = lv["n_pvconv"] + 1
@@ -377,6 +392,11 @@ def param_shapes(cfg: dict) -> Dict[str, tuple]:
         h = plan["heads"]
         S["global_att.to_qkv.weight"] = (3 * h * 32, cin, 1, 1)
         S["global_att.to_out.weight"] = (cin, h * 32, 1, 1); S["global_att.to_out.bias"] = (cin,)
+    elif str(pvd.get("attention_type")).lower() == "flash":
+        h = plan["heads"]
+        S["global_att.to_q.weight"] = (h * 32, cin)
+        S["global_att.to_kv.weight"] = (2 * h * 32, cin)
+        S["global_att.to_out.weight"] = (cin, h * 32)
     sa_in[0] = fe + ind
     fp_cfg = [((ch[3], ch[3]), ch[3]), ((ch[3], ch[3]), ch[3]), ((ch[3], ch[2]), ch[2]), ((ch[2], ch[2], ch[1]), ch[1])]
     for j, lv in enumerate(plan["fp"]):

@@ -19,14 +19,39 @@
 // Flat element indices are split with 32-bit unsigned divisions (a 64-bit division costs ~10x more ALU work than the
 // 16 bytes each thread moves); every launcher checks that the element count fits.
 // store 4 consecutive channels as fp32 or as IEEE half (round to nearest): the conv operands of the half path
+// Range guard of the IEEE-half operand storage: every value the engine rounds to half is checked against half's largest finite
+// value; a hit is counted here (the engine reads the counter after the graph replay and re-runs the call with fp32 / tf32 operand
+// storage, engine.py).  The reference's arithmetic (fp32 storage, TF32 multiply) has 8 exponent bits, half has 5.
+__device__ unsigned int g_half_overflow = 0;
+__device__ __forceinline__ void half_range_check(float m)
+{
+    if (!(m <= 65504.0f)) atomicAdd(&g_half_overflow, 1u);      // also catches NaN
+}
 __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void store4(__half* p, float4 v)
 {
+    half_range_check(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
     uint2 u;
     u.x = *reinterpret_cast<const unsigned*>(&lo);
     u.y = *reinterpret_cast<const unsigned*>(&hi);
     *reinterpret_cast<uint2*>(p) = u;
+}
+
+// values that did not fit IEEE half since the last reset (0 = the half operand storage was exact-range); synchronises `stream`
+P2PB_API int p2pb_half_overflow_count(int reset, unsigned int* host_count, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned int v = 0;
+    P2PB_CUDA_OK(cudaMemcpyFromSymbolAsync(&v, g_half_overflow, sizeof(v), 0, cudaMemcpyDeviceToHost, s));
+    P2PB_CUDA_OK(cudaStreamSynchronize(s));
+    if (host_count != nullptr) *host_count = v;
+    if (reset && v != 0) {
+        const unsigned int z = 0;
+        P2PB_CUDA_OK(cudaMemcpyToSymbolAsync(g_half_overflow, &z, sizeof(z), 0, cudaMemcpyHostToDevice, s));
+        P2PB_CUDA_OK(cudaStreamSynchronize(s));
+    }
+    return P2PB_OK;
 }
 
 #define P2PB_CHECK_U32(total, what) P2PB_CHECK_ARG((total) < 4294967296LL, what ": %lld elements exceed the 32-bit index range, split the batch", (long long)(total))
@@ -59,6 +84,7 @@ __global__ void coords_to_rows_f16_kernel(const float* __restrict__ coords, __ha
     const int n = (int)(i - b * N);
     const float* c = coords + b * 3 * N;
     __half* o = rows + i * ld + col0;
+    half_range_check(fmaxf(fabsf(c[n]), fmaxf(fabsf(c[n + N]), fabsf(c[n + 2 * N]))));
     o[0] = __float2half_rn(c[n]);
     o[1] = __float2half_rn(c[n + N]);
     o[2] = __float2half_rn(c[n + 2 * N]);
@@ -760,7 +786,9 @@ __global__ void __launch_bounds__(256) group_project_kernel(const float* __restr
                 s1 += v;
                 s2 = fmaf(v, v, s2);
             } else {
-                out[((size_t)warp * 32 + k) * ldo + c] = __float2half_rn(swishf(fmaf(v, a, bb)));
+                const float sv = swishf(fmaf(v, a, bb));
+                half_range_check(fabsf(sv));
+                out[((size_t)warp * 32 + k) * ldo + c] = __float2half_rn(sv);
             }
         }
         if (MODE == 0) *reinterpret_cast<float2*>(stats + ((size_t)warp * C + c) * 2) = make_float2(s1, s2);
@@ -930,6 +958,68 @@ P2PB_API int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N
     if (B == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)attention_small_kernel);
     (void)p2pb_launch(attention_small_kernel, dim3(B * H), dim3(dim3(32, 32)), (size_t)(0), (cudaStream_t)stream, qkv, ldq, H, N, out, ldo);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// attention_softmax_small: scaled dot-product softmax attention on the bottleneck tokens -- modules.Attention (norm=False, no
+// time conditioning, no qk-norm; /root/reference/models/modules.py:197-264) around Attend (:77-162), selected by
+// `attention_type: flash` (unet_pvc.py:98-99, 238-241).  qkv rows [B*N, 3*H*32], channel = qkv*H*32 + head*32 + d (to_q, then the
+// k and v halves of to_kv, each laid out "(h d)").  out[i, :] = softmax_j(q_i . k_j / sqrt(32)) v_j -> rows [B*N, H*32].
+// One CTA (32 x 32 threads) per (sample, head); N <= 64 tokens.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) attention_softmax_small_kernel(const float* __restrict__ qkv, int ldq, int H, int N,
+                                                                       float* __restrict__ out, int ldo)
+{
+    P2PB_PDL_SYNC();
+    __shared__ float sq[64][33], sk[64][33], sv[64][33], ss[64][65];
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 32
+    const float* base = qkv + (size_t)b * N * ldq;
+    for (int n = ty; n < N; n += 32) {
+        sq[n][tx] = base[(size_t)n * ldq + 0 * H * 32 + h * 32 + tx];
+        sk[n][tx] = base[(size_t)n * ldq + 1 * H * 32 + h * 32 + tx];
+        sv[n][tx] = base[(size_t)n * ldq + 2 * H * 32 + h * 32 + tx];
+    }
+    __syncthreads();
+    const float scale = 0.17677669529663687f;      // 32^-0.5 (modules.py:139)
+    for (int i = ty; i < N; i += 32)
+        for (int j = tx; j < N; j += 32) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < 32; ++d) s = fmaf(sq[i][d], sk[j][d], s);
+            ss[i][j] = s * scale;
+        }
+    __syncthreads();
+    for (int i = ty; i < N; i += 32) {             // one warp per row: softmax over j
+        float mx = -INFINITY;
+        for (int j = tx; j < N; j += 32) mx = fmaxf(mx, ss[i][j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = tx; j < N; j += 32) {
+            const float e = expf(ss[i][j] - mx);
+            ss[i][j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = tx; j < N; j += 32) ss[i][j] *= inv;
+    }
+    __syncthreads();
+    for (int i = ty; i < N; i += 32) {             // out[i][d = tx]
+        float s = 0.f;
+        for (int j = 0; j < N; ++j) s = fmaf(ss[i][j], sv[j][tx], s);
+        out[((size_t)b * N + i) * ldo + h * 32 + tx] = s;
+    }
+}
+
+P2PB_API int p2pb_attention_softmax_small(const float* qkv, int ldq, int B, int H, int N, float* out, int ldo, void* stream)
+{
+    P2PB_CHECK_ARG(N > 0 && N <= 64, "attention_softmax_small: N=%d tokens (bottleneck only, <= 64)", N);
+    if (B == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)attention_softmax_small_kernel);
+    (void)p2pb_launch(attention_softmax_small_kernel, dim3(B * H), dim3(dim3(32, 32)), (size_t)(0), (cudaStream_t)stream, qkv, ldq, H, N, out, ldo);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

@@ -96,7 +96,7 @@ class Engine:
     # mantissa -- for the r>=16 voxel convs), fp32 accumulation; everything else fp32
     dtype_name = "tf32"
 
-    def __init__(self, p2pb, net, B: int, N: int, F: int):
+    def __init__(self, p2pb, net, B: int, N: int, F: int, allow_half: bool = True):
         self.p2pb, self.net = p2pb, net
         self.B, self.N, self.F = B, N, F
         self.dev = next(net.parameters()).device
@@ -105,7 +105,9 @@ class Engine:
         assert self.ind == 3
         self.extra = net.extra_feature_channels
         assert F == self.extra, f"x_cond has {F} channels, model expects {self.extra}"
-        self.halo_f16, self.gemm_f16 = halo_f16(), gemm_f16()
+        # allow_half=False: this net produced values outside half's range in an earlier call (Engine._sample) -> fp32 / tf32 storage
+        self.halo_f16, self.gemm_f16 = halo_f16() and allow_half, gemm_f16() and allow_half
+        self.tf32_layers: List[str] = []      # layers whose WEIGHTS do not fit half's range and were packed as fp32 / tf32
         if self.halo_f16 or self.gemm_f16:
             self.dtype_name = "tf32+f16(10-bit mantissa operands), fp32 accumulate"
         self._emd_w: List[torch.Tensor] = []
@@ -127,6 +129,18 @@ class Engine:
     def _w(self, t):
         return t.detach().to(self.dev, torch.float32).contiguous()
 
+    def _half_ok(self, name: str, *ws) -> bool:
+        """IEEE half keeps tf32's 10 mantissa bits but only 5 exponent bits: a weight tensor is stored as half only if its largest
+        magnitude is finite in half (<= 6e4) and well inside the normal range (>= 1e-3: below, a growing share of the values is
+        sub-normal in half and loses relative precision).  Otherwise this layer keeps fp32 storage / kind::tf32 -- the reference's
+        arithmetic -- and is listed in ``tf32_layers``."""
+        for w in ws:
+            m = float(w.detach().abs().max())
+            if not (1e-3 <= m <= 6.0e4):
+                self.tf32_layers.append(f"{name} (max|w| = {m:.3g})")
+                return False
+        return True
+
     def _norm(self, mod, groups=8) -> _AdaGN:
         """AdaGN (norm + emd) or plain GroupNorm / MyGroupNorm."""
         if hasattr(mod, "emd"):
@@ -147,7 +161,7 @@ class Engine:
         return out.contiguous()
 
     # ------------------------------------------------------------------------------------------------ packing
-    def _pack_pvconv(self, mod, c_in: int, temb_in: bool, coords_first: bool):
+    def _pack_pvconv(self, mod, c_in: int, temb_in: bool, coords_first: bool, name: str = "pvconv"):
         """c_in = valid channels of the incoming rows (features[, xyz]); temb_in: 64 time channels follow in the
         reference's channel order.  coords_first: reference input order is [xyz, feats] (level 0) -> ours [feats, xyz]."""
         E = self.E if temb_in else 0
@@ -168,11 +182,12 @@ class Engine:
         P = {"cout": cout, "cin": c_in, "E": E, "cp": cp, "r": int(mod.resolution)}
         halo = int(mod.resolution) >= 16 and cout <= 128 and cout % 32 == 0   # large grid / few channels: conv_halo.cu
         P["halo"] = halo
-        if halo and self.halo_f16:
+        w_ok = (self.halo_f16 or self.gemm_f16) and self._half_ok(name + ".voxel_layers", conv1.weight, conv2.weight)
+        if halo and self.halo_f16 and w_ok:
             P["cp"] = cp = pad64(c_in + E)
             P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
             P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
-        elif not halo and self.gemm_f16 and cout % 32 == 0:
+        elif not halo and self.gemm_f16 and cout % 32 == 0 and w_ok:
             P["cp"] = cp = pad64(c_in + E)
             P["w1"] = dense.pack_conv3d_weight(self._w(conv1.weight), cp, perm_full).half()
             P["w2"] = dense.pack_conv3d_weight(self._w(conv2.weight), pad64(cout)).half()
@@ -196,7 +211,7 @@ class Engine:
         P["np"] = self._norm(pf[1])
         return P
 
-    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None, half_first=False):
+    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None, half_first=False, name: str = "mlp"):
         """SharedMLP -> list of dicts; first layer's columns remapped by first_cols; optional temb fold block.
         With gemm_f16 the layers after the first take IEEE-half operands (their input is a GroupNorm+Swish output written
         by this engine); the first layer too when its input rows are produced as half (half_first: grouped rows)."""
@@ -213,7 +228,7 @@ class Engine:
                 if temb_cols is not None:
                     w = self._w(conv.weight).reshape(o, c)
                     L["w_t"] = w[:, temb_cols[0]:temb_cols[0] + temb_cols[1]].contiguous()
-            elif self.gemm_f16 and o % 32 == 0:
+            elif self.gemm_f16 and o % 32 == 0 and self._half_ok(f"{name}.layers.{i}", conv.weight):
                 L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad64(c)).half()
             else:
                 L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad32(c))
@@ -251,7 +266,8 @@ class Engine:
                 conv, gn = seq[0], seq[1]
                 o, c = conv.weight.shape[:2]
                 L = {"cout": o, "b": self._w(conv.bias), "n": self._norm(gn)}
-                pnet_f16 = self.gemm_f16 and self.N % 128 == 0     # (the column max/min epilogue needs whole 128-row tiles per sample)
+                if j == 0:      # one storage type for the whole chain; (the column max/min epilogue needs whole 128-row tiles per sample)
+                    pnet_f16 = self.gemm_f16 and self.N % 128 == 0 and self._half_ok("global_pnet", *[q[0].weight for q in m])
                 padk = pad64 if pnet_f16 else pad32
                 if j == 2:  # input = cat[point feature (c/2), global max (c/2)]: second half becomes a per-sample bias
                     h = c // 2
@@ -274,17 +290,19 @@ class Engine:
             L = {"pv": [], "skip_c": c_feat}
             c_cur = c_feat
             for k, pv in enumerate(pvs):
-                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=(i > 0 and k == 0), coords_first=(i == 0 and k == 0)))
+                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=(i > 0 and k == 0), coords_first=(i == 0 and k == 0),
+                                                 name=f"sa_layers.{i}.{k}"))
                 c_cur = L["pv"][-1]["cout"]
             temb_sa = (len(pvs) == 0 and i > 0)
             # SA-module MLP: reference grouped input = [rel xyz (3), features (c_cur) (+ temb 64)]; ours [features, rel xyz]
             if i == 0 and len(pvs) == 0:
                 raise NotImplementedError("level 0 without PVConv")
             assert c_cur % 4 == 0
-            sa_half = self.gemm_f16 and sam.mlps[0].layers[0].weight.shape[0] % 32 == 0
+            sa_half = (self.gemm_f16 and sam.mlps[0].layers[0].weight.shape[0] % 32 == 0
+                       and self._half_ok(f"sa_layers.{i}.mlps.0.layers.0", sam.mlps[0].layers[0].weight))
             L["mlp"] = self._pack_mlp(sam.mlps[0].layers, [(3, c_cur, 0), (0, 3, c_cur)],
                                       pad64(c_cur + 3) if sa_half else pad32(c_cur + 3),
-                                      temb_cols=(3 + c_cur, E) if temb_sa else None, half_first=sa_half)
+                                      temb_cols=(3 + c_cur, E) if temb_sa else None, half_first=sa_half, name=f"sa_layers.{i}.mlps.0")
             # gather-after-GEMM form of the first layer (p2pb_group_project): feature part per point, coordinate part in fp32
             conv0 = sam.mlps[0].layers[0]
             o0 = conv0.weight.shape[0]
@@ -305,10 +323,16 @@ class Engine:
         # bottleneck attention
         if net.global_att is not None:
             ga = net.global_att
-            W["att_qkv"] = self._pack_rows_w(ga.to_qkv.weight, [(0, c_feat, 0)], pad32(c_feat))
+            if hasattr(ga, "to_qkv"):          # LinearAttention (modules.py:165-194)
+                W["att_kind"] = "linear"
+                W["att_qkv"] = self._pack_rows_w(ga.to_qkv.weight, [(0, c_feat, 0)], pad32(c_feat))
+                W["att_outb"] = self._w(ga.to_out.bias)
+            else:                              # Attention / Attend (modules.py:197-264, 77-162): [to_q | to_kv] as one GEMM, no biases
+                W["att_kind"] = "softmax"
+                W["att_qkv"] = self._pack_rows_w(torch.cat([ga.to_q.weight, ga.to_kv.weight], 0), [(0, c_feat, 0)], pad32(c_feat))
+                W["att_outb"] = None
             hid = ga.to_out.weight.shape[1]
             W["att_out"] = self._pack_rows_w(ga.to_out.weight, [(0, hid, 0)], pad32(hid))
-            W["att_outb"] = self._w(ga.to_out.bias)
             W["heads"] = ga.heads
         # FP levels
         fp = []
@@ -325,18 +349,19 @@ class Engine:
             else:
                 skip_cols = [(c_low + E, c_skip, c_low)]
             assert c_low % 32 == 0
-            L = {"mlp": self._pack_mlp(fpm.mlp.layers, [(0, c_low, 0)] + skip_cols, c_low + kp_skip, temb_cols=(c_low, E)),
+            L = {"mlp": self._pack_mlp(fpm.mlp.layers, [(0, c_low, 0)] + skip_cols, c_low + kp_skip, temb_cols=(c_low, E),
+                                       name=f"fp_layers.{j}.mlp"),
                  "c_low": c_low, "kp_skip": kp_skip, "lvl": lvl, "pv": []}
             c_cur = L["mlp"][-1]["cout"]
             for pv in pvs:
-                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=False, coords_first=False))
+                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=False, coords_first=False, name=f"fp_layers.{j}.{1 + len(L['pv'])}"))
                 c_cur = L["pv"][-1]["cout"]
             fp.append(L)
             c_low = c_cur
         W["fp"] = fp
         # classifier
         cl = net.classifier
-        W["cls"] = self._pack_mlp(cl[0].layers, [(0, c_low, 0)], pad32(c_low))
+        W["cls"] = self._pack_mlp(cl[0].layers, [(0, c_low, 0)], pad32(c_low), name="classifier.0")
         om = cl[-1].weight.shape[1]
         W["cls_out"] = self.zeros(16, pad32(om))
         W["cls_out"][:3, :om] = self._w(cl[-1].weight).reshape(3, om)
@@ -751,7 +776,7 @@ class Engine:
                  _p(coords[i + 1]), _p(nidx[i]), _p(grp), int(grp.stride(0)), B, n_pts, M, K, _s())
             feats = self.mlp_chain(f"sa{i}.mlp", L["mlp"], [grp], [kg], M * K, temb, final_pool=K)
         main.wait_event(join)       # 3-NN tables and the remaining voxel CSRs (feature propagation)
-        # ---- bottleneck linear attention (modules.py:165-194; no residual)
+        # ---- bottleneck attention, no residual: LinearAttention (modules.py:165-194) or softmax Attention (modules.py:197-264)
         nb = Ns[-1]
         if "att_qkv" in W:
             c = feats.shape[1]
@@ -759,7 +784,8 @@ class Engine:
             dense.gemm_rows([feats], W["att_qkv"], None, out=qkv, ks=[pad32(c)])
             hid = W["att_out"].shape[1]
             att = self.buf("att.ctx", B * nb, hid)
-            call("p2pb_attention_small", _p(qkv), int(qkv.stride(0)), B, W["heads"], nb, _p(att), hid, _s())
+            call("p2pb_attention_small" if W["att_kind"] == "linear" else "p2pb_attention_softmax_small", _p(qkv), int(qkv.stride(0)),
+                 B, W["heads"], nb, _p(att), hid, _s())
             fo = self.buf("att.out", B * nb, c)
             dense.gemm_rows([att], W["att_out"], W["att_outb"], out=fo, ks=[hid])
             feats = fo
@@ -820,13 +846,19 @@ class Engine:
         T = len(pairs)
         log_set = set(log_steps)
         n_log = sum(1 for prev, _ in pairs if prev in log_set)
-        # per-step host tables: sinusoid of the noise level, posterior scalars (fp32, same op order as p_posterior)
+        # per-step host tables: sinusoid of the noise level, posterior scalars (fp32, same op order as p_posterior); computed and
+        # uploaded once per step grid (the tables of one T never change)
         sin = self.buf(f"temb.sin{T}", T, E)       # keyed by T: sample(steps=...) may change between calls
         coef = self.buf(f"coef{T}", T, 3)
-        sin_h = torch.stack([self.time_embedding(float(p.noise_levels[step].item()), None) for _, step in pairs])
-        coef_h = torch.tensor([p.posterior_coefs(prev, step) for prev, step in pairs], dtype=torch.float32)
-        sin.copy_(sin_h)
-        coef.copy_(coef_h.to(self.dev))
+        tkey = tuple(pairs)
+        if getattr(self, "_tables_key", {}).get(T) != tkey:
+            sin_h = torch.stack([self.time_embedding(float(p.noise_levels[step].item()), None) for _, step in pairs])
+            coef_h = torch.tensor([p.posterior_coefs(prev, step) for prev, step in pairs], dtype=torch.float32)
+            sin.copy_(sin_h)
+            coef.copy_(coef_h.to(self.dev))
+            if not hasattr(self, "_tables_key"):
+                self._tables_key = {}
+            self._tables_key[T] = tkey
         self.buf("xt", B, 3, N).copy_(x1.detach().to(self.dev, torch.float32))
         if x_cond is not None:
             self.prepare_cond(x_cond.detach().to(self.dev, torch.float32))
@@ -868,6 +900,15 @@ class Engine:
         x0s = torch.flip(x0_buf.permute(1, 0, 2, 3), dims=(1,)).clone()
         return xs, x0s
 
+    def half_overflows(self) -> int:
+        """Values that did not fit IEEE half in any half-producing kernel since the last query (0 unless an activation
+        exceeded 65504); waits for the current stream."""
+        if not (self.halo_f16 or self.gemm_f16):
+            return 0
+        n = ctypes.c_uint(0)
+        call("p2pb_half_overflow_count", 1, ctypes.byref(n), _s())
+        return int(n.value)
+
 
 class DualEngine:
     """n (default 2) part-batch engines whose T-step loops run as INDEPENDENT chains on separate streams inside one CUDA graph.
@@ -878,16 +919,20 @@ class DualEngine:
     are persistent one-CTA-per-SM kernels that cannot overlap each other.  With several chains the small kernels of one
     part run in the shadow of another part's convolutions / GEMMs."""
 
-    def __init__(self, p2pb, net, B: int, N: int, F: int, n_chains: int = 2):
+    def __init__(self, p2pb, net, B: int, N: int, F: int, n_chains: int = 2, allow_half: bool = True):
         assert B % n_chains == 0
         self.B, self.N, self.F, self.n = B, N, F, n_chains
         self.part = B // n_chains
-        self.halves = [Engine(p2pb, net, self.part, N, F) for _ in range(n_chains)]
+        self.halves = [Engine(p2pb, net, self.part, N, F, allow_half) for _ in range(n_chains)]
+        self.tf32_layers = self.halves[0].tf32_layers
         self.dev = self.halves[0].dev
         self.dtype_name = self.halves[0].dtype_name
         self._graphs: Dict[tuple, tuple] = {}
         self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_chains - 1)]
         self.kernels_per_sample = 0
+
+    def half_overflows(self) -> int:
+        return self.halves[0].half_overflows()
 
     def _run_all(self, pairs, prep, clip):
         """Fork: chain 0 on the current stream, the others on their own streams; join."""
@@ -932,7 +977,7 @@ class DualEngine:
         return xs, x0s
 
 
-def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False):
+def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False, allow_half: bool = True):
     """Engine for (net, B, N, F), built once.  allow_dual (the sampling loop): with P2PB_CHAINS=n the batch is split into n
     independent part-batch chains (DualEngine).  Default 1: measured on B200 (PVDS) one chain 366 patches/s, two chains 361
     at 64 patches, 390 vs 384 at 128 -- since the small kernels were rewritten, batch efficiency of the big kernels
@@ -946,7 +991,8 @@ def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False):
     # the packed weights are a snapshot: key them by the parameters' in-place version counters, so that a
     # load_state_dict / optimizer step after the first sample() rebuilds the engine instead of running stale weights
     version = sum(int(p._version) for p in net.parameters()) + sum(int(b._version) for b in net.buffers())
-    key = (id(net), B, N, F, n if dual else 1)
+    allow_half = allow_half and id(net) not in getattr(p2pb, "_no_half", ())
+    key = (id(net), B, N, F, n if dual else 1, allow_half)
     entry = p2pb._engines.get(key)
     if entry is not None and entry[0] != version:
         for k in [k for k in p2pb._engines if k[0] == id(net)]:
@@ -955,7 +1001,7 @@ def get_engine(p2pb, net, x_shape, cond_shape, allow_dual: bool = False):
     if entry is None:
         dev = next(net.parameters()).device
         with torch.cuda.device(dev):
-            eng = DualEngine(p2pb, net, B, N, F, n) if dual else Engine(p2pb, net, B, N, F)
+            eng = DualEngine(p2pb, net, B, N, F, n, allow_half) if dual else Engine(p2pb, net, B, N, F, allow_half)
         entry = (version, eng)
         p2pb._engines[key] = entry
     eng = entry[1]

@@ -176,6 +176,21 @@ class P2PB(nn.Module):
 
             eng = get_engine(self, net, x1.shape, None if x_cond is None else x_cond.shape, allow_dual=True)
             xs, x0s = eng.sample(x1, x_cond, pairs, log_steps, clip_denoise)
+            n_over = eng.half_overflows()
+            if n_over:
+                # an activation left IEEE half's range (|x| > 65504; the reference's fp32 storage / TF32 multiply has 8 exponent
+                # bits): this net runs with fp32 / tf32 operand storage from now on, and this call is repeated that way
+                import warnings
+
+                warnings.warn(f"p2pb_b200: {n_over} activation values exceeded the IEEE-half range; switching this model to "
+                              "fp32/tf32 operand storage and re-running the call")
+                if not hasattr(self, "_no_half"):
+                    self._no_half = set()
+                self._no_half.add(id(net))
+                for k in [k for k in self._engines if k[0] == id(net)]:
+                    del self._engines[k]
+                eng = get_engine(self, net, x1.shape, None if x_cond is None else x_cond.shape, allow_dual=True)
+                xs, x0s = eng.sample(x1, x_cond, pairs, log_steps, clip_denoise)
         elif backend == "eager":
             # VALIDATION path (tests/, tools/): PVCNN2Unet.forward step by step with this repo's point/voxel ops and torch
             # library layers for the dense parts -- what the reference looks like with only its op extension swapped.  It is

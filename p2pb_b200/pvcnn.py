@@ -91,6 +91,31 @@ class LinearAttention(nn.Module):
         return self.to_out(out.unsqueeze(-1)).squeeze(-1)
 
 
+class Attention(nn.Module):
+    """Softmax attention over the bottleneck tokens, the reference's ``attention_type: flash`` (modules.py:197-264 with norm=False,
+    no time conditioning, no qk-norm, as unet_pvc.py:98-99 builds it; core = Attend, modules.py:77-162): parameters
+    ``to_q [h*32, dim]``, ``to_kv [2*h*32, dim]``, ``to_out [dim, h*32]``, all bias-free Linears.  Takes / returns ``[B, C, N]``
+    (the transposes of unet_pvc.py:239-241 are folded in)."""
+
+    def __init__(self, dim: int, heads: int = 4, dim_head: int = 32, **_unused):
+        super().__init__()
+        self.heads = heads
+        hidden = dim_head * heads
+        self.to_q = nn.Linear(dim, hidden, bias=False)
+        self.to_kv = nn.Linear(dim, hidden * 2, bias=False)
+        self.to_out = nn.Linear(hidden, dim, bias=False)
+
+    def forward(self, x):
+        B, C, N = x.shape
+        t = x.transpose(1, 2)                                                   # [B, N, C] tokens
+        q = self.to_q(t)
+        k, v = self.to_kv(t).chunk(2, dim=-1)
+        q, k, v = (z.view(B, N, self.heads, -1).transpose(1, 2) for z in (q, k, v))      # [B, h, N, d]
+        attn = (torch.einsum("bhid,bhjd->bhij", q, k) * (q.shape[-1] ** -0.5)).softmax(dim=-1)
+        out = torch.einsum("bhij,bhjd->bhid", attn, v).transpose(1, 2).reshape(B, N, -1)
+        return self.to_out(out).transpose(1, 2)
+
+
 def _norm(num_channels: int, dim: int, gn_groups: int, cond_dim: int, affine: bool = True):
     if cond_dim > 0:
         return AdaGN(num_channels, cond_dim, dim, gn_groups)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .pvcnn import (LinearAttention, Pnet2Stage, PVCData, SharedMLP, Swish, create_fp_components,
+from .pvcnn import (Attention, LinearAttention, Pnet2Stage, PVCData, SharedMLP, Swish, create_fp_components,
                     create_mlp_components, create_pvc_layer_params, create_sa_components)
 
 
@@ -50,7 +50,7 @@ class PVCNN2Unet(nn.Module):
         if str(attn_type).lower() == "linear":
             attention_fn = partial(LinearAttention, heads=pvd.attention_heads)
         elif str(attn_type).lower() == "flash":
-            raise NotImplementedError("attention_type=flash is not used by any shipped config (SURVEY.md §8 a18)")
+            attention_fn = partial(Attention, heads=pvd.attention_heads)        # unet_pvc.py:98-99 (norm=False, flash=True)
         else:
             attention_fn = None
         with_se = pvd.get("use_se", True)

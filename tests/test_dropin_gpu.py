@@ -74,9 +74,11 @@ def test_reference_model_code_runs_on_the_op_shim_pvds(golden_dir, ref_classes):
 
 
 def test_reference_sampling_loop_runs_on_the_op_shim_pvdl(golden_dir, ref_classes):
-    """PVDL at N = 8192: the reference's own ``P2PB.sample`` (T = 5, its Python loop, its modules) over the shim, against the
-    R-GPU chain -- teacher-forcing is not needed for the first logged state, and the final state is compared set-wise."""
-    from p2pb_b200 import ops
+    """PVDL at N = 8192: the reference's own ``P2PB.sample`` (its Python loop, its modules) over the shim.  The first step of the
+    free-running loop and every teacher-forced step of the T = 5 chain must reproduce the R-GPU chain at the fp32 rounding
+    level (measured 3e-7); the free-running END state of an un-damped random-weight model is chaotic for the reference itself
+    (profiles/r02_rgpu_report.json), so it is only required to be a valid result here."""
+    from oracle import model as OM
 
     RI, ref, classes = ref_classes
     z = np.load(os.path.join(golden_dir, "rgpu_golden.npz"))
@@ -84,9 +86,20 @@ def test_reference_sampling_loop_runs_on_the_op_shim_pvdl(golden_dir, ref_classe
     x = torch.from_numpy(z["pvdl8192_x_start"]).cuda()
     out = model.sample(x_start=x, steps=5, log_count=5, verbose=False, use_ema=False)
     chain = torch.from_numpy(z["pvdl8192_x_chain"]).cuda()
-    assert out["x_chain"].shape == chain.shape
+    assert out["x_chain"].shape == chain.shape and torch.isfinite(out["x_pred"]).all()
     first = (out["x_chain"][:, -1] - chain[:, -1]).abs()          # state after the first of the 5 steps
-    cd = ops.calculate_cd(out["x_pred"], chain[:, 0])
-    print(f"first step: mean|err|={first.mean():.3e} max|err|={first.max():.3e}; T=5 un-damped chamfer vs R-GPU: {max(cd):.3e}")
-    assert first.mean().item() <= 1e-5 and first.max().item() <= 5e-3
-    assert max(cd) <= 1e-4
+    print(f"free-running first step: mean|err|={first.mean():.3e} max|err|={first.max():.3e}")
+    assert first.max().item() <= 1e-5
+    model.model.eval()                                            # ddpm_sampling leaves the net in train mode (p2pb.py:333)
+    T = 5
+    rev = OM.space_indices(1000, T + 1)[::-1]
+    worst = 0.0
+    for s, (prev, step) in enumerate(zip(rev[1:], rev[:-1])):
+        before = x if s == 0 else chain[:, T - s]
+        st = torch.full((before.shape[0],), step, device="cuda", dtype=torch.long)
+        with torch.no_grad():
+            eps = model.model(before, model.noise_levels[st])
+        got = model.p_posterior(prev, step, before, model.compute_pred_x0_from_eps(st, before, eps, False))
+        worst = max(worst, (got - chain[:, T - 1 - s]).abs().max().item())
+    print(f"teacher-forced, 5 steps: worst max|err| = {worst:.3e}")
+    assert worst <= 1e-5

@@ -24,7 +24,7 @@ def _golden(golden_dir, name):
     return z, cfg
 
 
-@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino"])
+@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino", "pvds_flash", "pvdl_flash"])
 def test_engine_single_evaluation_vs_reference_golden(golden_dir, name):
     from p2pb_b200.engine import get_engine
 
@@ -328,50 +328,6 @@ def test_dual_chain_engine_equals_single_chain(monkeypatch):
     assert torch.equal(out_dual, out_single), (out_dual - out_single).abs().max()
 
 
-def test_denoise_room_entry_point_end_to_end(tmp_path):
-    """denoise_room.py CLI on a synthetic 30k-point room (noisy box walls, metres) with a seeded PVDL checkpoint
-    (data.npoints = 2048): device FPS centres + device radius query + pad / FPS-to-npoints patches -> batched sampling ->
-    reassembly -> .ply.  Patches larger than npoints are FPS-subsampled, so only part of the room is touched (the
-    reference behaves the same, denoise_room.py:400-419); touched points must move only a little."""
-    import yaml as _yaml
-
-    import denoise_room as D
-    from p2pb_b200.config import load_yaml
-    from p2pb_b200.io_ply import read_ply, write_ply
-    from p2pb_b200.model_loader import save_checkpoint, seeded_state_dict
-    from p2pb_b200.p2pb import P2PB
-    from p2pb_b200.unet_pvc import PVCNN2Unet
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cfg = load_yaml(os.path.join(root, "p2pb_b200", "configs", "PVDL_SNPP.yaml"))
-    d = cfg.to_dict()
-    d["data"]["npoints"] = 2048
-    d["model"]["extra_feature_channels"] = 0
-    d["model"]["ema"] = False
-    (tmp_path / "opt.yaml").write_text(_yaml.safe_dump(d))
-    cfg = load_yaml(str(tmp_path / "opt.yaml"))
-    cfg.gpu = "cpu"
-    net = PVCNN2Unet(cfg)
-    net.load_state_dict(seeded_state_dict(net, 0, head_scale=0.02))
-    save_checkpoint(str(tmp_path / "step_0.pth"), P2PB(cfg, net), step=0)
-    rng = np.random.default_rng(0)
-    n = 30000
-    pts = rng.uniform([0, 0, 0], [3.0, 2.0, 1.5], size=(n, 3))
-    face = rng.integers(0, 3, n)
-    pts[np.arange(n), face] = np.where(rng.random(n) < 0.5, 0.0, np.array([3.0, 2.0, 1.5])[face])   # snap to a wall
-    pts = (pts + rng.normal(0, 0.005, pts.shape)).astype(np.float32)
-    (tmp_path / "scans").mkdir()
-    room = tmp_path / "scans" / "room.ply"
-    write_ply(str(room), pts, (rng.random((n, 3)) * 255).astype(np.uint8))
-    out_path = tmp_path / "out.ply"
-    D.main(["--room_path", str(room), "--model_path", str(tmp_path / "step_0.pth"), "--out_path", str(out_path), "--steps", "2",
-            "--batch_size", "8", "--k", "2", "--use_ema", ""])
-    out, _ = read_ply(str(out_path))
-    assert out.shape == pts.shape and np.isfinite(out).all()
-    moved = np.linalg.norm(out - pts, axis=1)
-    assert moved.max() < 0.2 and 0.25 < (moved > 0).mean() <= 1.0, (moved.max(), (moved > 0).mean())
-
-
 def test_engine_tf32_operand_path_still_matches_golden(golden_dir, monkeypatch):
     """engine.OPTIONS.halo_f16 = gemm_f16 = False: every contraction with fp32-stored (tf32) operands -- the path the IEEE-half
     operand storage replaced -- stays available and inside the same tolerance.  Measured on B200 vs the fp32 golden:
@@ -434,3 +390,75 @@ def test_engine_refuses_configs_it_does_not_implement():
     x = patch_input(1, 1024, seed=3).cuda()
     with pytest.raises(NotImplementedError, match="ot_ode"):
         model.sample(x_start=x, steps=2, log_count=1, verbose=False)
+
+
+def _scaled_case(scale_keys, factor):
+    """PVDS, 1 x 1024 points, one seeded checkpoint with some tensors scaled by `factor`; engine vs the CPU oracle on the SAME
+    weights, T = 2 free-running (damped head)."""
+    from oracle import model as OM
+    from oracle import ops as OO
+    from p2pb_b200.config import Config
+    from p2pb_b200.p2pb import P2PB
+    from p2pb_b200.unet_pvc import PVCNN2Unet
+
+    cfg_dict = load_cfg("PVDS_PUNet")
+    sd = OM.make_state_dict(cfg_dict, seed=0, head_scale=0.02)
+    for k in scale_keys:
+        sd[k] = sd[k] * factor
+    cfg = Config.wrap(cfg_dict)
+    cfg.gpu = "cuda:0"
+    cfg.model.ema = False
+    net = PVCNN2Unet(cfg)
+    net.load_state_dict(sd, strict=True)
+    model = P2PB(cfg, net.cuda()).eval()
+    x = patch_input(1, 1024, seed=2)
+    ref = OM.sample(sd, cfg_dict, x, None, steps=2, log_count=2)["x_pred"]
+    return model, x.cuda(), ref, OO
+
+
+def test_half_operand_guard_weights_outside_half_range_fall_back_per_layer():
+    """A checkpoint whose first voxel convolution has weights of magnitude 3e5 (> 65504, the largest finite IEEE half): stored as
+    half they would be +-inf.  The engine must keep THAT layer in fp32 / tf32 storage (the reference's arithmetic), say so, and
+    still match the oracle; every other layer keeps half operands."""
+    from p2pb_b200 import ops
+
+    keys = ["sa_layers.0.0.voxel_layers.0.weight", "sa_layers.0.0.voxel_layers.0.bias"]
+    model, x, ref, _ = _scaled_case(keys, 1e7)
+    out = model.sample(x_start=x, steps=2, log_count=2, verbose=False)["x_pred"]
+    eng = model.last_engine
+    assert any("sa_layers.0.0.voxel_layers" in t for t in eng.tf32_layers), eng.tf32_layers
+    assert len(eng.tf32_layers) == 1 and eng.halo_f16 and eng.gemm_f16
+    assert torch.isfinite(out).all()
+    cd = ops.calculate_cd(out, ref.cuda())
+    d = (out.cpu() - ref).abs()
+    print(f"weights x1e7 in one conv: tf32 layers = {eng.tf32_layers}; chamfer vs oracle {max(cd):.2e}, mean|diff| {d.mean():.2e}")
+    assert max(cd) < 1e-5 and d.mean().item() < 1e-3
+    # tiny weights (sub-normal in half) fall back too
+    model2, x2, ref2, _ = _scaled_case(["fp_layers.3.1.voxel_layers.4.weight"], 1e-5)
+    out2 = model2.sample(x_start=x2, steps=2, log_count=2, verbose=False)["x_pred"]
+    assert any("fp_layers.3.1.voxel_layers" in t for t in model2.last_engine.tf32_layers)
+    assert max(ops.calculate_cd(out2, ref2.cuda())) < 1e-5
+
+
+def test_half_operand_guard_activation_overflow_switches_to_tf32_storage():
+    """GroupNorm gains of 1e6 make the activations between the two voxel convolutions ~1e6: they do not fit half.  The
+    half-producing kernels count the overflow, P2PB.sample warns, rebuilds the engine with fp32 / tf32 storage and repeats the
+    call; the result matches the oracle and later calls stay on the safe path."""
+    from p2pb_b200 import ops
+
+    model, x, ref, _ = _scaled_case(["sa_layers.0.0.voxel_layers.1.norm.weight"], 1e6)
+    with pytest.warns(UserWarning, match="IEEE-half range"):
+        out = model.sample(x_start=x, steps=2, log_count=2, verbose=False)["x_pred"]
+    eng = model.last_engine
+    assert not eng.halo_f16 and not eng.gemm_f16
+    assert torch.isfinite(out).all()
+    cd = ops.calculate_cd(out, ref.cuda())
+    d = (out.cpu() - ref).abs()
+    print(f"activations ~1e6: chamfer vs oracle {max(cd):.2e}, mean|diff| {d.mean():.2e}")
+    assert max(cd) < 1e-5 and d.mean().item() < 1e-3
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        out2 = model.sample(x_start=x, steps=2, log_count=2, verbose=False)["x_pred"]
+    assert torch.equal(out, out2)

@@ -38,7 +38,7 @@ def _fp32_dense():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino"])
+@pytest.mark.parametrize("name", ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino", "pvds_flash", "pvdl_flash"])
 def test_eager_forward_matches_reference_golden(golden_dir, name):
     """One network evaluation of the eager path (our CUDA ops + torch fp32 dense) vs the reference's real model."""
     z = np.load(os.path.join(golden_dir, f"model_{name}.npz"))

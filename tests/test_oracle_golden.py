@@ -15,7 +15,7 @@ from oracle import model as OM
 from oracle import ops as OO
 from tests.helpers import load_cfg
 
-CASES = ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino", "pvds_cfg1_damped"]
+CASES = ["pvds_cfg1", "pvds_b2", "pvdl_xyz", "pvdl_rgb", "pvdl_dino", "pvds_cfg1_damped", "pvds_flash", "pvdl_flash"]
 
 
 def _case(golden_dir, name):
