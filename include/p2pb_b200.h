@@ -19,8 +19,9 @@ extern "C" {
 
 const char* p2pb_last_error(void);
 int p2pb_abi_version(void);
-/* development aid for tools/: bit 0 = rows-GEMM epilogue skips its global stores (timing experiments only) */
-int p2pb_debug_set(int flags);
+/* development aid for tests/ and tools/: CTA grouping of the persistent GEMM for big shapes: 0 = cta_group::2 pairs (default),
+ * 4 = 2-CTA multicast clusters, 32 = independent CTAs; results are identical */
+int p2pb_gemm_tune(int mode);
 int p2pb_device_sm_count(void);
 /* programmatic dependent launch (griddepcontrol.wait, implicit trigger) between the hot-path kernels; default 1 */
 int p2pb_set_pdl(int on);
@@ -225,6 +226,19 @@ int p2pb_interp_rows(const float* f, int ldf, const int* idx, const float* w, fl
 int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw, const float* bias, int B, int K, int O, int act,
                       float* out, int ldo, void* stream);
 
+/* one launch per sampling step for everything that depends only on the time embedding: temb = embedf(sinusoid)
+ * (/root/reference/models/unet_pvc.py:52-56) and every `W[:, time columns] @ temb` fold of a cat[features, time_emb] in front of a 1x1
+ * conv.  Wall [R,E] = the stacked fold weights; stacked row r writes ((float*)row_ptr[r])[b * row_stride[r]] */
+int p2pb_step_vectors(const float* sin, int ld_sin, const float* w0, const float* b0, const float* w2, const float* b2, int B, int E,
+                      const float* Wall, int R, const long long* row_ptr, const int* row_stride, float* temb_out, void* stream);
+/* SE gate of a PVConv: sigmoid(W2 relu(W0 ymean)) (/root/reference/models/modules.py:362-378), one launch */
+int p2pb_se_excite(const float* ymean, const float* w0, const float* w2, int B, int C, int Hd, float* se, void* stream);
+/* classifier tail + bridge update in one pass: Swish(GN(raw)) -> 3 x C projection (fp32) -> p2pb_bridge_update arithmetic
+ * (/root/reference/models/unet_pvc.py:147-154,263-267 + p2pb.py:155-165,190-213); xt == NULL: eps only */
+int p2pb_head_bridge(const float* raw, int ldr, const float* A, const float* Bc, const float* W, const float* bias, int B, int C, int N,
+                     const float* xt, const float* coef, int clip, float* xt_next, float* pred_x0, float* eps_out, int lde,
+                     void* stream);
+
 /* LinearAttention core on the bottleneck tokens (/root/reference/models/modules.py:186-192) */
 int p2pb_attention_small(const float* qkv, int ldq, int B, int H, int N, float* out, int ldo, void* stream);
 
@@ -236,6 +250,13 @@ int p2pb_attention_softmax_small(const float* qkv, int ldq, int B, int H, int N,
  * coef = device pointer to {std_fwd[n], mu_x0, mu_xn} */
 int p2pb_bridge_update(const float* xt, const float* eps, int lde, const float* coef, int clip, float* xt_next,
                        float* pred_x0, int B, int N, void* stream);
+
+/* replaces pytorch3d._C.point_face_dist_forward + face_point_dist_forward as used by /root/reference/metrics/p2m.py:307-375
+ * (point_mesh_face_distance_custom) for the P2M / P2F metrics: pts [P,3], tris [T,3,3] -> squared distances point_dist [P] (point to
+ * closest triangle), face_dist [T] (triangle to closest point).  min_triangle_area: /root/reference/metrics/p2m.py:20 (5e-3).
+ * pytorch3d is un-vendored: parity unpinned, published algorithm restated (csrc/metrics.cu) */
+int p2pb_point_face_dist(const float* pts, int P, const float* tris, int T, float min_triangle_area, float* point_dist,
+                         float* face_dist, void* stream);
 
 /* ---- room sweep: device-side patch creation and reassembly (/root/reference/denoise_room.py) ---------------------------------
  * All work on the radius-query CSR of the room: room [N,3] fp32 row-major, off int64 [P+1], csr int32 [off[P]] (p2pb_radius_fill). */

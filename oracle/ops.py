@@ -204,6 +204,17 @@ def radius_query(centers, points, radius):
     return offsets, indices
 
 
+def point_face_dist(pts, tris, min_triangle_area=5e-3):
+    """pytorch3d point_face / face_point squared distances restated (metrics/p2m.py:307-375; PARITY UNPINNED, see p2pb_oracle.c):
+    pts [P,3], tris [T,3,3] -> (point_dist [P], face_dist [T])."""
+    pts = pts.contiguous().float()
+    tris = tris.contiguous().float()
+    P, T = pts.shape[0], tris.shape[0]
+    pd, fd = torch.empty((P,), dtype=torch.float32), torch.empty((T,), dtype=torch.float32)
+    lib().ora_point_face_dist(_f(pts), P, _f(tris), T, ctypes.c_float(min_triangle_area), _f(pd), _f(fd))
+    return pd, fd
+
+
 _BACKWARD = ["avg_voxelize_backward", "trilinear_devoxelize_backward", "three_nearest_neighbors_interpolate_backward",
              "grouping_backward", "gather_features_backward"]
 

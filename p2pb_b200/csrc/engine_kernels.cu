@@ -908,6 +908,188 @@ P2PB_API int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// step_vectors: everything of one sampling step that depends only on the time embedding, in ONE launch:
+//   temb = Linear(LeakyReLU_0.1(Linear(sinusoid)))                                   (embedf, unet_pvc.py:52-56)
+//   fold_i = W_i[:, time columns] @ temb  for every layer whose input is cat[features, time_emb] in front of a 1x1 conv
+//            (PVConv point branch, SA-module MLP, FP-module first Conv1d: the 64 constant channels are a per-sample bias)
+// All fold weights are stacked in Wall [R, E]; row r of the stack writes to  row_ptr[r] + b * row_stride[r]  (each fold keeps
+// its own dense [B, cout] buffer, the GEMM epilogue's bias2 operand).  Replaces 2 + (number of folds) linear_small launches.
+// grid (ceil(R / 64), B): every CTA recomputes the 2-layer MLP of its sample (8K FMAs) and produces 64 stacked rows.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_vectors_kernel(const float* __restrict__ sin, int ld_sin, const float* __restrict__ w0,
+                                                           const float* __restrict__ b0, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, int E, const float* __restrict__ Wall, int R,
+                                                           const long long* __restrict__ row_ptr, const int* __restrict__ row_stride,
+                                                           float* __restrict__ temb_out)
+{
+    P2PB_PDL_SYNC();
+    __shared__ float s_in[128], s_h[128], s_t[128];
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int k = t; k < E; k += 256) s_in[k] = sin[(size_t)b * ld_sin + k];
+    __syncthreads();
+    for (int o = warp; o < E; o += 8) {
+        float s = 0.f;
+        for (int k = lane; k < E; k += 32) s = fmaf(s_in[k], __ldg(w0 + (size_t)o * E + k), s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            s += b0[o];
+            s_h[o] = s > 0.f ? s : 0.1f * s;
+        }
+    }
+    __syncthreads();
+    for (int o = warp; o < E; o += 8) {
+        float s = 0.f;
+        for (int k = lane; k < E; k += 32) s = fmaf(s_h[k], __ldg(w2 + (size_t)o * E + k), s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            s += b2[o];
+            s_t[o] = s;
+            if (blockIdx.x == 0) temb_out[(size_t)b * E + o] = s;
+        }
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * 64 + warp * 8;
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        if (r >= R) break;
+        float s = 0.f;
+        for (int k = lane; k < E; k += 32) s = fmaf(s_t[k], __ldg(Wall + (size_t)r * E + k), s);
+        s = warp_sum(s);
+        if (lane == 0) reinterpret_cast<float*>(row_ptr[r])[(size_t)b * row_stride[r]] = s;
+    }
+}
+
+P2PB_API int p2pb_step_vectors(const float* sin, int ld_sin, const float* w0, const float* b0, const float* w2, const float* b2, int B,
+                               int E, const float* Wall, int R, const long long* row_ptr, const int* row_stride, float* temb_out,
+                               void* stream)
+{
+    P2PB_CHECK_ARG(B > 0 && E > 0 && E <= 128 && R >= 0, "step_vectors: bad sizes B=%d E=%d R=%d (E <= 128)", B, E, R);
+    p2pb_prefer_max_smem((const void*)step_vectors_kernel);
+    const int gx = R > 0 ? p2pb_cdiv(R, 64) : 1;
+    (void)p2pb_launch(step_vectors_kernel, dim3(gx, B), dim3(256), (size_t)(0), (cudaStream_t)stream, sin, ld_sin, w0, b0, w2, b2, E, Wall, R,
+                      row_ptr, row_stride, temb_out);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// se_excite: squeeze-excitation gate of a PVConv (modules.py:362-378) from the per-sample channel means the GroupNorm
+// coefficient kernel already produced: se = sigmoid(W2 @ relu(W0 @ ymean)).  One CTA per sample (both Linears, bias-free).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ ym, const float* __restrict__ w0,
+                                                        const float* __restrict__ w2, int C, int Hd, float* __restrict__ se)
+{
+    P2PB_PDL_SYNC();
+    extern __shared__ float s_se[];       // [C] means, [Hd] hidden
+    float* s_m = s_se;
+    float* s_hid = s_se + C;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int k = t; k < C; k += 256) s_m[k] = ym[(size_t)b * C + k];
+    __syncthreads();
+    for (int o = warp; o < Hd; o += 8) {
+        float s = 0.f;
+        for (int k = lane; k < C; k += 32) s = fmaf(s_m[k], __ldg(w0 + (size_t)o * C + k), s);
+        s = warp_sum(s);
+        if (lane == 0) s_hid[o] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int o = warp; o < C; o += 8) {
+        float s = 0.f;
+        for (int k = lane; k < Hd; k += 32) s = fmaf(s_hid[k], __ldg(w2 + (size_t)o * Hd + k), s);
+        s = warp_sum(s);
+        if (lane == 0) se[(size_t)b * C + o] = 1.0f / (1.0f + __expf(-s));
+    }
+}
+
+P2PB_API int p2pb_se_excite(const float* ymean, const float* w0, const float* w2, int B, int C, int Hd, float* se, void* stream)
+{
+    P2PB_CHECK_ARG(B >= 0 && C > 0 && Hd > 0 && (C + Hd) * 4 <= 48 * 1024, "se_excite: bad sizes C=%d hidden=%d", C, Hd);
+    if (B == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)se_excite_kernel);
+    (void)p2pb_launch(se_excite_kernel, dim3(B), dim3(256), (size_t)((C + Hd) * sizeof(float)), (cudaStream_t)stream, ymean, w0, w2, C, Hd, se);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// head_bridge: the end of one sampling step in one pass over the classifier's hidden rows:
+//   h = Swish(GroupNorm(raw))  (coefficients A, Bc from gn_coef)  ->  eps = W[3, C] h + bias   (classifier, unet_pvc.py:147-154,
+//   263-267; Dropout is the identity in eval)  ->  pred_x0 = xt - std*eps ; (clip) ; xt <- mu_x0*pred_x0 + mu_xn*xt
+//   (p2pb.py:155-165, 190-213, same operation order as the reference; scalars from the device table `coef`).
+// The [B*N, C] activation is never written, the 128 -> 3 projection runs in fp32 FMAs (the reference's Conv1d is TF32).
+// One warp per point: lanes stride the channels (coalesced 128-byte reads), three shuffle reductions.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_bridge_kernel(const float* __restrict__ raw, int ldr, const float* __restrict__ A,
+                                                          const float* __restrict__ Bc, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, int C, int N, long long total,
+                                                          const float* __restrict__ xt, const float* __restrict__ coef, int clip,
+                                                          float* __restrict__ xt_next, float* __restrict__ pred_x0,
+                                                          float* __restrict__ eps_out, int lde)
+{
+    P2PB_PDL_SYNC();
+    const long long pt = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= total) return;
+    const long long b = pt / N;
+    const int n = (int)(pt - b * N);
+    const float* x = raw + pt * ldr;
+    const float* a = A + b * C;
+    const float* bb = Bc + b * C;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + c);
+        const float4 av = __ldg(reinterpret_cast<const float4*>(a + c)), bv = __ldg(reinterpret_cast<const float4*>(bb + c));
+        const float h0 = swishf(fmaf(xv.x, av.x, bv.x)), h1 = swishf(fmaf(xv.y, av.y, bv.y));
+        const float h2 = swishf(fmaf(xv.z, av.z, bv.z)), h3 = swishf(fmaf(xv.w, av.w, bv.w));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + c)), w1 = __ldg(reinterpret_cast<const float4*>(W + C + c));
+        const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + 2 * C + c));
+        e0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, e0))));
+        e1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, e1))));
+        e2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, e2))));
+    }
+    e0 = warp_sum(e0);
+    e1 = warp_sum(e1);
+    e2 = warp_sum(e2);
+    if (lane == 0) {
+        const float ev[3] = {e0 + bias[0], e1 + bias[1], e2 + bias[2]};
+        if (eps_out != nullptr) {
+            eps_out[pt * lde] = ev[0];
+            eps_out[pt * lde + 1] = ev[1];
+            eps_out[pt * lde + 2] = ev[2];
+        }
+        if (xt != nullptr) {
+            const float std_n = coef[0], mu_x0 = coef[1], mu_xn = coef[2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const size_t o = ((size_t)b * 3 + k) * N + n;
+                const float xv = xt[o];
+                float p0 = __fsub_rn(xv, __fmul_rn(std_n, ev[k]));
+                if (clip) p0 = fminf(fmaxf(p0, -3.0f), 3.0f);
+                if (pred_x0 != nullptr) pred_x0[o] = p0;
+                xt_next[o] = __fadd_rn(__fmul_rn(mu_x0, p0), __fmul_rn(mu_xn, xv));
+            }
+        }
+    }
+}
+
+// raw [B*N, ldr] (pre-norm classifier hidden rows), A / Bc [B, C], W [3, C], bias [3]; xt [B,3,N] (null: eps only), coef = device
+// {std_fwd[n], mu_x0, mu_xn}; xt_next may alias xt; pred_x0 / eps_out (rows [B*N, lde], columns 0..2) optional
+P2PB_API int p2pb_head_bridge(const float* raw, int ldr, const float* A, const float* Bc, const float* W, const float* bias, int B, int C,
+                              int N, const float* xt, const float* coef, int clip, float* xt_next, float* pred_x0, float* eps_out,
+                              int lde, void* stream)
+{
+    P2PB_CHECK_ARG(B >= 0 && N > 0 && C > 0 && C % 4 == 0 && ldr % 4 == 0 && ldr >= C, "head_bridge: bad sizes C=%d ldr=%d", C, ldr);
+    P2PB_CHECK_ARG(xt != nullptr || eps_out != nullptr, "head_bridge: no output requested");
+    const long long total = (long long)B * N;
+    if (total == 0) return P2PB_OK;
+    p2pb_prefer_max_smem((const void*)head_bridge_kernel);
+    (void)p2pb_launch(head_bridge_kernel, dim3(p2pb_cdiv(total * 32, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, raw, ldr, A, Bc, W, bias,
+                      C, N, total, xt, coef, clip, xt_next, pred_x0, eps_out, lde);
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // attention_small: LinearAttention core (modules.py:186-192) on the bottleneck tokens.  qkv rows [B*N, 3*H*32] with
 // channel = qkv*H*32 + head*32 + d.  k <- softmax over the N tokens; ctx[d,e] = sum_n k[d,n] v[e,n];
 // out[e,n] = sum_d ctx[d,e] q[d,n]  -> out rows [B*N, H*32].  One CTA (32x32 threads) per (sample, head); N <= 64.

@@ -1,5 +1,8 @@
-// gemm_persist.cu -- persistent tcgen05 (TF32) GEMM / per-tap implicit-GEMM conv: the second generation of
-// gemm_tf32.cu (same math, same C ABI) built around what the round-1 profiles showed about the one-tile-per-CTA kernel:
+// gemm_persist.cu -- persistent tcgen05 GEMM / per-tap implicit-GEMM conv (fp32-stored operands -> kind::tf32, IEEE-half operands ->
+// kind::f16) and ALL dense-contraction entry points of the C ABI (p2pb_gemm_rows*, p2pb_conv3d_cl*).  One kernel family covers every
+// Conv1d / Conv2d(1x1) / Linear and the r = 8 Conv3d of the hot path (reference: cuDNN/cuBLAS behind models/pvcnn.py:174-192,265-284,
+// models/modules.py:337,365-370):  D[M,N] = A[M,K] W[N,K]^T (+ bias[N]) (+ bias2[sample(m),N]), fp32 accumulate / output.
+// Built around what the round-1 profiles showed about the first-generation one-tile-per-CTA kernel (removed in round 2):
 //
 //   * its epilogue (tcgen05.ld -> per-lane 128-byte row stores) was not overlapped with anything and every STG.128
 //     touched 32 different cache lines (32 LSU wavefronts per instruction);
@@ -451,7 +454,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     }
                 }
                 const int nb = n0 + c * 32;
-                if (a.dbg & 8) continue;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float x = v[j];
@@ -479,7 +481,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     p_tma_store_2d(&mapD, p_smem_u32(buf), nb, row0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if ((want_stats || want_mm) && !(a.dbg & 16)) {
+                if (want_stats || want_mm) {
                     // column `lane` of the 32 x 32 block: element (r, lane) sits at r*128 + (((lane>>2) ^ (r&7))<<4) + (lane&3)*4
                     float s1 = 0.f, s2 = 0.f, mx = -INFINITY, mn = INFINITY;
                     const uint8_t* colp = buf + (lane & 3) * 4;
@@ -603,19 +605,24 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
 
 }  // namespace
 
-int g_p2pb_gemm_mode = 0;   // bit 1: force the legacy one-tile-per-CTA kernel; bit 2: 2-CTA multicast clusters instead of CTA pairs;
-                            // bits 3,4: timing experiments; bit 5: never form CTA pairs (cta_group::2)
+static int g_p2pb_gemm_mode = 0;   // p2pb_gemm_tune: 4 = 2-CTA multicast clusters instead of CTA pairs; 32 = never form CTA pairs
 
-// Returns P2PB_ERR_UNSUPPORTED (without setting an error) when the shape is outside this kernel's envelope; the
-// caller then uses the legacy kernel (gemm_tf32.cu).  mapsA: up to 3 prepared A maps (rows mode: box {32,128};
-// conv mode: 5-D box), W: [N, Ktot].
+// development aid for tests/ and tools/: how the persistent GEMM groups CTAs for the big shapes.  0 (default) = cta_group::2 CTA
+// pairs (M = 256), 4 = 2-CTA clusters with multicast weights, 32 = independent CTAs only.  Results are identical in every mode.
+P2PB_API int p2pb_gemm_tune(int mode)
+{
+    P2PB_CHECK_ARG(mode == 0 || mode == 4 || mode == 32, "gemm_tune: mode %d (0, 4 or 32)", mode);
+    g_p2pb_gemm_mode = mode;
+    return P2PB_OK;
+}
+
+// mapsA: up to 3 prepared A maps (rows mode: box {32 fp32 | 64 half, 128}; conv mode: 5-D box), W: [N, Ktot].
 static int gemm_persist_launch(const CUtensorMap* mapsA, int nseg, const int* seg_chunks, int conv, int cin_chunks, int tiles_per_sample,
                                int r, const void* W, int ktot, const float* bias, const float* bias2, int rows_per_sample, float* D,
                                int ldd, float* stats, float* colmm, int M, int N, bool f16, cudaStream_t s)
 {
-    if (g_p2pb_gemm_mode & 2) return P2PB_ERR_UNSUPPORTED;
-    if (N % 32 != 0) return P2PB_ERR_UNSUPPORTED;
-    if (D != nullptr && ((reinterpret_cast<uintptr_t>(D) & 15) != 0 || ldd % 4 != 0)) return P2PB_ERR_UNSUPPORTED;
+    P2PB_CHECK_ARG(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+    P2PB_CHECK_ARG(D == nullptr || ((reinterpret_cast<uintptr_t>(D) & 15) == 0 && ldd % 4 == 0), "gemm: D must be 16-byte aligned with ldd %% 4 == 0");
     const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
     PArgs a = {};
     a.M = M; a.n_total = N; a.n_tiles = N / bn; a.m_tiles = p2pb_cdiv(M, PBM);
@@ -629,13 +636,12 @@ static int gemm_persist_launch(const CUtensorMap* mapsA, int nseg, const int* se
     a.total_chunks = conv ? 27 * cin_chunks : total;
     a.rows_per_sample = rows_per_sample;
     a.store = D != nullptr;
-    a.dbg = g_p2pb_gemm_mode;
     a.f16 = f16 ? 1 : 0;
     a.bias = bias; a.bias2 = bias2; a.stats = stats; a.colmm = colmm;
     // 2-CTA cluster with multicast weights when the weight tile dominates the operand traffic and there is enough work
     // CTA pairs (cta_group::2, M = 256): each SM fetches only half of the weight tile -> for the tensor-bound shapes
-    const bool pair = !(g_p2pb_gemm_mode & 32) && !(g_p2pb_gemm_mode & 4) && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
-    const bool cl2 = !pair && (g_p2pb_gemm_mode & 4) && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
+    const bool pair = g_p2pb_gemm_mode == 0 && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
+    const bool cl2 = g_p2pb_gemm_mode == 4 && bn >= 128 && a.m_tiles >= 2 && (long long)a.m_tiles * a.n_tiles >= 2LL * p2pb_num_sms();
     CUtensorMap maps[5];
     for (int i = 0; i < 3; ++i) maps[i] = mapsA[i < nseg ? i : 0];
     {
@@ -675,12 +681,75 @@ static int gemm_persist_launch(const CUtensorMap* mapsA, int nseg, const int* se
     return P2PB_ERR_UNSUPPORTED;
 }
 
-int p2pb_gemm_persist_try(const CUtensorMap* mapsA, int nseg, const int* seg_chunks, int conv, int cin_chunks, int tiles_per_sample,
-                          int r, const float* W, int ktot, const float* bias, const float* bias2, int rows_per_sample, float* D,
-                          int ldd, float* stats, float* colmm, int M, int N, cudaStream_t s)
+// ---- fp32-stored (tf32) operand entry points ------------------------------------------------------------------------------------
+// rows-mode GEMM:  D[M, N] = sum_i A_i[M, K_i] * W[N, sum K_i]^T + bias + bias2[m / rows_per_sample]
+//   A_i : row-major, row pitch lda_i floats (K_i multiples of 32, lda_i of 4), i < nseg <= 3 (replaces torch.cat)
+//   W   : [N, Ktot] row-major, Ktot = sum K_i;  N multiple of 32
+//   D   : [M, ldd] (16-byte aligned, ldd % 4 == 0) or null;  stats / colmm (optional): [4*ceil(M/128), N, 2] column (sum, sum of
+//         squares) / (max, min) of every 32-row block
+// Replaces the cuDNN / cuBLAS calls behind models/pvcnn.py:174-192 (Conv1d / Conv2d 1x1) and models/modules.py:337,365-370 (Linear).
+P2PB_API int p2pb_gemm_rows_ex(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2,
+                               int lda2, const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                               int ldd, float* stats, float* colmm, int M, int N, void* stream)
 {
-    return gemm_persist_launch(mapsA, nseg, seg_chunks, conv, cin_chunks, tiles_per_sample, r, W, ktot, bias, bias2, rows_per_sample, D,
-                               ldd, stats, colmm, M, N, false, s);
+    const float* Ap[3] = {A0, A1, A2};
+    const int Ks[3] = {K0, K1, K2}, lds[3] = {lda0, lda1, lda2};
+    P2PB_CHECK_ARG(M > 0 && N > 0 && N % 32 == 0, "gemm_rows: bad M=%d N=%d (N must be a multiple of 32)", M, N);
+    P2PB_CHECK_ARG(D == nullptr || (ldd % 4 == 0 && ldd >= N), "gemm_rows: ldd=%d must be >= N and a multiple of 4", ldd);
+    P2PB_CHECK_ARG(D != nullptr || stats != nullptr || colmm != nullptr, "gemm_rows: no output requested");
+    P2PB_CHECK_ARG(bias2 == nullptr || rows_per_sample > 0, "gemm_rows: bias2 needs rows_per_sample");
+    CUtensorMap maps[3];
+    int chunks[3] = {0, 0, 0}, ktot = 0, nseg = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (Ap[i] == nullptr || Ks[i] == 0) break;
+        P2PB_CHECK_ARG(Ks[i] % 32 == 0 && lds[i] % 4 == 0 && lds[i] >= Ks[i], "gemm_rows: segment %d K=%d lda=%d (K %% 32, lda %% 4)", i, Ks[i], lds[i]);
+        P2PB_CHECK_ARG((reinterpret_cast<uintptr_t>(Ap[i]) & 15) == 0, "gemm_rows: segment %d not 16-byte aligned", i);
+        cuuint64_t dims[2] = {(cuuint64_t)Ks[i], (cuuint64_t)M};
+        cuuint64_t str[1] = {(cuuint64_t)lds[i] * 4};
+        cuuint32_t box[2] = {32, PBM};
+        int rc = p_make_map(&maps[i], Ap[i], 2, dims, str, box);
+        if (rc != P2PB_OK) return rc;
+        chunks[i] = Ks[i] / 32;
+        ktot += Ks[i];
+        ++nseg;
+    }
+    P2PB_CHECK_ARG(nseg > 0, "gemm_rows: no A segment");
+    return gemm_persist_launch(maps, nseg, chunks, 0, 0, 0, 0, W, ktot, bias, bias2, rows_per_sample, D, ldd, stats, colmm, M, N, false,
+                               (cudaStream_t)stream);
+}
+
+P2PB_API int p2pb_gemm_rows(const float* A0, int K0, int lda0, const float* A1, int K1, int lda1, const float* A2, int K2,
+                            int lda2, const float* W, const float* bias, const float* bias2, int rows_per_sample, float* D,
+                            int ldd, float* stats, int M, int N, void* stream)
+{
+    return p2pb_gemm_rows_ex(A0, K0, lda0, A1, K1, lda1, A2, K2, lda2, W, bias, bias2, rows_per_sample, D, ldd, stats, nullptr, M, N,
+                             stream);
+}
+
+// implicit-GEMM 3x3x3 convolution, stride 1, zero padding 1, channels-last (replaces cuDNN Conv3d, models/pvcnn.py:265-284):
+//   grid [B, r, r, r, Cin] (Cin multiple of 32; x slowest, z fastest = the reference's flat voxel index x*r^2+y*r+z)
+//   W    [Cout, 27*Cin] with k = ((kx*3+ky)*3+kz)*Cin + c  (repacked from the reference's [Cout, Cin, 3, 3, 3]), Cout % 32 == 0
+//   D    [B*r^3, ldd] ; stats (optional) [B*r^3/32, Cout, 2]
+// The im2col matrix is never built: per tap a 5-D TMA box load shifted by (dx,dy,dz) brings the 128-voxel x 32-channel operand
+// tile, out-of-range voxels are zero-filled by the TMA unit (= the conv's zero padding).
+P2PB_API int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
+                            int Cin, int Cout, void* stream)
+{
+    P2PB_CHECK_ARG(B > 0 && Cin % 32 == 0 && Cout % 32 == 0, "conv3d_cl: bad B=%d Cin=%d Cout=%d (Cin %% 32, Cout %% 32)", B, Cin, Cout);
+    P2PB_CHECK_ARG(r >= 8 && (r & (r - 1)) == 0 && r <= 128, "conv3d_cl: r=%d must be a power of two in [8,128]", r);
+    P2PB_CHECK_ARG(ldd % 4 == 0 && ldd >= Cout && (reinterpret_cast<uintptr_t>(D) & 15) == 0, "conv3d_cl: bad D/ldd");
+    const int r3 = r * r * r;
+    const int bz = r < PBM ? r : PBM;
+    const int by = (PBM / bz) < r ? (PBM / bz) : r;
+    const int bx = PBM / (bz * by);
+    CUtensorMap map;
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)r, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cin * 4 * r, (cuuint64_t)Cin * 4 * r * r, (cuuint64_t)Cin * 4 * r3};
+    cuuint32_t box[5] = {32, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
+    int rc = p_make_map(&map, grid, 5, dims, str, box);
+    if (rc != P2PB_OK) return rc;
+    return gemm_persist_launch(&map, 1, nullptr, 1, Cin / 32, r3 / PBM, r, W, 27 * Cin, bias, nullptr, 0, D, ldd, stats, nullptr, B * r3,
+                               Cout, false, (cudaStream_t)stream);
 }
 
 // ---- IEEE-half operand entry points (A segments and W are __half; K_i multiples of 64; bias / D / stats fp32) -------------

@@ -1,4 +1,4 @@
-"""Torch-tensor front end of the tcgen05 GEMM / implicit-GEMM conv kernels (``csrc/gemm_tf32.cu``).
+"""Torch-tensor front end of the tcgen05 GEMM / implicit-GEMM conv kernels (``csrc/gemm_persist.cu``, ``csrc/conv_halo.cu``).
 
 Channels-last fp32 activations ("rows": ``[M, C]`` with C padded to a multiple of 32); weights pre-packed K-major
 ``[N, K]``.  Kernels run on torch's current stream; CUDA only."""

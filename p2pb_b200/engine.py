@@ -110,6 +110,7 @@ class Engine:
         self.tf32_layers: List[str] = []      # layers whose WEIGHTS do not fit half's range and were packed as fp32 / tf32
         if self.halo_f16 or self.gemm_f16:
             self.dtype_name = "tf32+f16(10-bit mantissa operands), fp32 accumulate"
+        self._folds: List[Tuple[str, torch.Tensor]] = []      # (bias2 buffer name, W[:, time columns]) of every temb fold
         self._emd_w: List[torch.Tensor] = []
         self._emd_b: List[torch.Tensor] = []
         self._emd_total = 0
@@ -161,7 +162,7 @@ class Engine:
         return out.contiguous()
 
     # ------------------------------------------------------------------------------------------------ packing
-    def _pack_pvconv(self, mod, c_in: int, temb_in: bool, coords_first: bool, name: str = "pvconv"):
+    def _pack_pvconv(self, mod, c_in: int, temb_in: bool, coords_first: bool, name: str = "pvconv", ename: str = "pv"):
         """c_in = valid channels of the incoming rows (features[, xyz]); temb_in: 64 time channels follow in the
         reference's channel order.  coords_first: reference input order is [xyz, feats] (level 0) -> ours [feats, xyz]."""
         E = self.E if temb_in else 0
@@ -207,11 +208,12 @@ class Engine:
         P["wp"][:, :c_in] = wp[:, perm]
         P["wp"] = P["wp"].contiguous()
         P["bp"] = self._w(pf[0].bias)
-        P["wp_t"] = wp[:, c_in:c_in + E].contiguous() if E else None
+        if E:       # cat[features, time_emb] in front of the point branch's 1x1 conv == per-sample bias (p2pb_step_vectors)
+            self._folds.append((f"{ename}.ptb", wp[:, c_in:c_in + E].contiguous()))
         P["np"] = self._norm(pf[1])
         return P
 
-    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None, half_first=False, name: str = "mlp"):
+    def _pack_mlp(self, layers, first_cols, k_pad_first, temb_cols=None, half_first=False, name: str = "mlp", ename: str = "mlp"):
         """SharedMLP -> list of dicts; first layer's columns remapped by first_cols; optional temb fold block.
         With gemm_f16 the layers after the first take IEEE-half operands (their input is a GroupNorm+Swish output written
         by this engine); the first layer too when its input rows are produced as half (half_first: grouped rows)."""
@@ -227,7 +229,8 @@ class Engine:
                     L["w"] = L["w"].half()
                 if temb_cols is not None:
                     w = self._w(conv.weight).reshape(o, c)
-                    L["w_t"] = w[:, temb_cols[0]:temb_cols[0] + temb_cols[1]].contiguous()
+                    L["tb_name"] = f"{ename}.0.tb"
+                    self._folds.append((L["tb_name"], w[:, temb_cols[0]:temb_cols[0] + temb_cols[1]].contiguous()))
             elif self.gemm_f16 and o % 32 == 0 and self._half_ok(f"{name}.layers.{i}", conv.weight):
                 L["w"] = self._pack_rows_w(conv.weight, [(0, c, 0)], pad64(c)).half()
             else:
@@ -291,7 +294,7 @@ class Engine:
             c_cur = c_feat
             for k, pv in enumerate(pvs):
                 L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=(i > 0 and k == 0), coords_first=(i == 0 and k == 0),
-                                                 name=f"sa_layers.{i}.{k}"))
+                                                 name=f"sa_layers.{i}.{k}", ename=f"sa{i}.pv{k}"))
                 c_cur = L["pv"][-1]["cout"]
             temb_sa = (len(pvs) == 0 and i > 0)
             # SA-module MLP: reference grouped input = [rel xyz (3), features (c_cur) (+ temb 64)]; ours [features, rel xyz]
@@ -302,7 +305,8 @@ class Engine:
                        and self._half_ok(f"sa_layers.{i}.mlps.0.layers.0", sam.mlps[0].layers[0].weight))
             L["mlp"] = self._pack_mlp(sam.mlps[0].layers, [(3, c_cur, 0), (0, 3, c_cur)],
                                       pad64(c_cur + 3) if sa_half else pad32(c_cur + 3),
-                                      temb_cols=(3 + c_cur, E) if temb_sa else None, half_first=sa_half, name=f"sa_layers.{i}.mlps.0")
+                                      temb_cols=(3 + c_cur, E) if temb_sa else None, half_first=sa_half, name=f"sa_layers.{i}.mlps.0",
+                                      ename=f"sa{i}.mlp")
             # gather-after-GEMM form of the first layer (p2pb_group_project): feature part per point, coordinate part in fp32
             conv0 = sam.mlps[0].layers[0]
             o0 = conv0.weight.shape[0]
@@ -350,11 +354,12 @@ class Engine:
                 skip_cols = [(c_low + E, c_skip, c_low)]
             assert c_low % 32 == 0
             L = {"mlp": self._pack_mlp(fpm.mlp.layers, [(0, c_low, 0)] + skip_cols, c_low + kp_skip, temb_cols=(c_low, E),
-                                       name=f"fp_layers.{j}.mlp"),
+                                       name=f"fp_layers.{j}.mlp", ename=f"fp{j}.mlp"),
                  "c_low": c_low, "kp_skip": kp_skip, "lvl": lvl, "pv": []}
             c_cur = L["mlp"][-1]["cout"]
             for pv in pvs:
-                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=False, coords_first=False, name=f"fp_layers.{j}.{1 + len(L['pv'])}"))
+                L["pv"].append(self._pack_pvconv(pv, c_cur, temb_in=False, coords_first=False, name=f"fp_layers.{j}.{1 + len(L['pv'])}",
+                                                 ename=f"fp{j}.pv{len(L['pv'])}"))
                 c_cur = L["pv"][-1]["cout"]
             fp.append(L)
             c_low = c_cur
@@ -363,10 +368,9 @@ class Engine:
         cl = net.classifier
         W["cls"] = self._pack_mlp(cl[0].layers, [(0, c_low, 0)], pad32(c_low), name="classifier.0")
         om = cl[-1].weight.shape[1]
-        W["cls_out"] = self.zeros(16, pad32(om))
-        W["cls_out"][:3, :om] = self._w(cl[-1].weight).reshape(3, om)
-        W["cls_outb"] = self.zeros(16)
-        W["cls_outb"][:3] = self._w(cl[-1].bias)
+        assert cl[-1].weight.shape[0] == 3 and om % 4 == 0
+        W["cls_out"] = self._w(cl[-1].weight).reshape(3, om).contiguous()       # fp32 [3, C]: p2pb_head_bridge
+        W["cls_outb"] = self._w(cl[-1].bias)
         # batched AdaGN emd weights
         if self._emd_total:
             W["emd_w"] = torch.cat(self._emd_w, 0).contiguous()
@@ -377,6 +381,17 @@ class Engine:
                 W["emd_b"] = torch.cat([W["emd_b"], self.zeros(pad)], 0).contiguous()
             self._emd_ld = W["emd_w"].shape[0]
         self.W = W
+        # temb folds: one dense [B, cout] bias2 buffer each, all produced by ONE p2pb_step_vectors launch per step
+        self._fold_R = sum(w.shape[0] for _, w in self._folds)
+        if self._folds:
+            W["fold_w"] = torch.cat([w for _, w in self._folds], 0).contiguous()
+            ptr, stride = [], []
+            for nm, w in self._folds:
+                b = self.buf(nm, self.B, w.shape[0])
+                ptr += [b.data_ptr() + 4 * o for o in range(w.shape[0])]
+                stride += [w.shape[0]] * w.shape[0]
+            W["fold_ptr"] = torch.tensor(ptr, dtype=torch.int64, device=self.dev)
+            W["fold_stride"] = torch.tensor(stride, dtype=torch.int32, device=self.dev)
 
     # ------------------------------------------------------------------------------------------------ buffers
     def buf(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
@@ -449,10 +464,7 @@ class Engine:
         x_segs, x_ks = segs, ks
         for li, L in enumerate(layers):
             nm = f"{name}.{li + li0}"
-            bias2 = None
-            if li == 0 and "w_t" in L:
-                bias2 = self.buf(nm + ".tb", B, L["cout"])
-                self.linear(temb, L["w_t"], None, 0, bias2)
+            bias2 = self.buf(L["tb_name"], B, L["cout"]) if (li == 0 and "tb_name" in L) else None     # filled by step_vectors
             last = li == len(layers) - 1
             # neighbourhood max-pool over K = 32 grouped rows == one 32-row block of the GEMM epilogue's column (max, min):
             # the last layer's [B*M*32, C] output is never written and the pooling pass disappears (p2pb_pool32_minmax)
@@ -487,10 +499,7 @@ class Engine:
         L0 = L["mlp"][0]
         c0 = L0["cout"]
         nm = f"{name}.mlp.0"
-        bias2 = None
-        if "w_t" in L0:
-            bias2 = self.buf(nm + ".tb", B, c0)
-            self.linear(temb, L0["w_t"], None, 0, bias2)
+        bias2 = self.buf(L0["tb_name"], B, c0) if "tb_name" in L0 else None       # filled by step_vectors
         pf, _, _ = self.gemm(nm + ".pf", [feats], [pad32(cg)], L["w_f"], L0["b"], c0, n_pts, bias2=bias2, want_stats=False)
         stats = self.buf(nm + ".stats", B * M, c0, 2)
         args = (_p(pf), int(pf.stride(0)), _p(L["w_x"]), _p(coords_pts), _p(coords_ctr), _p(nidx))
@@ -515,10 +524,7 @@ class Engine:
             fork.record(main)
             pstream.wait_event(fork)
         with torch.cuda.stream(pstream if pstream is not None else main):
-            bias2 = None
-            if P["E"]:
-                bias2 = self.buf(f"{name}.ptb", B, cout)
-                self.linear(temb, P["wp_t"], None, 0, bias2)
+            bias2 = self.buf(f"{name}.ptb", B, cout) if P["E"] else None       # filled by step_vectors
             kp = P["wp"].shape[1]
             praw, pst, ptiles = self.gemm(f"{name}.pt", [feats], [kp], P["wp"], P["bp"], cout, n_pts, bias2=bias2)
             pA, pB, _ = self.coef(f"{name}.np", pst, ptiles, P["np"], cout, n_pts)
@@ -568,10 +574,8 @@ class Engine:
         A2, B2, ym = self.coef(f"{name}.n2", st2, tiles, P["n2"], cout, r3, want_mean="se0" in P)
         se = None
         if "se0" in P:
-            hid = self.buf(f"{name}.seh", B, P["se0"].shape[0])
-            self.linear(ym, P["se0"], None, 2, hid)
             se = self.buf(f"{name}.se", B, cout)
-            self.linear(hid, P["se2"], None, 3, se)
+            call("p2pb_se_excite", _p(ym), _p(P["se0"]), _p(P["se2"]), B, cout, P["se0"].shape[0], _p(se), _s())
         if pt_done is not None:
             torch.cuda.current_stream().wait_event(pt_done)
         out = self.buf(f"{name}.out", B * n_pts, cout)
@@ -673,11 +677,17 @@ class Engine:
         else:
             F0[:, :fe] = xc[:, :fe]
 
-    def evaluate(self, xt, temb):
-        """One network evaluation: xt [B,3,N], temb [B,E] (after the embedf MLP) -> eps rows [B*N, 16] (cols 0..2)."""
+    def evaluate(self, xt, sin, bridge=None):
+        """One network evaluation: xt [B,3,N], sin = sinusoid of the noise level, [B,E] (row stride may be 0: every sample of a
+        sampling step shares the noise level) -> eps rows [B*N, 16] (cols 0..2).  bridge = (coef device pointer table row, clip,
+        pred_x0 buffer or None): the bridge update xt <- p_posterior(...) runs inside the head kernel (xt is updated in place)."""
         B, N, W, fe, E = self.B, self.N, self.W, self.fe, self.E
         Ns = self.Ns
         n_levels = len(W["sa"])
+        # ---- everything that depends only on the time embedding: embedf MLP + every temb fold, one launch
+        temb = self.buf("temb", B, E)
+        call("p2pb_step_vectors", _p(sin), int(sin.stride(0)), _p(W["tw0"]), _p(W["tb0"]), _p(W["tw2"]), _p(W["tb2"]), B, E,
+             _p(W.get("fold_w")), self._fold_R, _p(W.get("fold_ptr")), _p(W.get("fold_stride")), _p(temb), _s())
         # ---- geometry: FPS chain, ball queries, 3-NN, voxel CSRs (coordinates only).  It is latency-bound (one CTA per
         # patch for FPS) and independent of the features, so it runs on a side stream concurrently with the feature
         # embedding / global PointNet / AdaGN GEMMs below (fork/join with events; captured into the same CUDA graph).
@@ -802,9 +812,24 @@ class Engine:
                 prep = self.voxel_prep(preps, lvl, coords[lvl], P["r"])
                 feats = self.pvconv(f"fp{j}.pv{k}", P, feats, coords[lvl], prep, temb, n_up)
         # ---- classifier head (unet_pvc.py:147-154,263-267)
-        h = self.mlp_chain("cls", W["cls"], [feats], [pad32(feats.shape[1])], N, temb)
+        cls = W["cls"]
+        segs, ks = [feats], [pad32(feats.shape[1])]
+        if len(cls) > 1:
+            hmid = self.mlp_chain("cls", cls[:-1], segs, ks, N, temb)
+            segs, ks = [hmid], [hmid.shape[1]]
+        L = cls[-1]
+        nm = f"cls.{len(cls) - 1}"
+        raw, st, tl = self.gemm(nm, segs, ks, L["w"], L["b"], L["cout"], N)
+        A, Bc, _ = self.coef(nm, st, tl, L["n"], L["cout"], N)
         eps = self.buf("eps", B * N, 16)
-        dense.gemm_rows([h], W["cls_out"], W["cls_outb"], out=eps, ks=[W["cls_out"].shape[1]])
+        # last GroupNorm + Swish, the C -> 3 projection (fp32) and, inside the sampling loop, the bridge update: one pass
+        if bridge is None:
+            call("p2pb_head_bridge", _p(raw), int(raw.stride(0)), _p(A), _p(Bc), _p(W["cls_out"]), _p(W["cls_outb"]), B, L["cout"], N,
+                 _vp(0), _vp(0), 0, _vp(0), _vp(0), _p(eps), 16, _s())
+        else:
+            coef, clip, x0 = bridge
+            call("p2pb_head_bridge", _p(raw), int(raw.stride(0)), _p(A), _p(Bc), _p(W["cls_out"]), _p(W["cls_outb"]), B, L["cout"], N,
+                 _p(xt), _p(coef), int(bool(clip)), _p(xt), _p(x0), _p(eps), 16, _s())
         return eps
 
     def time_embedding(self, noise_level: float, out):
@@ -825,16 +850,10 @@ class Engine:
         li = 0
         for s, (prev, step) in enumerate(pairs):
             sin = self.buf(f"temb.sin{len(pairs)}", len(pairs), E)
-            th = self.buf("temb.h", B, E)
-            temb = self.buf("temb", B, E)
             row = sin[s:s + 1].expand(B, E)       # stride-0 view: every sample shares the noise level in sampling
-            self.linear(row, self.W["tw0"], self.W["tb0"], 4, th)
-            self.linear(th, self.W["tw2"], self.W["tb2"], 0, temb)
-            eps = self.evaluate(xt, temb)
             logged = prev in log_set
             x0 = x0_buf[li] if logged else None
-            call("p2pb_bridge_update", _p(xt), _p(eps), 16, _p(self.buf(f"coef{len(pairs)}", len(pairs), 3)[s]), int(bool(clip)), _p(xt),
-                 _p(x0), B, N, _s())
+            self.evaluate(xt, row, bridge=(self.buf(f"coef{len(pairs)}", len(pairs), 3)[s], clip, x0))
             if logged:
                 xs_buf[li].copy_(xt)
                 li += 1

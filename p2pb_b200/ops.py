@@ -320,3 +320,46 @@ def room_accumulate(x_pred: torch.Tensor, center: torch.Tensor, scale: torch.Ten
     with torch.cuda.device(x_pred.device):
         call("p2pb_room_accumulate", _ptr(x_pred), _ptr(center), _ptr(scale), _ptr(idx), _ptr(cut), P, M, _ptr(sum_fixed), _ptr(count),
              _stream())
+
+
+# ---- evaluation metrics at scale (metrics/metrics.py:139-225, metrics/p2m.py:307-375) --------------------------------------
+def normalize_sphere(pc: torch.Tensor, radius: float = 1.0):
+    """metrics/metrics.py:139-158: bounding-box centre, max-norm scale -> (pc, center [B,1,3], scale [B,1,1])."""
+    p_max = pc.max(dim=-2, keepdim=True)[0]
+    p_min = pc.min(dim=-2, keepdim=True)[0]
+    center = (p_max + p_min) / 2
+    pc = pc - center
+    scale = (pc ** 2).sum(dim=-1, keepdim=True).sqrt().max(dim=-2, keepdim=True)[0] / radius
+    return pc / scale, center, scale
+
+
+def cd_unit_sphere(gen: torch.Tensor, ref: torch.Tensor, normalize: bool = True):
+    """metrics/metrics.py:176-195: Chamfer distance of ``gen [B,N,3]`` vs ``ref [B,M,3]`` after normalising BOTH with the
+    reference cloud's unit-sphere transform -> (mean squared distance gen->ref, ref->gen) as floats."""
+    if normalize:
+        ref, center, scale = normalize_sphere(ref)
+        gen = (gen - center) / scale
+    d1, d2, _, _ = chamfer_forward(gen.contiguous().float(), ref.contiguous().float())
+    return d1.mean().item(), d2.mean().item()
+
+
+def point_face_dist(pcl: torch.Tensor, verts: torch.Tensor, faces: torch.Tensor, normalize: bool = True,
+                    min_triangle_area: float = 5e-3):
+    """metrics/metrics.py:196-225 ``point_face_dist`` (P2F metric): ``pcl [P,3]``, mesh ``verts [V,3]`` / ``faces int [T,3]``,
+    both normalised with the MESH's unit-sphere transform -> (mean squared point->face distance, mean squared face->point
+    distance), the two terms of ``point_mesh_face_distance_custom`` (metrics/p2m.py:307-375; default min_triangle_area 5e-3,
+    p2m.py:20)."""
+    assert pcl.dim() == 2 and verts.dim() == 2 and faces.dim() == 2, "Batch is not supported."
+    if normalize:
+        v, center, scale = normalize_sphere(verts.unsqueeze(0))
+        verts = v[0]
+        pcl = ((pcl.unsqueeze(0) - center) / scale)[0]
+    pcl = pcl.contiguous().float()
+    tris = verts.float()[faces.long()].contiguous()          # [T,3,3]
+    _chk(pcl, torch.float32, "pcl", 2)
+    P, T = pcl.shape[0], tris.shape[0]
+    pd = torch.empty((P,), dtype=torch.float32, device=pcl.device)
+    fd = torch.empty((T,), dtype=torch.float32, device=pcl.device)
+    with torch.cuda.device(pcl.device):
+        call("p2pb_point_face_dist", _ptr(pcl), P, _ptr(tris), T, _f(float(min_triangle_area)), _ptr(pd), _ptr(fd), _stream())
+    return pd.mean().item(), fd.mean().item(), pd, fd

@@ -39,10 +39,7 @@ def test_engine_single_evaluation_vs_reference_golden(golden_dir, name):
         if xc is not None:
             eng.prepare_cond(xc)
         sin = eng.time_embedding(nl, None)[None].expand(B, -1).contiguous()
-        th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
-        eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
-        eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
-        eps_rows = eng.evaluate(x.contiguous(), temb)
+        eps_rows = eng.evaluate(x.contiguous(), sin)
     torch.cuda.synchronize()
     eps = eps_rows[:, :3].reshape(B, N, 3).permute(0, 2, 1).cpu().numpy()
     err = np.abs(eps - z["eps"])
@@ -114,10 +111,7 @@ def _one_evaluation(eng, x, noise_level):
     B, _, N = x.shape
     with torch.no_grad():
         sin = eng.time_embedding(noise_level, None)[None].expand(B, -1).contiguous()
-        th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
-        eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
-        eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
-        eps_rows = eng.evaluate(x.contiguous(), temb)
+        eps_rows = eng.evaluate(x.contiguous(), sin)
     torch.cuda.synchronize()
     return eps_rows[:, :3].reshape(B, N, 3).permute(0, 2, 1)
 
@@ -258,10 +252,7 @@ def test_engine_pvdl_8192_vs_eager(extra):
         if xc is not None:
             eng.prepare_cond(xc)
         sin = eng.time_embedding(float(nl[0].item()), None)[None].expand(B, -1).contiguous()
-        th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
-        eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
-        eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
-        eps = eng.evaluate(x.contiguous(), temb)[:, :3].reshape(B, N, 3).permute(0, 2, 1)
+        eps = eng.evaluate(x.contiguous(), sin)[:, :3].reshape(B, N, 3).permute(0, 2, 1)
     torch.backends.cudnn.allow_tf32 = True
     err = (eps - ref).abs()
     print(f"PVDL N=8192 extra={extra}: engine vs eager fp32: mean|err|={err.mean():.3e} max|err|={err.max():.3e} |eps|max={ref.abs().max():.2f}")
@@ -349,10 +340,7 @@ def test_engine_tf32_operand_path_still_matches_golden(golden_dir, monkeypatch):
         assert eng.halo_f16 == (flag == "1")
         with torch.no_grad():
             sin = eng.time_embedding(nl, None)[None].expand(B, -1).contiguous()
-            th, temb = eng.buf("t.th", B, eng.E), eng.buf("t.temb", B, eng.E)
-            eng.linear(sin, eng.W["tw0"], eng.W["tb0"], 4, th)
-            eng.linear(th, eng.W["tw2"], eng.W["tb2"], 0, temb)
-            eps = eng.evaluate(x.contiguous(), temb)[:, :3].reshape(B, N, 3).permute(0, 2, 1).cpu().numpy()
+            eps = eng.evaluate(x.contiguous(), sin)[:, :3].reshape(B, N, 3).permute(0, 2, 1).cpu().numpy()
         err = np.abs(eps - z["eps"])
         print(f"operands {'half' if flag == '1' else 'tf32'}: mean|err|={err.mean():.3e} max|err|={err.max():.3e}")
         assert err.mean() <= 2e-3 and err.max() <= 3e-2

@@ -16,8 +16,8 @@ def _close(out, ref):
     assert err <= TOL * ref.abs().max().item() + 1e-6, (err, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("M,K,N", [(128, 32, 16), (256, 64, 64), (1000, 96, 32), (64, 1024, 256), (4096, 128, 512),
-                                   (300, 32, 48), (131072, 64, 128), (8, 512, 384)])
+@pytest.mark.parametrize("M,K,N", [(128, 32, 32), (256, 64, 64), (1000, 96, 32), (64, 1024, 256), (4096, 128, 512),
+                                   (300, 32, 96), (131072, 64, 128), (8, 512, 384)])
 def test_gemm_rows_vs_fp64(M, K, N):
     from p2pb_b200 import dense
 
@@ -29,13 +29,12 @@ def test_gemm_rows_vs_fp64(M, K, N):
     _close(out, A.double() @ W.double().t() + bias.double())
 
 
-@pytest.mark.parametrize("mode", [0, 2, 4, 32])
+@pytest.mark.parametrize("mode", [0, 4, 32])
 @pytest.mark.parametrize("M,K,N", [(128 * 301 - 50, 96, 256), (128 * 300, 512, 1024), (40000, 64, 128), (5000, 160, 96)])
 def test_gemm_persistent_cluster_minmax(M, K, N, mode):
-    """Persistent kernel with cta_group::2 CTA pairs, M = 256, for the big shapes (mode 0; odd tile count = unpaired tail),
-    legacy one-tile-per-CTA kernel (mode 2), persistent with 2-CTA multicast clusters (mode 4) and persistent with
-    independent CTAs only (mode 32): results, GroupNorm partials and,
-    for the persistent kernel, column (max, min) and the statistics-only variant (no D)."""
+    """Persistent kernel with cta_group::2 CTA pairs, M = 256, for the big shapes (mode 0; odd tile count = unpaired tail), with
+    2-CTA multicast clusters (mode 4) and with independent CTAs only (mode 32), p2pb_gemm_tune: results, GroupNorm partials,
+    column (max, min) and the statistics-only variant (no D)."""
     from p2pb_b200 import dense
     from p2pb_b200._lib import lib
 
@@ -45,10 +44,10 @@ def test_gemm_persistent_cluster_minmax(M, K, N, mode):
     bias = torch.randn(N, device="cuda", generator=g)
     ref = A.double() @ W.double().t() + bias.double()
     T = dense.num_stat_blocks(M)
-    lib().p2pb_debug_set(mode)
+    assert lib().p2pb_gemm_tune(mode) == 0
     try:
         stats = torch.zeros(T, N, 2, device="cuda")
-        colmm = torch.zeros(T, N, 2, device="cuda") if mode != 2 else None
+        colmm = torch.zeros(T, N, 2, device="cuda")
         out = dense.gemm_rows([A], W, bias, stats=stats, colmm=colmm)
         _close(out, ref)
         assert torch.allclose(stats[..., 0].double().sum(0), out.double().sum(0), rtol=1e-4, atol=1e-2)
@@ -61,7 +60,7 @@ def test_gemm_persistent_cluster_minmax(M, K, N, mode):
             assert dense.gemm_rows([A], W, bias, stats=stats2, colmm=colmm2, store=False) is None
             assert torch.equal(stats2, stats) and torch.equal(colmm2, colmm)
     finally:
-        lib().p2pb_debug_set(0)
+        lib().p2pb_gemm_tune(0)
 
 
 def test_gmax_minmax_matches_dense_pass():
@@ -114,7 +113,7 @@ def test_gemm_rows_segments_bias2_stats():
     assert torch.allclose(s[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("B,r,cin,cout", [(2, 8, 32, 16), (1, 16, 64, 64), (2, 32, 32, 32), (3, 8, 256, 256), (1, 16, 128, 128),
+@pytest.mark.parametrize("B,r,cin,cout", [(2, 8, 32, 32), (1, 16, 64, 64), (2, 32, 32, 32), (3, 8, 256, 256), (1, 16, 128, 128),
                                           (1, 32, 64, 64), (2, 8, 192, 128)])
 def test_conv3d_vs_fp64(B, r, cin, cout):
     import torch.nn.functional as F
@@ -257,3 +256,66 @@ def test_conv3d_cl_half_operands(B, r, cin, cout):
     assert err <= 1e-4 * ref.abs().max().item() + 1e-6, err
     s = stats.double().view(B, -1, cout, 2).sum(1)
     assert torch.allclose(s[..., 0], out.double().view(B, -1, cout).sum(1), rtol=1e-4, atol=1e-2)
+
+
+def test_gemm_rejects_shapes_outside_the_envelope():
+    """N must be a multiple of 32 (one TMEM column block); there is no second kernel to fall back to -- the call raises."""
+    from p2pb_b200 import dense
+    from p2pb_b200._lib import P2PBError
+
+    A = torch.randn(128, 32, device="cuda")
+    with pytest.raises(P2PBError, match="multiple of 32"):
+        dense.gemm_rows([A], torch.randn(16, 32, device="cuda"), None)
+
+
+def test_step_vectors_se_excite_head_bridge_match_torch():
+    """The three small fused kernels of one sampling step against plain torch fp32."""
+    import ctypes
+
+    from p2pb_b200._lib import call
+
+    vp = ctypes.c_void_p
+    p = lambda t: vp(t.data_ptr()) if t is not None else vp(0)
+    s = vp(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    B, E = 5, 64
+    sin, w0, b0, w2, b2 = rn(B, E), rn(E, E) / 8, rn(E), rn(E, E) / 8, rn(E)
+    folds = [rn(c, E) / 8 for c in (64, 128, 37, 256)]
+    bufs = [torch.zeros(B, w.shape[0], device="cuda") for w in folds]
+    ptr = torch.tensor([b.data_ptr() + 4 * o for b, w in zip(bufs, folds) for o in range(w.shape[0])], dtype=torch.int64, device="cuda")
+    stride = torch.tensor([w.shape[0] for w in folds for _ in range(w.shape[0])], dtype=torch.int32, device="cuda")
+    wall = torch.cat(folds, 0).contiguous()
+    temb = torch.zeros(B, E, device="cuda")
+    call("p2pb_step_vectors", p(sin), E, p(w0), p(b0), p(w2), p(b2), B, E, p(wall), wall.shape[0], p(ptr), p(stride), p(temb), s)
+    t_ref = torch.nn.functional.linear(torch.nn.functional.leaky_relu(torch.nn.functional.linear(sin, w0, b0), 0.1), w2, b2)
+    assert torch.allclose(temb, t_ref, atol=1e-5)
+    for b, w in zip(bufs, folds):
+        assert torch.allclose(b, t_ref @ w.t(), atol=1e-4)
+    # shared noise level (row stride 0), no folds
+    temb0 = torch.zeros(B, E, device="cuda")
+    call("p2pb_step_vectors", p(sin[:1]), 0, p(w0), p(b0), p(w2), p(b2), B, E, vp(0), 0, vp(0), vp(0), p(temb0), s)
+    assert torch.allclose(temb0, t_ref[:1].expand(B, E), atol=1e-5)
+    # SE gate
+    C, Hd = 256, 32
+    ym, v0, v2 = rn(B, C), rn(Hd, C) / 16, rn(C, Hd) / 6
+    se = torch.zeros(B, C, device="cuda")
+    call("p2pb_se_excite", p(ym), p(v0), p(v2), B, C, Hd, p(se), s)
+    assert torch.allclose(se, torch.sigmoid(torch.relu(ym @ v0.t()) @ v2.t()), atol=1e-5)
+    # classifier tail + bridge update
+    N, C = 777, 128
+    raw, A, Bc, W, bias = rn(B * N, C), rn(B, C), rn(B, C), rn(3, C) / 11, rn(3)
+    xt, coef = rn(B, 3, N), torch.tensor([0.7, 0.3, 0.65], device="cuda")
+    h = torch.nn.functional.silu(raw.view(B, N, C) * A[:, None] + Bc[:, None])
+    eps_ref = (h @ W.t() + bias).permute(0, 2, 1)                                   # [B,3,N]
+    eps = torch.zeros(B * N, 16, device="cuda")
+    call("p2pb_head_bridge", p(raw), C, p(A), p(Bc), p(W), p(bias), B, C, N, vp(0), vp(0), 0, vp(0), vp(0), p(eps), 16, s)
+    got = eps[:, :3].view(B, N, 3).permute(0, 2, 1)
+    assert torch.allclose(got, eps_ref, atol=2e-5, rtol=1e-5)
+    for clip in (0, 1):
+        xn, x0 = torch.zeros_like(xt), torch.zeros_like(xt)
+        call("p2pb_head_bridge", p(raw), C, p(A), p(Bc), p(W), p(bias), B, C, N, p(xt * 4), p(coef), clip, p(xn), p(x0), vp(0), 0, s)
+        p0 = xt * 4 - coef[0] * got
+        if clip:
+            p0 = p0.clamp(-3.0, 3.0)
+        assert torch.equal(x0, p0) and torch.equal(xn, coef[1] * p0 + coef[2] * (xt * 4))   # same fp32 op order as p2pb.py:155-165,190-213

@@ -1,5 +1,6 @@
-"""Dev tool: time the rows-GEMMs / r=8 convs of the PVDS evaluation (B=64): legacy one-tile-per-CTA kernel (mode 2),
-persistent kernel without clusters (mode 4) and persistent kernel with 2-CTA multicast clusters (mode 0)."""
+"""Dev tool: the rows-GEMMs / r = 8 convs of one PVDS evaluation (64 patches) on the persistent tcgen05 kernel -- fp32-stored
+(kind::tf32) and IEEE-half operands (kind::f16), CTA pairs vs independent CTAs -- next to cuBLAS (torch.nn.functional.linear with
+TF32 and with fp16 inputs).  Prints a markdown table (profiles/r02_gemm_bench.md)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,55 +8,53 @@ from p2pb_b200 import dense
 from p2pb_b200._lib import lib
 
 
-def timeit(fn, n=10):
+def timeit(fn, n=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
+    return e0.elapsed_time(e1) / n * 1e3       # us
 
 
-print("rows GEMM: us for legacy | persist | persist+cluster | persist stats-only(minmax) | torch fp32-linear(tf32 off)")
-for (M, K, N) in [(131072, 32, 128), (131072, 128, 256), (131072, 256, 512), (131072, 512, 1024), (1048576, 64, 32),
-                  (1048576, 32, 64), (262144, 96, 64), (262144, 64, 128), (65536, 160, 128), (65536, 128, 256), (131072, 256, 128),
+HBM, TENSOR16 = 6550.7e9, 1602.9e12
+print("| M | K | N | tf32 pairs | tf32 single | half pairs | half stats-only | cuBLAS tf32 | cuBLAS fp16 | half: TFLOP/s | half: GB/s (frac of 6551) | bound |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|")
+for (M, K, N) in [(131072, 64, 128), (131072, 128, 256), (131072, 256, 512), (131072, 512, 1024), (1048576, 64, 32),
+                  (1048576, 64, 64), (262144, 128, 64), (262144, 64, 128), (65536, 192, 128), (65536, 128, 256), (131072, 256, 128),
                   (131072, 128, 128), (131072, 64, 64), (8192, 384, 256), (2048, 832, 512)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5
+    Ah, Wh = A.half(), W.half()
     bias = torch.randn(N, device="cuda"); out = torch.empty(M, N, device="cuda")
     stats = torch.zeros(dense.num_stat_blocks(M), N, 2, device="cuda")
     colmm = torch.zeros(dense.num_stat_blocks(M), N, 2, device="cuda")
-    res = []
-    for mode in (2, 32, 4, 0):
-        lib().p2pb_debug_set(mode)
-        res.append(timeit(lambda: dense.gemm_rows([A], W, bias, out=out, stats=stats)))
-    lib().p2pb_debug_set(0)
-    res.append(timeit(lambda: dense.gemm_rows([A], W, bias, stats=stats, colmm=colmm, store=False)))
-    extra = []
-    extra.append(timeit(lambda: dense.gemm_rows([A], W, bias, out=out)))            # no stats
-    lib().p2pb_debug_set(16)
-    extra.append(timeit(lambda: dense.gemm_rows([A], W, bias, out=out, stats=stats)))  # stats combine only, no column loop
-    lib().p2pb_debug_set(8)
-    extra.append(timeit(lambda: dense.gemm_rows([A], W, bias, out=out, stats=stats)))  # tmem_ld only
-    lib().p2pb_debug_set(0)
-    extra.append(timeit(lambda: dense.gemm_rows([A], W, None, out=out)))            # no stats, no bias
-    print("   experiments: no-stats %.1f | no-col-loop %.1f | tmem_ld only %.1f | no-stats-no-bias %.1f" % tuple(e * 1e3 for e in extra))
+    t_pair = timeit(lambda: dense.gemm_rows([A], W, bias, out=out, stats=stats))
+    lib().p2pb_gemm_tune(32)
+    t_single = timeit(lambda: dense.gemm_rows([A], W, bias, out=out, stats=stats))
+    lib().p2pb_gemm_tune(0)
+    t_half = timeit(lambda: dense.gemm_rows([Ah], Wh, bias, out=out, stats=stats))
+    t_half_so = timeit(lambda: dense.gemm_rows([Ah], Wh, bias, stats=stats, colmm=colmm, store=False))
     torch.backends.cuda.matmul.allow_tf32 = True
-    tl = timeit(lambda: torch.nn.functional.linear(A, W, bias))
-    fl = 2.0 * M * K * N; by = 4.0 * (M * K + M * N)
-    print(f"M={M:8d} K={K:4d} N={N:4d}: {res[0]*1e3:7.1f} | {res[1]*1e3:7.1f} | {res[2]*1e3:7.1f} | pair {res[3]*1e3:7.1f} | {res[4]*1e3:7.1f} | torch-tf32 {tl*1e3:7.1f}"
-          f" | ideal hbm {by/6.4e12*1e6:6.1f} tensor {fl/1.15e15*1e6:6.1f} | best {fl/min(res[:4])/1e9:7.1f} TFLOP/s {by/min(res[:4])/1e6:7.1f} GB/s")
+    t_cb = timeit(lambda: torch.nn.functional.linear(A, W, bias))
+    bh = bias.half()
+    t_cbh = timeit(lambda: torch.nn.functional.linear(Ah, Wh, bh))
+    fl = 2.0 * M * K * N
+    by_half = 2.0 * M * K + 4.0 * M * N
+    tf, gb = fl / t_half / 1e6, by_half / t_half / 1e3
+    bound = "tensor" if fl / TENSOR16 > by_half / HBM else "hbm"
+    print(f"| {M} | {K} | {N} | {t_pair:.1f} | {t_single:.1f} | {t_half:.1f} | {t_half_so:.1f} | {t_cb:.1f} | {t_cbh:.1f} | {tf:.0f} | {gb:.0f} ({gb / 6550.7:.2f}) | {bound} |")
 
-print("conv3d r=8 (per-tap implicit GEMM): us legacy | persist | persist+cluster")
+print()
+print("| conv r=8 (64 patches) | tf32 | half | half TFLOP/s |")
+print("|---|---|---|---|")
 for (B, r, cin, cout) in [(64, 8, 256, 256), (64, 8, 256, 128), (64, 8, 128, 128)]:
     grid = torch.randn(B, r, r, r, cin, device="cuda")
     w = torch.randn(cout, 27 * cin, device="cuda") / (27 * cin) ** 0.5
     bias = torch.randn(cout, device="cuda"); out = torch.empty(B * r ** 3, cout, device="cuda")
     stats = torch.zeros(B * r ** 3 // 32, cout, 2, device="cuda")
-    res = []
-    for mode in (2, 32, 4, 0):
-        lib().p2pb_debug_set(mode)
-        res.append(timeit(lambda: dense.conv3d_cl(grid, w, bias, B, r, cin, cout, out=out, stats=stats)))
-    lib().p2pb_debug_set(0)
+    t32 = timeit(lambda: dense.conv3d_cl(grid, w, bias, B, r, cin, cout, out=out, stats=stats))
+    gh, wh = grid.half(), w.half()
+    t16 = timeit(lambda: dense.conv3d_cl(gh, wh, bias, B, r, cin, cout, out=out, stats=stats))
     fl = 2.0 * B * r ** 3 * 27 * cin * cout
-    print(f"B={B} r={r} {cin}->{cout}: {res[0]*1e3:7.1f} | {res[1]*1e3:7.1f} | {res[2]*1e3:7.1f} | pair {res[3]*1e3:7.1f} | best {fl/min(res)/1e9:7.1f} TFLOP/s")
+    print(f"| {cin}->{cout} | {t32:.1f} | {t16:.1f} | {fl / t16 / 1e6:.0f} |")
