@@ -153,6 +153,9 @@ int p2pb_conv3d_cl(const float* grid, const float* W, const float* bias, float* 
  * X = zero-padded padded-linear rows [B*(r+1)^3 + slack, Cin] with SHARED padding: voxel (x,y,z) at row
  * (x+1)P^2 + (y+1)P + (z+1), P = r+1 (p2pb_conv_halo_layout gives rows/slack/tiles) */
 int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int* tiles_per_sample_out);
+/* tiles per sample of the kernel variant p2pb_conv3d_halo* runs for (r, Cin, Cout, operand type): its `stats` output has B * tiles
+ * rows.  (half operands with Cout = 32, or Cout = 64 and Cin >= 192, run the dz-stacked form: N = 3 Cout per MMA, 126 output rows per tile) */
+int p2pb_conv_halo_tiles(int r, int Cin, int Cout, int f16);
 int p2pb_conv3d_halo(const float* X, const float* W, const float* bias, float* D, int ldd, float* stats, int B, int r,
                      int Cin, int Cout, void* stream);
 /* development aid: override the halo kernel's pipeline shape (0 = automatic) */

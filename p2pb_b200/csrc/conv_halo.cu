@@ -46,6 +46,7 @@ struct HaloArgs {
     int G;                    // tiles per work unit (their accumulators share one TMEM half)
     int halves;               // 2: units ping-pong between two 256-column TMEM halves; 1: one unit owns all 512 columns
     int tiles_per_sample, total_tiles;
+    int tile_rows;            // output rows a tile advances by: 128, or 126 in the dz-stacked form (rows 0 and 127 of a tile are halo)
     int q_first, q_last;
     int ldd;
     int a_stages, w_stages;
@@ -183,7 +184,15 @@ __device__ __forceinline__ void h_tmem_ld32(uint32_t taddr, float* v)
 // the L2 -> SM weight stream was.  The leader CTA issues all MMAs; both CTAs load their own windows / weight halves and
 // run their own epilogue.
 // F16: operands are IEEE half (X and W); a 128-byte chunk row then holds 64 channels and one MMA covers K = 16.
-template <bool PAIR, bool F16>
+// STACK (half operands, Cout <= 64): the three dz-taps of one (dx, dy) are ONE MMA with N = 3 Cout.  At N <= 64 an MMA costs
+// ~49 cycles whatever N is (the 4 KB A-operand fetch from shared memory, tools/ubench/mma_rate.cu), i.e. 35 % (N = 64) to 67 %
+// (N = 32) of the tensor pipe idles; stacking the taps' weight rows -- which already sit contiguously in the sub-slab -- gives
+// 3x fewer MMAs at 2x (N = 192) or 1x (N = 96) the cost each.  The three column groups are the PARTIAL outputs
+//   P_dz[q'] = sum_{dx,dy} X[q' + dx P^2 + dy P] W(dx,dy,dz)         (A rows WITHOUT the dz shift)
+// and the convolution is  out[q] = P_-1[q-1] + P_0[q] + P_+1[q+1]:  a +-1 shift along the TMEM LANES, done in the epilogue with
+// two warp shuffles per value (+ a shared-memory hand-over of the two rows at every warp boundary).  Rows 0 and 127 of a tile
+// have no complete sum, so tiles advance by 126 rows (1.6 % more tiles).
+template <bool PAIR, bool F16, bool STACK>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const HaloArgs a)
 {
@@ -210,6 +219,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
     float* s_stats = reinterpret_cast<float*>(tmem_ptr_smem + 2);  // [2 sets][4][cout][2]
     // epilogue staging tiles: 4 warps x (32 rows x 128 B), 1024-byte aligned for the XOR swizzle
     uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_stats + 2 * 4 * a.cout * 2) + 1023) & ~(uintptr_t)1023);
+    float* s_edge = reinterpret_cast<float*>(sStage + 8 * 4096);   // STACK: [2 sets][4 warps][2][32] boundary rows of the +-1 lane shift
+    const int ncols = STACK ? 3 * a.cout : a.cout;      // accumulator columns of one tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank = 0;
@@ -276,7 +287,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         int tile = tile0 + NC * g + (int)rank;
                         if (tile >= tile_end) tile = tile0;       // dummy slot of an odd range (pair mode)
                         const int b = tile / a.tiles_per_sample;
-                        const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * HBM;
+                        const int q0 = a.q_first + (tile - b * a.tiles_per_sample) * a.tile_rows - (STACK ? 1 : 0);
                         const long long qs = (long long)q0 + (long long)(dx - 1) * a.P2 - (a.P + 1);  // window start row (>= 0)
                         h_mbar_wait(h_smem_u32(&a_empty[ast]), aph ^ 1u);
                         if (!PAIR) {
@@ -319,9 +330,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                             // this CTA's half of the output channels of every tap; completes on the leader's barrier
                             const uint32_t fb = h_smem_u32(&w_full[wst]) & H_PEER_MASK;
                             if (rank == 0) h_mbar_expect_tx(fb, (uint32_t)(2 * sub_bytes));
-                            for (int dz = 0; dz < 3; ++dz)
+                            for (int dz = 0; dz < 3; ++dz) {
+                                // un-stacked: this CTA's half of the rows of every tap.  STACK: the operand is the 3 taps stacked
+                                // ([3 Cout] rows, dz-major); this CTA keeps rows [rank * 1.5 Cout, +1.5 Cout) = three half-tap boxes
+                                const int hb = STACK ? (int)rank * 3 + dz : 2 * dz + (int)rank;      // half-tap index 0..5
                                 h_tma_load_2d_pair(h_smem_u32(sW + (size_t)wst * sub_bytes + (size_t)dz * tap_bytes), &mapW, fb,
-                                                   ((dx * 9 + dy * 3 + dz) * a.cin_chunks + kc) * CHK, (int)rank * (a.cout / 2));
+                                                   ((dx * 9 + dy * 3 + (hb >> 1)) * a.cin_chunks + kc) * CHK, (hb & 1) * (a.cout / 2));
+                            }
                         }
                         if (++wst == a.w_stages) {
                             wst = 0;
@@ -338,7 +353,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         // single elected thread, so there is no per-step warp re-convergence.
         if ((!PAIR || rank == 0) && h_elect_one()) {
             // instruction descriptor: D = f32; A, B = tf32 (format 2) or f16 (format 0), both K-major; N >> 3 @17, M >> 4 @24
-            const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(a.cout >> 3) << 17) |
+            const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((uint32_t)(ncols >> 3) << 17) |
                                    ((uint32_t)((NC * HBM) >> 4) << 24);
             const uint32_t tap_step = (uint32_t)(tap_bytes >> 4);
             const uint32_t sA_lo = (h_smem_u32(sA) & 0x3ffff) >> 4, sW_lo = (h_smem_u32(sW) & 0x3ffff) >> 4;
@@ -364,7 +379,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t b_lo = sW_lo + (uint32_t)wst * w_stride_lo;
                         // first tap (dz = -1) of this dy inside a window, in 16-byte descriptor units (128 B per row)
-                        const uint32_t row_lo = (uint32_t)(((a.P + 1) + (dy - 1) * a.P - 1) * 8);
+                        const uint32_t row_lo = (uint32_t)(((a.P + 1) + (dy - 1) * a.P - (STACK ? 0 : 1)) * 8);
                         int st = ast0;
                         uint32_t aph = aph0;
                         for (int g = 0; g < ntiles; ++g) {
@@ -373,8 +388,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             }
                             const uint32_t a_lo = sA_lo + (uint32_t)st * a_stride_lo + row_lo;
-                            const uint32_t dcol = dcol0 + (uint32_t)(g * a.cout);
+                            const uint32_t dcol = dcol0 + (uint32_t)(g * ncols);
                             const uint32_t first = (uint32_t)((sl | dy) != 0);
+                            if (STACK) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (j < nj) {
+                                        const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (uint32_t)(j * 2));
+                                        const uint64_t bd = DESC_HI | (uint64_t)(b_lo + (uint32_t)(j * 2));
+                                        const uint32_t acc = j != 0 ? 1u : first;
+                                        if (PAIR) h_umma_f16_pair(dcol, ad, bd, idesc, acc);
+                                        else h_umma_f16(dcol, ad, bd, idesc, acc);
+                                    }
+                                }
+                            } else
 #pragma unroll
                             for (int dz = 0; dz < 3; ++dz) {
 #pragma unroll
@@ -423,19 +450,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
         float* s_stats_set = s_stats + (size_t)eset * 4 * a.cout * 2;
         const int r = a.r, r3 = r * r * r;
         int it_unit = 0;
+        int epar = 0;
         for (int tile0 = tile_begin; tile0 < tile_end; tile0 += NC * a.G, ++it_unit) {
             const int ntiles = min(a.G, (tile_end - tile0 + NC - 1) / NC);
             const int h = a.halves == 2 ? (it_unit & 1) : 0;
             const uint32_t use = (uint32_t)(a.halves == 2 ? (it_unit >> 1) : it_unit);
             h_mbar_wait(h_smem_u32(&tmem_full[h]), use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int g = eset; g < ntiles; g += 2) {
+            // two epilogue warp sets alternate over the tiles of a unit -- over the UNITS when a unit is a single tile (G = 1)
+            for (int g = (a.G == 1 ? ((it_unit & 1) == eset ? 0 : 1) : eset); g < ntiles; g += 2) {
                 const int tile = tile0 + NC * g + (int)rank;
                 const bool tile_ok = tile < tile_end;         // false only for the dummy slot of an odd range (pair mode)
                 const int b = tile / a.tiles_per_sample;
-                const int q = a.q_first + (tile - b * a.tiles_per_sample) * HBM + qd * 32 + lane;
+                const int it = qd * 32 + lane;                // row inside the tile = TMEM lane
+                const int q = a.q_first + (tile - b * a.tiles_per_sample) * a.tile_rows - (STACK ? 1 : 0) + it;
                 const int x = q / a.P2, rem = q - x * a.P2, y = rem / a.P, z = rem - y * a.P;
-                const bool ok = tile_ok && q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r;
+                const bool ok = tile_ok && q <= a.q_last && x >= 1 && x <= r && y >= 1 && y <= r && z >= 1 && z <= r &&
+                                (!STACK || (it >= 1 && it <= HBM - 2));
                 const size_t v = (size_t)b * r3 + (size_t)(x - 1) * r * r + (size_t)(y - 1) * r + (size_t)(z - 1);
                 // The valid rows of a tile are CONSECUTIVE dense voxel rows (v enumerates the interior voxels in the same order
                 // as q, pads skipped), so the warp's valid rows are compacted into a 128B-swizzled staging tile and leave as
@@ -449,7 +480,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                 uint8_t* stg = sStage + (size_t)(eset * 4 + qd) * 4096;
                 for (int c = 0; c < a.cout / 32; ++c) {
                     float vv[32];
-                    h_tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * half_cols + g * a.cout + c * 32), vv);
+                    const uint32_t tcol = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(h * half_cols + g * ncols + c * 32);
+                    if (STACK) {
+                        // out[row] = P_-1[row-1] + P_0[row] + P_+1[row+1]: column groups 0 / 1 / 2 of the tile, shifted along the lanes
+                        float vm[32], vp[32];
+                        h_tmem_ld32(tcol, vm);
+                        h_tmem_ld32(tcol + (uint32_t)a.cout, vv);
+                        h_tmem_ld32(tcol + (uint32_t)(2 * a.cout), vp);
+                        float* eb = s_edge + (size_t)((eset * 2 + epar) * 4) * 64;     // [warp][{last row of P_-1, first row of P_+1}][32]
+                        epar ^= 1;         // double-buffered: the barrier of use k+1 separates the reads of use k from the writes of use k+2
+                        if (lane == 31) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(eb + qd * 64 + 4 * j) = make_float4(vm[4 * j], vm[4 * j + 1], vm[4 * j + 2], vm[4 * j + 3]);
+                        }
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(eb + qd * 64 + 32 + 4 * j) = make_float4(vp[4 * j], vp[4 * j + 1], vp[4 * j + 2], vp[4 * j + 3]);
+                        }
+                        if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                        else asm volatile("bar.sync 2, 128;" ::: "memory");
+                        // branch-free: every lane reads the neighbour warps' boundary rows (broadcast), lanes 0 / 31 select them
+                        // (rows 0 and 127 of the tile have no neighbour: they are masked halo rows anyway)
+                        const float4* pu = reinterpret_cast<const float4*>(eb + (qd > 0 ? qd - 1 : qd) * 64);
+                        const float4* pd = reinterpret_cast<const float4*>(eb + (qd < 3 ? qd + 1 : qd) * 64 + 32);
+                        const bool l0 = lane == 0, l31 = lane == 31;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 u = pu[j4], d = pd[j4];
+                            const float ua[4] = {u.x, u.y, u.z, u.w}, da[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int j = 4 * j4 + k;
+                                const float up = __shfl_up_sync(0xffffffffu, vm[j], 1);
+                                const float dn = __shfl_down_sync(0xffffffffu, vp[j], 1);
+                                vv[j] += (l0 ? ua[k] : up) + (l31 ? da[k] : dn);
+                            }
+                        }
+                    } else {
+                        h_tmem_ld32(tcol, vv);
+                    }
                     __syncwarp();              // the previous chunk's readers are done with the staging tile
                     if (ok) {
                         uint8_t* rowp = stg + pos * 128;
@@ -533,6 +604,23 @@ typedef CUresult (*PFN_encodeTiled_h)(CUtensorMap*, CUtensorMapDataType, cuuint3
 // slab is slab 0 of the next sample (or the slack rows after the last sample) -- every out-of-range neighbour of an
 // interior voxel still lands on a zero row, and taps are still constant row shifts dx*P^2 + dy*P + dz.  Compared with
 // padding both sides (P = r + 2) the rows to sweep shrink from (r+2)^3 to (r+1)^3: 17 % fewer tiles at r = 16, 9 % at r = 32.
+// dz-stacked form (see the kernel): half operands, Cout = 32, or Cout = 64 with Cin >= 192.  Measured on B200 (64 patches,
+// tools/bench_halo.py, stacked vs un-stacked): 64(35)->32 @32^3 234 vs 269 us, 32->32 @32^3 225 vs 253, 192->64 @16^3 129 vs 148;
+// but 64->64 @32^3 494 vs 397 and 64->64 @16^3 70 vs 56: with one 192-column tile per TMEM half (G = 1) every tile streams all 27
+// taps' weights again, and the L2 -> SM fill (Little's law: ~100 KB in flight per SM at ~1.5 us) cannot feed 185 KB per 1.9 us tile.
+static inline bool halo_stacked(bool f16, int Cin, int Cout) { return f16 && (Cout == 32 || (Cout == 64 && Cin >= 192)); }
+static int g_halo_stack = 1;      // p2pb_conv_halo_tune(.., .., G): G in [100, 200) = stacking OFF, [200, 300) = stacking forced ON (A/B timing)
+
+// tiles per sample of the kernel variant that will run for (r, Cout, operand type): the stats buffer of p2pb_conv3d_halo* has
+// B * tiles rows
+P2PB_API int p2pb_conv_halo_tiles(int r, int Cin, int Cout, int f16)
+{
+    const int P = r + 1, P2 = P * P;
+    const int q_first = P2 + P + 1, q_last = r * P2 + r * P + r;
+    const int rows = (g_halo_stack == 2 || (g_halo_stack && halo_stacked(f16 != 0, Cin, Cout))) && f16 && (Cout == 32 || Cout == 64) ? HBM - 2 : HBM;
+    return (q_last - q_first + 1 + rows - 1) / rows;
+}
+
 P2PB_API int p2pb_conv_halo_layout(int r, int* P3_out, int* slack_rows_out, int* tiles_per_sample_out)
 {
     const int P = r + 1, P2 = P * P, P3 = P2 * P;
@@ -551,6 +639,14 @@ static int g_halo_pair = 1;   // 1: cta_group::2 CTA pairs when there is enough 
 P2PB_API int p2pb_conv_halo_tune(int w_stages, int a_stages, int G)
 {
     g_halo_w_stages = w_stages; g_halo_a_stages = a_stages;
+    g_halo_stack = 1;
+    if (G >= 200) {                    // 200 + G: dz-stacking forced on for every half-operand Cout in {32, 64} shape
+        g_halo_stack = 2;
+        G -= 200;
+    } else if (G >= 100) {             // 100 + G: dz-stacking off (the round-1 kernel), G tiles per unit (0 = automatic)
+        g_halo_stack = 0;
+        G -= 100;
+    }
     g_halo_pair = G < 0 ? 0 : 1;       // a negative G selects the un-paired kernel with |G| (0 = automatic) tiles per unit
     g_halo_G = G < 0 ? (G == -1 ? 0 : -G) : G;
     return P2PB_OK;
@@ -573,8 +669,11 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     a.W = 128 + 2 * a.P + 2;
     a.q_first = a.P2 + a.P + 1;
     a.q_last = r * a.P2 + r * a.P + r;
-    a.tiles_per_sample = (a.q_last - a.q_first + 1 + HBM - 1) / HBM;
+    const bool stack = f16 && (Cout == 32 || Cout == 64) && (g_halo_stack == 2 || (g_halo_stack && halo_stacked(f16, Cin, Cout)));
+    a.tile_rows = stack ? HBM - 2 : HBM;
+    a.tiles_per_sample = (a.q_last - a.q_first + 1 + a.tile_rows - 1) / a.tile_rows;
     a.total_tiles = B * a.tiles_per_sample;
+    const int ncols = stack ? 3 * Cout : Cout;
     const bool pair_hint = g_halo_pair && a.total_tiles >= 2 * p2pb_num_sms();
     // (half operands in CTA pairs at Cout = 64: G = 2 measured faster than 4 -- 459 vs 526 us at 64 -> 64 @ 32^3 -- the
     // weight stream is already a quarter of the tf32 single-CTA one and shorter units balance better)
@@ -582,23 +681,34 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     // Cout = 128) and units ping-pong between the halves, so the epilogue overlaps the next unit's mainloop (measured at
     // Cout = 128: G = 4 without overlap 467 us, G = 2 with overlap 390 us)
     a.G = (Cout <= 32 || (Cout <= 64 && !(f16 && pair_hint))) ? 4 : 2;
-    if (g_halo_G > 0 && g_halo_G * Cout <= 512) a.G = g_halo_G;
-    a.halves = a.G * Cout <= 256 ? 2 : 1;
+    if (stack) a.G = 256 / ncols;          // 2 tiles (N = 96) or 1 tile (N = 192) per 256-column TMEM half, units ping-pong
+    if (g_halo_G > 0 && g_halo_G * ncols <= 512) a.G = g_halo_G;
+    a.halves = a.G * ncols <= 256 ? 2 : 1;
     a.ldd = ldd;
     a.X = reinterpret_cast<const float*>(X); a.bias = bias; a.D = D; a.stats = stats;
     const int n_sms = p2pb_num_sms();
     const bool pair = g_halo_pair && a.total_tiles >= 2 * n_sms && n_sms >= 2;
     const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * 128;     // per CTA: pair mode keeps half of the output channels
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
-    const int stage_bytes = 8 * 4096 + 1024;      // epilogue staging tiles (+ alignment)
+    const int stage_bytes = 8 * 4096 + 1024 + 4096;      // epilogue staging tiles (+ alignment) + boundary rows of the stacked form
     const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 8 * Cout * 2 * 4 - stage_bytes;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
     a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
+    int a_cap = 2 * a.G;
+    if (stack) {
+        // the stacked mainloop consumes a weight sub-slab in G * 4 MMAs (0.2-0.4 us) and a window in 12 (0.3-0.6 us), 3x faster
+        // than the un-stacked one, while a TMA round trip stays ~1 us: keep ~64 KB of weights and 4-5 windows in flight
+        a_cap = 2 * a.G > 4 ? 2 * a.G : 4;
+        a.w_stages = 8;
+        while (a.w_stages > 3 && a.w_stages * sub_bytes + a_cap * a_stage_stride > budget) --a.w_stages;
+        a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
+        if (a.a_stages > a_cap + 1) a.a_stages = a_cap + 1;
+    }
     if (g_halo_w_stages >= 2) {
         a.w_stages = g_halo_w_stages;
         a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
     }
-    if (a.a_stages > 2 * a.G) a.a_stages = 2 * a.G;
+    if (!stack && a.a_stages > a_cap) a.a_stages = a_cap;
     if (g_halo_a_stages > 0 && g_halo_a_stages < a.a_stages) a.a_stages = g_halo_a_stages;
     P2PB_CHECK_ARG(a.a_stages >= a.G + 1, "conv3d_halo: shared memory budget exceeded (Cout=%d r=%d)", Cout, r);
     const size_t smem = 1024 + (size_t)a.w_stages * sub_bytes + (size_t)a.a_stages * a_stage_stride + 256 + (size_t)8 * Cout * 2 * 4 + stage_bytes;
@@ -640,10 +750,12 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     }
     static bool attr_set = false;
     if (!attr_set) {
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        P2PB_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     if (pair) {
@@ -661,13 +773,15 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_p2pb_pdl ? 2 : 1;
-        if (f16) P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, true>, mapW, mapX, a));
-        else P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, false>, mapW, mapX, a));
+        if (stack) P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, true, true>, mapW, mapX, a));
+        else if (f16) P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, true, false>, mapW, mapX, a));
+        else P2PB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, false, false>, mapW, mapX, a));
     } else {
         int grid = n_sms;
         if (grid > a.total_tiles) grid = a.total_tiles;
-        if (f16) (void)p2pb_launch(conv_halo_kernel<false, true>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
-        else (void)p2pb_launch(conv_halo_kernel<false, false>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
+        if (stack) (void)p2pb_launch(conv_halo_kernel<false, true, true>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
+        else if (f16) (void)p2pb_launch(conv_halo_kernel<false, true, false>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
+        else (void)p2pb_launch(conv_halo_kernel<false, false, false>, dim3(grid), dim3(HALO_THREADS), (size_t)(smem), s, mapW, mapX, a);
     }
     P2PB_LAUNCH_OK();
     return P2PB_OK;

@@ -916,6 +916,19 @@ P2PB_API int p2pb_linear_small(const float* in, int ldi, const float* W, int ldw
 // its own dense [B, cout] buffer, the GEMM epilogue's bias2 operand).  Replaces 2 + (number of folds) linear_small launches.
 // grid (ceil(R / 64), B): every CTA recomputes the 2-layer MLP of its sample (8K FMAs) and produces 64 stacked rows.
 // ---------------------------------------------------------------------------------------------------------
+// dot product of a shared-memory vector with a global weight row, split over TPO consecutive lanes (TPO a power of two <= 32): every
+// thread issues its K / TPO loads back to back (one memory latency per layer instead of one per output), then log2(TPO) shuffles
+template <int TPO>
+__device__ __forceinline__ float dot_tpo(const float* __restrict__ xs, const float* __restrict__ wrow, int K, int sub)
+{
+    float s = 0.f;
+#pragma unroll 4
+    for (int k = sub; k < K; k += TPO) s = fmaf(xs[k], __ldg(wrow + k), s);
+#pragma unroll
+    for (int m = TPO >> 1; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    return s;
+}
+
 __global__ void __launch_bounds__(256) step_vectors_kernel(const float* __restrict__ sin, int ld_sin, const float* __restrict__ w0,
                                                            const float* __restrict__ b0, const float* __restrict__ w2,
                                                            const float* __restrict__ b2, int E, const float* __restrict__ Wall, int R,
@@ -924,39 +937,44 @@ __global__ void __launch_bounds__(256) step_vectors_kernel(const float* __restri
 {
     P2PB_PDL_SYNC();
     __shared__ float s_in[128], s_h[128], s_t[128];
-    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int k = t; k < E; k += 256) s_in[k] = sin[(size_t)b * ld_sin + k];
-    __syncthreads();
-    for (int o = warp; o < E; o += 8) {
-        float s = 0.f;
-        for (int k = lane; k < E; k += 32) s = fmaf(s_in[k], __ldg(w0 + (size_t)o * E + k), s);
-        s = warp_sum(s);
-        if (lane == 0) {
-            s += b0[o];
-            s_h[o] = s > 0.f ? s : 0.1f * s;
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int sub = t & 3, o4 = t >> 2;                 // 4 threads per output, 64 outputs per pass
+    // prefetch this CTA's slice of the stacked fold weights while the two small layers run (independent of them)
+    const int r = blockIdx.x * 64 + o4;
+    float wreg[32];                                     // E <= 128 -> at most 32 values per thread
+    if (r < R) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int k = sub + 4 * i;
+            wreg[i] = k < E ? __ldg(Wall + (size_t)r * E + k) : 0.f;
         }
     }
+    for (int k = t; k < E; k += 256) s_in[k] = sin[(size_t)b * ld_sin + k];
     __syncthreads();
-    for (int o = warp; o < E; o += 8) {
-        float s = 0.f;
-        for (int k = lane; k < E; k += 32) s = fmaf(s_h[k], __ldg(w2 + (size_t)o * E + k), s);
-        s = warp_sum(s);
-        if (lane == 0) {
-            s += b2[o];
+    for (int o = o4; o < E; o += 64) {
+        float s = dot_tpo<4>(s_in, w0 + (size_t)o * E, E, sub) + b0[o];
+        if (sub == 0) s_h[o] = s > 0.f ? s : 0.1f * s;
+    }
+    __syncthreads();
+    for (int o = o4; o < E; o += 64) {
+        const float s = dot_tpo<4>(s_h, w2 + (size_t)o * E, E, sub) + b2[o];
+        if (sub == 0) {
             s_t[o] = s;
             if (blockIdx.x == 0) temb_out[(size_t)b * E + o] = s;
         }
     }
     __syncthreads();
-    const int r0 = blockIdx.x * 64 + warp * 8;
-    for (int i = 0; i < 8; ++i) {
-        const int r = r0 + i;
-        if (r >= R) break;
-        float s = 0.f;
-        for (int k = lane; k < E; k += 32) s = fmaf(s_t[k], __ldg(Wall + (size_t)r * E + k), s);
-        s = warp_sum(s);
-        if (lane == 0) reinterpret_cast<float*>(row_ptr[r])[(size_t)b * row_stride[r]] = s;
+    float s = 0.f;
+    if (r < R) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int k = sub + 4 * i;
+            if (k < E) s = fmaf(s_t[k], wreg[i], s);
+        }
     }
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (r < R && sub == 0) reinterpret_cast<float*>(row_ptr[r])[(size_t)b * row_stride[r]] = s;
 }
 
 P2PB_API int p2pb_step_vectors(const float* sin, int ld_sin, const float* w0, const float* b0, const float* w2, const float* b2, int B,
@@ -983,21 +1001,23 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
     extern __shared__ float s_se[];       // [C] means, [Hd] hidden
     float* s_m = s_se;
     float* s_hid = s_se + C;
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int b = blockIdx.x, t = threadIdx.x;
     for (int k = t; k < C; k += 256) s_m[k] = ym[(size_t)b * C + k];
     __syncthreads();
-    for (int o = warp; o < Hd; o += 8) {
-        float s = 0.f;
-        for (int k = lane; k < C; k += 32) s = fmaf(s_m[k], __ldg(w0 + (size_t)o * C + k), s);
-        s = warp_sum(s);
-        if (lane == 0) s_hid[o] = fmaxf(s, 0.f);
+    {   // hidden layer: 8 threads per output, 32 outputs per pass (Hd = C / 8 <= 64)
+        const int sub = t & 7;
+        for (int o = t >> 3; o < Hd; o += 32) {
+            const float s = dot_tpo<8>(s_m, w0 + (size_t)o * C, C, sub);
+            if (sub == 0) s_hid[o] = fmaxf(s, 0.f);
+        }
     }
     __syncthreads();
-    for (int o = warp; o < C; o += 8) {
+    for (int o = t; o < C; o += 256) {     // gate: one thread per channel, Hd independent loads each
+        const float* wr = w2 + (size_t)o * Hd;
         float s = 0.f;
-        for (int k = lane; k < Hd; k += 32) s = fmaf(s_hid[k], __ldg(w2 + (size_t)o * Hd + k), s);
-        s = warp_sum(s);
-        if (lane == 0) se[(size_t)b * C + o] = 1.0f / (1.0f + __expf(-s));
+#pragma unroll 8
+        for (int k = 0; k < Hd; ++k) s = fmaf(s_hid[k], __ldg(wr + k), s);
+        se[(size_t)b * C + o] = 1.0f / (1.0f + __expf(-s));
     }
 }
 
@@ -1019,6 +1039,9 @@ P2PB_API int p2pb_se_excite(const float* ymean, const float* w0, const float* w2
 // The [B*N, C] activation is never written, the 128 -> 3 projection runs in fp32 FMAs (the reference's Conv1d is TF32).
 // One warp per point: lanes stride the channels (coalesced 128-byte reads), three shuffle reductions.
 // ---------------------------------------------------------------------------------------------------------
+// A warp owns 32 CONSECUTIVE points of one sample: per point the lanes stride the channels (coalesced 16-byte loads, 4 points in
+// flight), the three dot products are reduced by shuffles, and lane j keeps the result of point j -- so the bridge update reads and
+// writes xt / pred_x0 [B,3,N] with unit stride across the warp.
 __global__ void __launch_bounds__(256) head_bridge_kernel(const float* __restrict__ raw, int ldr, const float* __restrict__ A,
                                                           const float* __restrict__ Bc, const float* __restrict__ W,
                                                           const float* __restrict__ bias, int C, int N, long long total,
@@ -1027,31 +1050,43 @@ __global__ void __launch_bounds__(256) head_bridge_kernel(const float* __restric
                                                           float* __restrict__ eps_out, int lde)
 {
     P2PB_PDL_SYNC();
-    const long long pt = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (pt >= total) return;
-    const long long b = pt / N;
-    const int n = (int)(pt - b * N);
-    const float* x = raw + pt * ldr;
+    const int groups_per_sample = (N + 31) >> 5;
+    const long long gw = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;          // warp = (sample, 32-point group)
+    const long long b = gw / groups_per_sample;
+    if (b * N >= total) return;
+    const int n0 = (int)(gw - b * groups_per_sample) << 5;
+    const int cnt = min(32, N - n0);
     const float* a = A + b * C;
     const float* bb = Bc + b * C;
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;      // lane j: eps of point n0 + j
     for (int c = lane * 4; c < C; c += 128) {
-        const float4 xv = *reinterpret_cast<const float4*>(x + c);
         const float4 av = __ldg(reinterpret_cast<const float4*>(a + c)), bv = __ldg(reinterpret_cast<const float4*>(bb + c));
-        const float h0 = swishf(fmaf(xv.x, av.x, bv.x)), h1 = swishf(fmaf(xv.y, av.y, bv.y));
-        const float h2 = swishf(fmaf(xv.z, av.z, bv.z)), h3 = swishf(fmaf(xv.w, av.w, bv.w));
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + c)), w1 = __ldg(reinterpret_cast<const float4*>(W + C + c));
         const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + 2 * C + c));
-        e0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, e0))));
-        e1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, e1))));
-        e2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, e2))));
+        const float* x = raw + ((size_t)b * N + n0) * ldr + c;
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)j * ldr);
+            const float h0 = swishf(fmaf(xv.x, av.x, bv.x)), h1 = swishf(fmaf(xv.y, av.y, bv.y));
+            const float h2 = swishf(fmaf(xv.z, av.z, bv.z)), h3 = swishf(fmaf(xv.w, av.w, bv.w));
+            float e0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, h3 * w0.w)));
+            float e1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, h3 * w1.w)));
+            float e2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, h3 * w2.w)));
+            e0 = warp_sum(e0);
+            e1 = warp_sum(e1);
+            e2 = warp_sum(e2);
+            if (lane == j) {
+                r0 += e0;
+                r1 += e1;
+                r2 += e2;
+            }
+        }
     }
-    e0 = warp_sum(e0);
-    e1 = warp_sum(e1);
-    e2 = warp_sum(e2);
-    if (lane == 0) {
-        const float ev[3] = {e0 + bias[0], e1 + bias[1], e2 + bias[2]};
+    if (lane < cnt) {
+        const int n = n0 + lane;
+        const long long pt = b * N + n;
+        const float ev[3] = {r0 + bias[0], r1 + bias[1], r2 + bias[2]};
         if (eps_out != nullptr) {
             eps_out[pt * lde] = ev[0];
             eps_out[pt * lde + 1] = ev[1];
@@ -1083,7 +1118,8 @@ P2PB_API int p2pb_head_bridge(const float* raw, int ldr, const float* A, const f
     const long long total = (long long)B * N;
     if (total == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)head_bridge_kernel);
-    (void)p2pb_launch(head_bridge_kernel, dim3(p2pb_cdiv(total * 32, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, raw, ldr, A, Bc, W, bias,
+    const long long warps = (long long)B * ((N + 31) / 32);
+    (void)p2pb_launch(head_bridge_kernel, dim3(p2pb_cdiv(warps * 32, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, raw, ldr, A, Bc, W, bias,
                       C, N, total, xt, coef, clip, xt_next, pred_x0, eps_out, lde);
     P2PB_LAUNCH_OK();
     return P2PB_OK;

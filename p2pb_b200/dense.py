@@ -89,11 +89,15 @@ def pack_conv3d_weight(w: torch.Tensor, cin_pad: int, perm: Optional[Sequence[in
 
 
 # ---- halo-reuse conv (csrc/conv_halo.cu): zero-bordered row-major input -------------------------------------------
-def halo_layout(r: int):
-    """(rows per sample P^3, slack rows after the last sample, tiles per sample) of the padded layout."""
+def halo_layout(r: int, cout: Optional[int] = None, f16: bool = True, cin: int = 64):
+    """(rows per sample P^3, slack rows after the last sample, tiles per sample) of the padded layout.  The tile count (= rows
+    of the ``stats`` output per sample) depends on the kernel variant: pass ``cin`` (padded) / ``cout`` / ``f16`` of the convolution."""
+    from ._lib import lib
+
     a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     call("p2pb_conv_halo_layout", int(r), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-    return a.value, b.value, c.value
+    tiles = c.value if cout is None else int(lib().p2pb_conv_halo_tiles(int(r), int(cin), int(cout), int(bool(f16))))
+    return a.value, b.value, tiles
 
 
 def alloc_padded(B: int, C: int, r: int, device, dtype=torch.float32) -> torch.Tensor:

@@ -539,16 +539,17 @@ class Engine:
             dt = torch.float16 if f16 else torch.float32
             sfx = "_f16" if f16 else ""
             c2 = pad64(cout) if f16 else pad32(cout)
-            _, _, tiles = dense.halo_layout(r)
+            _, _, tiles1 = dense.halo_layout(r, cout, f16, cin=cp)          # conv1: padded Cin = cp, conv2: Cin = c2
+            _, _, tiles = dense.halo_layout(r, cout, f16, cin=c2)
             grid = self.padded(f"{name}.grid", B, cp, r, dt)
             # the grid stays all-zero between evaluations: write the occupied voxels, convolve, zero them again
             vox_args = (_p(feats), int(feats.stride(0)), P["cin"], tvox, P["E"], _p(prep["order"]), _p(prep["ind"]),
                         _p(prep["start"]), _p(prep["cnt"]), _p(grid), cp, B, n_pts, r)
             call("p2pb_voxelize_padded_sparse" + sfx, *vox_args, 0, _s())
-            st1 = self.buf(f"{name}.st1", B * tiles, cout, 2)
+            st1 = self.buf(f"{name}.st1", B * tiles1, cout, 2)
             dense.conv3d_halo(grid, P["w1"], P["b1"], B, r, cp, cout, out=raw1, stats=st1, cin_valid=P["cin"] + P["E"])
             call("p2pb_voxelize_padded_sparse" + sfx, *vox_args, 1, _s())
-            A1, B1, _ = self.coef(f"{name}.n1", st1, tiles, P["n1"], cout, r3)
+            A1, B1, _ = self.coef(f"{name}.n1", st1, tiles1, P["n1"], cout, r3)
             act1 = self.padded(f"{name}.act1", B, c2, r, dt)
             if f16:
                 call("p2pb_affine_act_padded_f16", _p(raw1), cout, _p(A1), _p(B1), B, cout, r, _p(act1), c2, _s())

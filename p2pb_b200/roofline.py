@@ -48,7 +48,7 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
     w = (torch.randn(cout, 27 * cin, device=dev, generator=g) / (27 * cin) ** 0.5).to(dt)
     bias = torch.zeros(cout, device=dev)
     out = torch.empty(B * r ** 3, cout, device=dev)
-    _, _, tps = dense.halo_layout(r)
+    _, _, tps = dense.halo_layout(r, cout, HALO_F16, cin=cin)
     stats = torch.zeros(B * tps, cout, 2, device=dev)
     for _ in range(3):
         dense.conv3d_halo(X, w, bias, B, r, cin, cout, out=out, stats=stats)

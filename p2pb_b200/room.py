@@ -126,6 +126,14 @@ def create_patches(room: torch.Tensor, plan: Plan, lo: int, hi: int, npoints: in
     return Patches(xyz, idx, cut)
 
 
+def balanced_batch(n_jobs: int, batch_size: int) -> int:
+    """Largest-needed batch for ceil(n_jobs / batch_size) equally filled sample() calls."""
+    if n_jobs <= 0:
+        return batch_size
+    nb = -(-n_jobs // batch_size)
+    return -(-n_jobs // nb)
+
+
 @dataclass
 class SweepResult:
     denoised: Optional[torch.Tensor]        # f64 [N,3] (average_predictions) or fp32 [N,3] (FPS of all denoised patches); rank 0
@@ -150,6 +158,9 @@ def sweep_shard(model, room: torch.Tensor, npoints: int, k: int, radius: float, 
     acc_steps = [RoomAccumulator(N, dev) for _ in range(steps)] if (intermediate and average_predictions) else None
     loose = []
     nj = hi - lo
+    # balanced batches: the same number of sample() calls as ceil(nj / batch_size), all (nearly) full -- a shard of 261 jobs runs
+    # as 9 x 29 instead of 8 x 32 + 5 padded to 32 (the captured graph has a static batch shape; one shape per sweep)
+    batch_size = balanced_batch(nj, batch_size)
     for s in range(0, nj, batch_size):
         e = min(s + batch_size, nj)
         take = torch.arange(s, e, device=dev)

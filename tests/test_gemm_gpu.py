@@ -166,7 +166,7 @@ def test_conv3d_halo_vs_fp64(B, r, cin, cout):
     w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5
     bias = torch.randn(cout, device="cuda", generator=g)
     X = dense.dense_to_padded(x.permute(0, 2, 3, 4, 1).contiguous(), r)
-    _, _, tps = dense.halo_layout(r)
+    _, _, tps = dense.halo_layout(r, cout, f16=False, cin=cin)
     stats = torch.zeros(B * tps, cout, 2, device="cuda")
     out = torch.full((B * r ** 3, cout), float("nan"), device="cuda")
     dense.conv3d_halo(X, dense.pack_conv3d_weight(w, cin), bias, B, r, cin, cout, out=out, stats=stats)
@@ -179,7 +179,8 @@ def test_conv3d_halo_vs_fp64(B, r, cin, cout):
 
 
 @pytest.mark.parametrize("B,r,cin,cin_valid,cout", [(1, 16, 64, 64, 64), (2, 32, 64, 35, 32), (9, 16, 128, 128, 128), (3, 32, 64, 32, 32),
-                                                    (15, 16, 128, 100, 64)])
+                                                    (15, 16, 128, 100, 64), (5, 32, 64, 64, 64), (9, 16, 192, 192, 64), (12, 32, 64, 35, 32),
+                                                    (1, 16, 64, 64, 32), (64, 16, 64, 64, 64)])
 def test_conv3d_halo_half_operands_vs_fp64(B, r, cin, cin_valid, cout):
     """IEEE-half operand variant (kind::f16, 64 channels per chunk, K-valid MMA skipping), un-paired and CTA-pair
     launches: compared with the fp64 convolution of the SAME half-rounded operands at the tf32 tolerance (half and
@@ -196,7 +197,7 @@ def test_conv3d_halo_half_operands_vs_fp64(B, r, cin, cin_valid, cout):
     bias = torch.randn(cout, device="cuda", generator=g)
     xh, wh = x.half(), w.half()
     X = dense.dense_to_padded(xh.permute(0, 2, 3, 4, 1).contiguous(), r)
-    _, _, tps = dense.halo_layout(r)
+    _, _, tps = dense.halo_layout(r, cout, f16=True, cin=cin)       # Cout = 32 / (Cout = 64, Cin >= 192): the dz-stacked form
     stats = torch.zeros(B * tps, cout, 2, device="cuda")
     out = torch.full((B * r ** 3, cout), float("nan"), device="cuda")
     dense.conv3d_halo(X, dense.pack_conv3d_weight(wh.float(), cin).half(), bias, B, r, cin, cout, out=out, stats=stats,
@@ -319,3 +320,31 @@ def test_step_vectors_se_excite_head_bridge_match_torch():
         if clip:
             p0 = p0.clamp(-3.0, 3.0)
         assert torch.equal(x0, p0) and torch.equal(xn, coef[1] * p0 + coef[2] * (xt * 4))   # same fp32 op order as p2pb.py:155-165,190-213
+
+
+@pytest.mark.parametrize("B,r,cin,cout", [(3, 32, 64, 64), (5, 16, 64, 64), (2, 16, 128, 64)])
+def test_conv3d_halo_stacked_form_forced_equals_default(B, r, cin, cout):
+    """p2pb_conv_halo_tune(0, 0, 200) forces the dz-stacked form (N = 3 Cout per MMA, +-1 lane shift in the epilogue) on the shapes
+    the default dispatch keeps un-stacked: same convolution, fp32-accumulation-order differences only."""
+    from p2pb_b200 import dense
+    from p2pb_b200._lib import lib
+
+    g = torch.Generator(device="cuda").manual_seed(r + cin + cout)
+    x = torch.randn(B, r, r, r, cin, device="cuda", generator=g).half()
+    w = (torch.randn(cout, 27 * cin, device="cuda", generator=g) / (27 * cin) ** 0.5).half()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    X = dense.dense_to_padded(x, r)
+    outs = []
+    for G in (0, 200, 100):
+        assert lib().p2pb_conv_halo_tune(0, 0, G) == 0
+        try:
+            _, _, tps = dense.halo_layout(r, cout, True, cin=cin)
+            st = torch.zeros(B * tps, cout, 2, device="cuda")
+            out = torch.full((B * r ** 3, cout), float("nan"), device="cuda")
+            dense.conv3d_halo(X, w, bias, B, r, cin, cout, out=out, stats=st)
+            outs.append((out, st.view(B, tps, cout, 2).sum(1)))
+        finally:
+            lib().p2pb_conv_halo_tune(0, 0, 0)
+    for out, st in outs[1:]:
+        assert torch.allclose(out, outs[0][0], rtol=1e-4, atol=1e-4)
+        assert torch.allclose(st, outs[0][1], rtol=1e-4, atol=1e-2)

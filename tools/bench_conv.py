@@ -34,7 +34,7 @@ for r, cin, cout in shapes:
     th = float("nan")
     if r >= 16 and cout <= 128:
         X = dense.dense_to_padded(grid, r)
-        _, _, tps = dense.halo_layout(r)
+        _, _, tps = dense.halo_layout(r, cout, False)
         hst = torch.zeros(B * tps, cout, 2, device="cuda")
         th = timeit(lambda: dense.conv3d_halo(X, wp, bias, B, r, cin, cout, out=out, stats=hst))
     fl = 2.0 * B * r ** 3 * 27 * cin * cout

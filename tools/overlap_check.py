@@ -11,7 +11,7 @@ B, r, cin, cout = 32, 32, 64, 64
 grid = torch.randn(B, r, r, r, cin, device="cuda")
 wp = dense.pack_conv3d_weight(torch.randn(cout, cin, 3, 3, 3, device="cuda") / 40, cin)
 bias = torch.randn(cout, device="cuda"); out = torch.empty(B * r ** 3, cout, device="cuda")
-X = dense.dense_to_padded(grid, r); _, _, tps = dense.halo_layout(r)
+X = dense.dense_to_padded(grid, r); _, _, tps = dense.halo_layout(r, cout, False)
 hst = torch.zeros(B * tps, cout, 2, device="cuda")
 M, C = 32 * 2048 * 8, 64
 x = torch.randn(M, C, device="cuda"); y = torch.empty_like(x)
