@@ -758,6 +758,9 @@ __global__ void __launch_bounds__(256) group_project_kernel(const float* __restr
                                                             __half* __restrict__ out, int ldo, int C, int N, int M, int total_centers)
 {
     P2PB_PDL_SYNC();
+    // The kernel is instruction-bound (a gather of L2-resident rows): every lane owns TWO adjacent channels per 64-channel pass,
+    // so the four shuffles that broadcast neighbour k's (index, dx, dy, dz) are shared by 64 channels, the gather is one 8-byte
+    // load and the half output one 4-byte store per lane.
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= total_centers) return;
     const int b = warp / M, j = warp - b * M;
@@ -765,33 +768,41 @@ __global__ void __launch_bounds__(256) group_project_kernel(const float* __restr
     const float cx = centers[((size_t)b * 3 + 0) * M + j], cy = centers[((size_t)b * 3 + 1) * M + j], cz = centers[((size_t)b * 3 + 2) * M + j];
     const int my_src = idx[(size_t)warp * 32 + lane];
     const float mdx = co[my_src] - cx, mdy = co[my_src + N] - cy, mdz = co[my_src + 2 * N] - cz;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        const int c = c0 + lane;
-        const float wx = Wx[c * 3], wy = Wx[c * 3 + 1], wz = Wx[c * 3 + 2];
-        float a = 0.f, bb = 0.f;
+    const float* pf_b = Pf + (size_t)b * N * ldp;
+    for (int c0 = 0; c0 < C; c0 += 64) {
+        const int c = c0 + 2 * lane;
+        const bool act = c < C;                         // C % 32 == 0: the last pass of C = 32 (mod 64) uses half of the lanes
+        const int cc = act ? c : 0;
+        const float wx0 = Wx[cc * 3], wy0 = Wx[cc * 3 + 1], wz0 = Wx[cc * 3 + 2];
+        const float wx1 = Wx[cc * 3 + 3], wy1 = Wx[cc * 3 + 4], wz1 = Wx[cc * 3 + 5];
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
         if (MODE == 1) {
-            a = A[(size_t)b * C + c];
-            bb = Bc[(size_t)b * C + c];
+            const float2 av = *reinterpret_cast<const float2*>(A + (size_t)b * C + cc), bv = *reinterpret_cast<const float2*>(Bc + (size_t)b * C + cc);
+            a0 = av.x; a1 = av.y; b0 = bv.x; b1 = bv.y;
         }
-        float s1 = 0.f, s2 = 0.f;
+        float s10 = 0.f, s20 = 0.f, s11 = 0.f, s21 = 0.f;
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) {
             const int src = __shfl_sync(0xffffffffu, my_src, k);
             const float dx = __shfl_sync(0xffffffffu, mdx, k), dy = __shfl_sync(0xffffffffu, mdy, k), dz = __shfl_sync(0xffffffffu, mdz, k);
-            float v = Pf[((size_t)b * N + src) * ldp + c];
-            v = fmaf(wx, dx, v);
-            v = fmaf(wy, dy, v);
-            v = fmaf(wz, dz, v);
+            const float2 pv = *reinterpret_cast<const float2*>(pf_b + (size_t)src * ldp + cc);
+            float v0 = fmaf(wx0, dx, pv.x), v1 = fmaf(wx1, dx, pv.y);
+            v0 = fmaf(wy0, dy, v0);
+            v1 = fmaf(wy1, dy, v1);
+            v0 = fmaf(wz0, dz, v0);
+            v1 = fmaf(wz1, dz, v1);
             if (MODE == 0) {
-                s1 += v;
-                s2 = fmaf(v, v, s2);
+                s10 += v0;
+                s20 = fmaf(v0, v0, s20);
+                s11 += v1;
+                s21 = fmaf(v1, v1, s21);
             } else {
-                const float sv = swishf(fmaf(v, a, bb));
-                half_range_check(fabsf(sv));
-                out[((size_t)warp * 32 + k) * ldo + c] = __float2half_rn(sv);
+                const float y0 = swishf(fmaf(v0, a0, b0)), y1 = swishf(fmaf(v1, a1, b1));
+                half_range_check(fmaxf(fabsf(y0), fabsf(y1)));
+                if (act) *reinterpret_cast<__half2*>(out + ((size_t)warp * 32 + k) * ldo + c) = __floats2half2_rn(y0, y1);
             }
         }
-        if (MODE == 0) *reinterpret_cast<float2*>(stats + ((size_t)warp * C + c) * 2) = make_float2(s1, s2);
+        if (MODE == 0 && act) *reinterpret_cast<float4*>(stats + ((size_t)warp * C + c) * 2) = make_float4(s10, s20, s11, s21);
     }
 }
 
@@ -802,7 +813,8 @@ P2PB_API int p2pb_group_project(const float* Pf, int ldp, const float* Wx, const
                                 int mode, void* stream)
 {
     P2PB_CHECK_ARG(U == 32 && C % 32 == 0 && C > 0, "group_project: needs 32 neighbours per centre and C %% 32 == 0 (U=%d C=%d)", U, C);
-    P2PB_CHECK_ARG(mode == 0 ? stats != nullptr : (out != nullptr && A != nullptr && Bc != nullptr && ldo >= C), "group_project: bad outputs for mode %d", mode);
+    P2PB_CHECK_ARG(mode == 0 ? stats != nullptr : (out != nullptr && A != nullptr && Bc != nullptr && ldo >= C && ldo % 2 == 0), "group_project: bad outputs for mode %d", mode);
+    P2PB_CHECK_ARG(ldp % 2 == 0, "group_project: ldp=%d must be even", ldp);
     const long long total = (long long)B * M;
     if (total == 0) return P2PB_OK;
     P2PB_CHECK_U32(total * 32, "group_project");

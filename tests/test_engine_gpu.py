@@ -450,3 +450,39 @@ def test_half_operand_guard_activation_overflow_switches_to_tf32_storage():
         warnings.simplefilter("error")
         out2 = model.sample(x_start=x, steps=2, log_count=2, verbose=False)["x_pred"]
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("C", [32, 64, 96, 128])
+def test_group_project_matches_torch(C):
+    """First set-abstraction layer in gather-after-GEMM form: v = Pf[idx] + Wx.(xyz[idx] - centre); mode 0 = per-centre GroupNorm
+    partials, mode 1 = swish(v*A + B) as IEEE-half rows.  Against plain torch fp32 (C = 32 / 96: the half-used last 64-channel pass)."""
+    import ctypes
+
+    from p2pb_b200._lib import call
+
+    vp = ctypes.c_void_p
+    p = lambda t: vp(t.data_ptr()) if t is not None else vp(0)
+    s = vp(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(C)
+    B, N, M, K = 3, 300, 37, 32
+    Pf = torch.randn(B * N, C, device="cuda", generator=g)
+    Wx = torch.randn(C, 3, device="cuda", generator=g)
+    coords = torch.randn(B, 3, N, device="cuda", generator=g)
+    centers = torch.randn(B, 3, M, device="cuda", generator=g)
+    idx = torch.randint(0, N, (B, M, K), device="cuda", generator=g, dtype=torch.int32)
+    A = torch.randn(B, C, device="cuda", generator=g)
+    Bc = torch.randn(B, C, device="cuda", generator=g)
+    bi = torch.arange(B, device="cuda")[:, None, None]
+    pf = Pf.view(B, N, C)[bi, idx.long()]                                             # [B,M,K,C]
+    rel = coords.permute(0, 2, 1)[bi, idx.long()] - centers.permute(0, 2, 1)[:, :, None, :]   # [B,M,K,3]
+    v = pf + rel @ Wx.t()
+    stats = torch.zeros(B * M, C, 2, device="cuda")
+    call("p2pb_group_project", p(Pf), C, p(Wx), p(coords), p(centers), p(idx), vp(0), vp(0), p(stats), vp(0), 0, B, C, N, M, K, 0, s)
+    assert torch.allclose(stats[..., 0].view(B, M, C), v.sum(2), atol=1e-3, rtol=1e-4)
+    assert torch.allclose(stats[..., 1].view(B, M, C), (v * v).sum(2), atol=1e-3, rtol=1e-4)
+    ldo = (C + 63) // 64 * 64
+    out = torch.zeros(B * M * K, ldo, device="cuda", dtype=torch.float16)
+    call("p2pb_group_project", p(Pf), C, p(Wx), p(coords), p(centers), p(idx), p(A), p(Bc), vp(0), p(out), ldo, B, C, N, M, K, 1, s)
+    ref = torch.nn.functional.silu(v * A[:, None, None, :] + Bc[:, None, None, :]).reshape(B * M * K, C)
+    assert torch.allclose(out[:, :C].float(), ref, atol=2e-3, rtol=2e-3)
+    assert int(out[:, C:].count_nonzero()) == 0
