@@ -82,6 +82,7 @@ def patch_based_denoise(model, pcl_noisy: torch.Tensor, patch_size: int, seed_k:
 def sample(cfg) -> None:
     torch.manual_seed(cfg.seed)
     np.random.seed(cfg.seed)
+    torch.cuda.set_device(cfg.gpu)           # --gpu cuda:1: buffers, streams and graph capture all on that device
     model, _ = load_diffusion(cfg)
     model.eval()
     if cfg.data_path.endswith("ply"):

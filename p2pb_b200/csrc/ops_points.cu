@@ -275,6 +275,152 @@ static int launch_fps_cluster(const float* coords, int B, int N, int M, int* idx
     return P2PB_OK;
 }
 
+// Whole-GPU FPS for clouds beyond the cluster kernel's capacity (room-sized: 2*10^5 .. 2*10^6 points; the patch-centre planner of
+// denoise_room draws ~10^3 centres from 2 M points): a cooperative grid of one CTA per SM, every CTA keeps its contiguous chunk of
+// points AND running distances in shared memory (16 B per point, <= 13 800 points per CTA), per iteration: local argmax ->
+// {key, x, y, z} into this CTA's global slot -> one grid barrier (arrive counter + generation flag) -> every CTA reduces the <= 148
+// slots and continues with the winner's coordinates.  ~2.5 us per iteration instead of ~300 us for the one-CTA global-memory scan
+// (0.3 s -> 3 ms for the planner of a 2 M-point room).  Same selection key as every other FPS kernel here: bit-identical indices.
+struct FpsGridSlot {
+    unsigned long long key;
+    float x, y, z, pad;
+};
+
+__device__ __forceinline__ void fps_grid_barrier(unsigned* count, volatile unsigned* gen, unsigned nblocks, unsigned& local_gen)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(count, 1u);
+        if (prev == nblocks - 1) {
+            *count = 0;
+            __threadfence();
+            atomicAdd(const_cast<unsigned*>(gen), 1u);
+        } else {
+            while (*gen == local_gen) {
+            }
+        }
+        __threadfence();
+    }
+    ++local_gen;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1) fps_grid_kernel(const float* __restrict__ coords, int N, int M, int chunk,
+                                                           FpsGridSlot* __restrict__ slots, unsigned* __restrict__ bar,
+                                                           int* __restrict__ idx)
+{
+    extern __shared__ float s_pts[];                 // [4][chunk]: x, y, z, running min distance
+    __shared__ unsigned long long s_warp[32];
+    __shared__ int s_warp_loc[32];
+    __shared__ FpsGridSlot s_win;
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, NW = T >> 5;
+    const int nb = gridDim.x, cta = blockIdx.x;
+    const int k0 = cta * chunk;
+    const int n_loc = max(0, min(chunk, N - k0));
+    float* sx = s_pts, *sy = s_pts + chunk, *sz = s_pts + 2 * chunk, *sd = s_pts + 3 * chunk;
+    for (int i = t; i < n_loc; i += T) {
+        sx[i] = coords[k0 + i];
+        sy[i] = coords[k0 + i + N];
+        sz[i] = coords[k0 + i + 2 * N];
+        sd[i] = 1e38f;
+    }
+    float x1 = coords[0], y1 = coords[N], z1 = coords[2 * N];
+    if (cta == 0 && t == 0) idx[0] = 0;
+    unsigned local_gen = 0;
+    __syncthreads();
+    for (int j = 1; j < M; ++j) {
+        unsigned long long best = 0ull;
+        int best_loc = 0;
+        for (int i = t; i < n_loc; i += T) {
+            const float d = sqdist3(sx[i] - x1, sy[i] - y1, sz[i] - z1);
+            const float d2 = fminf(d, sd[i]);
+            sd[i] = d2;
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(d2) << 32) | fps_tie_key(k0 + i);
+            if (cand > best) {
+                best = cand;
+                best_loc = i;
+            }
+        }
+        const unsigned long long wbest = warp_max_u64(best);
+        const unsigned owner = __ballot_sync(0xffffffffu, best == wbest && best != 0ull);
+        const int wloc = __shfl_sync(0xffffffffu, best_loc, owner ? (__ffs(owner) - 1) : 0);
+        if (lane == 0) {
+            s_warp[warp] = wbest;
+            s_warp_loc[warp] = wloc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long v = lane < NW ? s_warp[lane] : 0ull;
+            const unsigned long long cbest = warp_max_u64(v);
+            const unsigned own = __ballot_sync(0xffffffffu, v == cbest && lane < NW);
+            const int loc = s_warp_loc[own ? (__ffs(own) - 1) : 0];
+            if (lane == 0) {
+                FpsGridSlot o;
+                o.key = cbest;
+                o.x = cbest != 0ull ? sx[loc] : 0.f;
+                o.y = cbest != 0ull ? sy[loc] : 0.f;
+                o.z = cbest != 0ull ? sz[loc] : 0.f;
+                o.pad = 0.f;
+                slots[(size_t)(j & 1) * nb + cta] = o;
+            }
+        }
+        fps_grid_barrier(bar, bar + 1, (unsigned)nb, local_gen);
+        // every CTA picks the same winner among the nb candidates (warp 0: up to 5 slots per lane for 148 CTAs)
+        if (warp == 0) {
+            unsigned long long win = 0ull;
+            int wr = 0;
+            for (int r = lane; r < nb; r += 32) {
+                const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(&slots[(size_t)(j & 1) * nb + r].key);
+                if (v > win) {
+                    win = v;
+                    wr = r;
+                }
+            }
+            const unsigned long long gwin = warp_max_u64(win);
+            const unsigned own = __ballot_sync(0xffffffffu, win == gwin);
+            const int src = __ffs(own) - 1;
+            const int wcta = __shfl_sync(0xffffffffu, wr, src);
+            if (lane == 0) {
+                const volatile FpsGridSlot* w = &slots[(size_t)(j & 1) * nb + wcta];
+                s_win.key = gwin;
+                s_win.x = w->x;
+                s_win.y = w->y;
+                s_win.z = w->z;
+                if (cta == 0) idx[j] = fps_key_to_index((unsigned)gwin);
+            }
+        }
+        __syncthreads();
+        x1 = s_win.x;
+        y1 = s_win.y;
+        z1 = s_win.z;
+    }
+}
+
+// one cloud; scratch: >= 2 * grid * 32 B slots + 8 B barrier (the B*N-float scratch of the ABI is ample)
+static int launch_fps_grid(const float* coords, int N, int M, int* idx, float* scratch, cudaStream_t s)
+{
+    int grid = p2pb_num_sms();
+    int chunk = ((N + grid - 1) / grid + 31) & ~31;
+    const size_t smem = (size_t)4 * chunk * sizeof(float);
+    if (smem > 216 * 1024) return P2PB_ERR_UNSUPPORTED;
+    grid = (N + chunk - 1) / chunk;
+    P2PB_CUDA_OK(cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(216 * 1024)));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fps_grid_kernel, 1024, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        return P2PB_ERR_UNSUPPORTED;
+    }
+    FpsGridSlot* slots = reinterpret_cast<FpsGridSlot*>(scratch);
+    unsigned* bar = reinterpret_cast<unsigned*>(slots + 2 * (size_t)grid);
+    P2PB_CUDA_OK(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), s));
+    void* args[] = {(void*)&coords, (void*)&N, (void*)&M, (void*)&chunk, (void*)&slots, (void*)&bar, (void*)&idx};
+    // cooperative launch: the runtime guarantees that all CTAs are co-resident (the grid barrier spins)
+    P2PB_CUDA_OK(cudaLaunchCooperativeKernel((const void*)fps_grid_kernel, dim3((unsigned)grid), dim3(1024), args, smem, s));
+    P2PB_LAUNCH_OK();
+    return P2PB_OK;
+}
+
 template <int P, int T>
 static int launch_fps_reg(const float* coords, int B, int N, int M, int* idx, float* centers, cudaStream_t s)
 {
@@ -337,6 +483,12 @@ P2PB_API int p2pb_furthest_point_sampling(const float* coords, int B, int N, int
     if (N <= 16384) return launch_fps_reg<16, 1024>(coords, B, N, M, idx, centers, s);
     P2PB_CHECK_ARG(scratch != nullptr, "fps: N=%d > 16384 needs a B*N float scratch buffer", N);
     P2PB_CHECK_ARG(centers == nullptr, "fps: fused centre gather only for N <= 16384");
+    if (g_fps_cluster && N > 16 * 12288) {       // room-sized clouds: the whole GPU on one cloud (cooperative grid kernel)
+        int rc = P2PB_OK;
+        for (int b = 0; b < B && rc == P2PB_OK; ++b)
+            rc = launch_fps_grid(coords + (size_t)b * 3 * N, N, M, idx + (size_t)b * M, scratch + (size_t)b * N, s);
+        if (rc != P2PB_ERR_UNSUPPORTED) return rc;
+    }
     p2pb_prefer_max_smem((const void*)fps_global_kernel);
     (void)p2pb_launch(fps_global_kernel, dim3(B), dim3(1024), (size_t)(0), s, coords, N, M, scratch, idx);
     P2PB_LAUNCH_OK();

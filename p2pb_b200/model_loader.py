@@ -59,7 +59,15 @@ def load_diffusion(cfg) -> tuple:
             if cfg.get("use_ema", False) and ema_dict and model.ema is not None:
                 ema_dict = {k.replace("ema_model.module.", "ema_model.").replace("online_model.module.", "online_model."): v
                             for k, v in ema_dict.items()}
-                model.ema.load_state_dict(ema_dict, strict=False)
+                # ema_pytorch keeps bookkeeping buffers this minimal holder does not have (and vice versa): load non-strictly,
+                # but a key mismatch INSIDE ema_model (the weights that are evaluated) is an error, not a silent skip
+                res = model.ema.load_state_dict(ema_dict, strict=False)
+                bad = [k for k in list(res.missing_keys) + list(res.unexpected_keys) if k.startswith("ema_model.")]
+                if bad:
+                    raise RuntimeError(f"EMA weights do not match the model: {bad[:8]}{' ...' if len(bad) > 8 else ''}")
+                other = [k for k in list(res.missing_keys) + list(res.unexpected_keys) if not k.startswith("ema_model.")]
+                if other:
+                    logger.info(f"EMA bookkeeping keys not loaded: {other[:6]}{' ...' if len(other) > 6 else ''}")
                 logger.success("Loaded EMA from checkpoint!")
             logger.success("Loaded Model from checkpoint!")
         except RuntimeError as e:

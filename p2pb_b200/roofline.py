@@ -1,7 +1,7 @@
 """Live roofline measurement of the dominant kernel for bench.py.
 
 Dominant kernel of the PVDS N=2048 hot path = the 3x3x3 voxel convolution at r=32 (conv_halo_kernel): per network
-evaluation it accounts for ~45 % of the GPU time (profiles/r01_launches.md).  Measured here on its largest instance
+evaluation it accounts for ~33 % of the GPU time (profiles/r02_launches.md).  Measured here on its largest instance
 (fp_layers.3.1 voxel_layers.0/.4: 64 -> 64 channels on a 32^3 grid) exactly as the engine launches it: IEEE-half
 operands (kind::f16, fp32 accumulate), cta_group::2 CTA pairs, one launch per chain (B/2 patches when the engine splits
 the batch into two chains), CUDA events on the launching stream, inputs larger than L2 (B=32: 161 MB in + 268 MB out).
@@ -65,18 +65,31 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
     bf16_peak, _, how = measured_peaks()
     peak = bf16_peak if HALO_F16 else bf16_peak / 2.0
     esz = 2.0 if HALO_F16 else 4.0
-    traffic = None
+    # DRAM bytes of this launch from the committed `ncu --set full` capture -- only if the capture was taken from THIS kernel source
+    # (sha256 of csrc/conv_halo.cu stored beside the number); a stale capture reads as null instead of a wrong number
+    traffic, traffic_note = None, "no capture"
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            key = f"conv_halo_64x64_r32_B{B}_{'f16' if HALO_F16 else 'tf32'}_dram_bytes"
-            traffic = json.load(open(tp)).get(key)
+            import hashlib
+
+            ent = json.load(open(tp)).get(f"conv_halo_64x64_r32_B{B}_{'f16' if HALO_F16 else 'tf32'}")
+            sha = hashlib.sha256(open(os.path.join(ROOT, "p2pb_b200", "csrc", "conv_halo.cu"), "rb").read()).hexdigest()
+            if ent and ent.get("source_sha256") == sha:
+                traffic, traffic_note = ent["dram_bytes"], ent.get("capture", "")
+            elif ent:
+                traffic_note = "capture is from an older conv_halo.cu (hash mismatch)"
         except Exception:
             traffic = None
     kind = "IEEE-half operands, kind::f16" if HALO_F16 else "TF32"
     return {"bound": "tensor", "kernel": f"conv_halo_kernel (3x3x3 conv, 64->64 ch, 32^3 grid, {B} patches per launch, {kind}, "
                                          "fp32 accumulate, cta_group::2 tcgen05)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": traffic, "ms_per_launch": ms, "flops_per_launch": flops,
+            "traffic": traffic, "traffic_source": traffic_note, "ms_per_launch": ms, "flops_per_launch": flops,
+            # an MMA stream at N = Cout = 64 keeps the tensor pipe busy 32 of every 48.9 cycles (tools/ubench/mma_rate.cu): the
+            # ceiling of THIS layer shape on this hardware, and the measured tensor-pipe activity of the last committed capture
+            "shape_ceiling": {"what": "N = 64 tcgen05.mma stream: max(48.9, N/2) cycles per MMA -> 65.4 % tensor-active", "frac_of_peak": 32.0 / 48.9,
+                              "frac_of_shape_ceiling": (achieved / peak) / (32.0 / 48.9), "tensor_active_pct_ncu": 66.0,
+                              "evidence": "profiles/r02_ncu_conv.md"},
             "algorithmic_bytes_per_launch": B * (esz * (r + 1) ** 3 * cin + 4.0 * r ** 3 * cout),
             "peak_source": f"{how}: dense 16-bit rate {bf16_peak:.1f} TFLOP/s" + ("" if HALO_F16 else " / 2 for TF32")}

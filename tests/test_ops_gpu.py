@@ -209,6 +209,25 @@ def test_fps_cluster_kernel_bit_exact(B, N, M, snap):
         lib().p2pb_fps_set_cluster(1)
 
 
+@pytest.mark.parametrize("B,N,M,snap", [(1, 400000, 300, None), (1, 1000003, 64, 32), (2, 250000, 100, None)])
+def test_fps_grid_kernel_bit_exact(B, N, M, snap):
+    """Whole-GPU cooperative FPS (one CTA per SM, grid barrier per iteration) for room-sized clouds: indices identical to the oracle
+    (reference tie-break; heavy ties on the snapped lattice) and to the one-CTA global-memory kernel."""
+    from oracle import ops as OO
+    from p2pb_b200 import ops
+    from p2pb_b200._lib import lib
+
+    coords = cloud(B, N, seed=N + M, snap=snap)
+    cd = coords.cuda()
+    idx = ops.furthest_point_sampling(cd, M)
+    assert torch.equal(idx.cpu(), OO.furthest_point_sampling_forward(coords, M))
+    lib().p2pb_fps_set_cluster(0)          # one CTA per cloud, distances in global memory
+    try:
+        assert torch.equal(ops.furthest_point_sampling(cd, M), idx)
+    finally:
+        lib().p2pb_fps_set_cluster(1)
+
+
 @pytest.mark.parametrize("N,P,radius", [(50000, 37, 0.2), (3000, 5, 10.0), (4097, 9, 0.0)])
 def test_radius_query_matches_oracle(N, P, radius):
     """Device radius query (count + index-ordered fill) == oracle CSR, bit for bit (incl. 'everything' and 'only the centre')."""
