@@ -229,12 +229,21 @@ def test_denoise_object_entry_point_end_to_end(tmp_path):
     out = np.loadtxt(str(tmp_path / "out.xyz"))
     assert out.shape == (6144, 3) and np.isfinite(out).all()
     assert np.abs(np.linalg.norm(out, axis=1) - 1.0).mean() < 0.1      # still the noisy unit sphere, moved a little
-    # ---- value check: the same pipeline with the patch extraction and the merge done by the CPU restatement of the reference's
-    # host code (denoise_object.py:64-122; models/evaluation.py:297-311 FPS from index 0, truncated; pytorch3d knn_points contract:
-    # K nearest, ascending) around the SAME network.  FPS / kNN kernels are bit-exact to the oracle and the engine is deterministic,
-    # so the written cloud must equal the oracle-built one to the precision of the "%8f" text format.
+    # ---- value check: the same pipeline with the patch extraction (seed FPS, kNN-2048) and the merge FPS done by the CPU restatement
+    # of the reference's host code (denoise_object.py:64-122; models/evaluation.py:297-311 FPS from index 0, truncated; pytorch3d
+    # knn_points contract: K nearest, ascending) around the SAME network and the same torch normalisation.  The FPS / kNN kernels are
+    # bit-exact to the oracle and the engine is deterministic, so the written cloud must equal the oracle-built one to the precision
+    # of the "%8f" text format.
     from oracle import ops as OO
     from p2pb_b200.model_loader import load_diffusion
+
+    def o_fps(pcls, num_pnts):
+        idx = OO.furthest_point_sampling_forward(pcls.cpu().transpose(1, 2).contiguous().float(), num_pnts).long().to(pcls.device)
+        return torch.gather(pcls, 1, idx.unsqueeze(-1).expand(-1, -1, 3)), [i for i in idx]
+
+    def o_knn(seeds, pcl, K):
+        idx, _ = OO.knn_points(seeds.cpu(), pcl.cpu(), K)
+        return pcl[idx.long().to(pcl.device)]
 
     a = D.parse_args(["--data_path", str(tmp_path / "in.xyz"), "--save_path", str(tmp_path / "out2.xyz"),
                       "--model_path", str(tmp_path / "step_0.pth"), "--steps", "3"])
@@ -242,20 +251,13 @@ def test_denoise_object_entry_point_end_to_end(tmp_path):
     model.eval()
     pcl = torch.tensor(np.loadtxt(str(tmp_path / "in.xyz")), dtype=torch.float32)
     pcl, center, scale_n = D.normalize_unit_sphere(pcl)
-    N, K = pcl.shape[0], 2048
-    P = int(a.k * N / K)
-    seeds = pcl[OO.furthest_point_sampling_forward(pcl.t().contiguous()[None], P)[0].long()]
-    kidx, _ = OO.knn_points(seeds, pcl, K)
-    patches = pcl[kidx.long()]
-    centers = patches.mean(dim=1, keepdim=True)
-    patches = patches - centers
-    sc = torch.max(torch.norm(patches, dim=-1))
-    patches = patches / sc
-    den = model.sample(x_start=patches.transpose(1, 2).contiguous().cuda(), use_ema=a.use_ema, steps=a.steps, log_count=a.steps,
-                       verbose=False)["x_pred"].cpu().transpose(1, 2) * sc + centers
-    allp = den.reshape(-1, 3)
-    midx = OO.furthest_point_sampling_forward(allp.t().contiguous()[None], N)[0].long()
-    ref = (allp[midx] * scale_n + center).numpy()
+    orig = (D.farthest_point_sampling, D.knn_patches)
+    D.farthest_point_sampling, D.knn_patches = o_fps, o_knn
+    try:
+        den = D.patch_based_denoise(model, pcl.to(a.gpu), patch_size=2048, seed_k=a.k, cfg=a).cpu()
+    finally:
+        D.farthest_point_sampling, D.knn_patches = orig
+    ref = (den * scale_n + center).numpy()
     assert np.abs(out - ref).max() <= 1.5e-6, np.abs(out - ref).max()
 
 
