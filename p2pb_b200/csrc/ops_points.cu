@@ -443,7 +443,7 @@ P2PB_API int p2pb_fps_set_shape(int shape)
 // development aid / cross-check: 0 = never use the cluster kernel, 1 = for whole clouds (default), 2 = also for patches > 2048 points
 P2PB_API int p2pb_fps_set_cluster(int on)
 {
-    g_fps_cluster = on < 0 ? 0 : (on > 2 ? 2 : on);
+    g_fps_cluster = on < 0 ? 0 : (on > 3 ? 3 : on);        // 3: development aid -- whole-GPU grid kernel for every cloud of more than 16384 points
     return P2PB_OK;
 }
 
@@ -466,6 +466,12 @@ P2PB_API int p2pb_furthest_point_sampling(const float* coords, int B, int N, int
     if (N <= 512) return launch_fps_reg<2, 256>(coords, B, N, M, idx, centers, s);
     if (N <= 1024) return launch_fps_reg<4, 256>(coords, B, N, M, idx, centers, s);
     if (N <= 2048) return launch_fps_reg<8, 256>(coords, B, N, M, idx, centers, s);
+    if (g_fps_cluster == 3 && N > 16384 && centers == nullptr && scratch != nullptr) {
+        int rc = P2PB_OK;
+        for (int b = 0; b < B && rc == P2PB_OK; ++b)
+            rc = launch_fps_grid(coords + (size_t)b * 3 * N, N, M, idx + (size_t)b * M, scratch + (size_t)b * N, s);
+        if (rc != P2PB_ERR_UNSUPPORTED) return rc;
+    }
     if (g_fps_cluster) {
         // Whole clouds (N > 16384): 16 CTAs x 1024 threads.  For patches (N <= 16384) one cluster barrier per iteration costs
         // as much (~1.1 us) as the whole register-resident iteration of fps_reg_kernel, so those keep one CTA per patch
