@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2pb_b200.so")
+# P2PB_LIB: development aid (A/B of two builds of the library on the same box, tools/gpu_ab.sh)
+LIB_PATH = os.environ.get("P2PB_LIB") or os.path.join(_HERE, "libp2pb_b200.so")
 
 _lib = None
 

@@ -373,39 +373,46 @@ __device__ __forceinline__ float4 affine4(float4 x, float4 a, float4 b)
     return y;
 }
 
-// 4 float4 per thread (all loads issued before the first use): the pass is HBM-bound and one 16-byte load per thread
-// does not keep enough bytes in flight (measured 4.0 TB/s with 1, see profiles/)
+// 4 float4 per thread, all four x loads issued before anything else and ONLY they live while in flight: the (L1-resident)
+// coefficient rows are fetched after the x loads return, which keeps the kernel at 40 registers = 6 CTAs per SM = 96 KB of loads in
+// flight per SM.  Measured at 64 patches (tools/bench_act.py): 1 load per thread 4.0 TB/s; 4 loads with the coefficients loaded
+// alongside (76 registers) 4.9 TB/s; this form 6.4 TB/s.  x is read once -> evict-first loads.
 // lC4 / lrps >= 0: C/4 resp. rows_per_sample are powers of two (every layer of the network) -> shifts instead of divisions
+__device__ __forceinline__ float4 ld_stream4(const float* p)     // read-once input: evict-first
+{
+    return __ldcs(reinterpret_cast<const float4*>(p));
+}
+
 template <int ACT, typename OUT>
-__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
-                                                         const float* __restrict__ Bc, int rows_per_sample, int C,
-                                                         OUT* __restrict__ out, int ldo, unsigned total4, int lC4, int lrps)
+__global__ void __launch_bounds__(256, 5) affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
+                                                            const float* __restrict__ Bc, int rows_per_sample, int C,
+                                                            OUT* __restrict__ out, int ldo, unsigned total4, int lC4, int lrps)
 {
     P2PB_PDL_SYNC();
     const unsigned C4 = C >> 2;
     // grid-stride over blocks of 4 x blockDim float4 (the launcher picks a persistent grid for large tensors)
     for (unsigned base = blockIdx.x * (blockDim.x * 4); base < total4; base += gridDim.x * (blockDim.x * 4)) {
         const unsigned e0 = base + threadIdx.x;
-        float4 xv[4], a[4], bb[4];
-        size_t m[4];
-        int c[4];
+        float4 xv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned e = e0 + k * blockDim.x;
             if (e < total4) {
                 const unsigned mu = lC4 >= 0 ? (e >> lC4) : e / C4;
-                c[k] = (int)(e - mu * C4) * 4;
-                m[k] = mu;
-                const size_t b = lrps >= 0 ? (mu >> lrps) : mu / (unsigned)rows_per_sample;
-                xv[k] = *reinterpret_cast<const float4*>(x + m[k] * ldx + c[k]);
-                a[k] = __ldg(reinterpret_cast<const float4*>(A + b * C + c[k]));
-                bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c[k]));
+                xv[k] = ld_stream4(x + (size_t)mu * ldx + (e - mu * C4) * 4);
             }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned e = e0 + k * blockDim.x;
-            if (e < total4) store4(out + m[k] * ldo + c[k], affine4<ACT>(xv[k], a[k], bb[k]));
+            if (e < total4) {
+                const unsigned mu = lC4 >= 0 ? (e >> lC4) : e / C4;
+                const int c = (int)(e - mu * C4) * 4;
+                const size_t b = lrps >= 0 ? (mu >> lrps) : mu / (unsigned)rows_per_sample;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(A + b * C + c));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + b * C + c));
+                store4(out + (size_t)mu * ldo + c, affine4<ACT>(xv[k], a, bb));
+            }
         }
     }
 }
@@ -1464,45 +1471,47 @@ P2PB_API int p2pb_voxelize_padded_sparse_f16(const float* feat, int ldf, int Cf,
 // y = swish(x*A + B) of dense conv-output rows [B*r^3, ldx] -> zero-bordered padded input rows of the next conv
 // lC4 / lr >= 0: C/4 resp. r are powers of two -> the (sample, x, y, z) split of a voxel row is shifts and masks
 template <typename OUT>
-__global__ void __launch_bounds__(256) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
-                                                                const float* __restrict__ Bc, int C, OUT* __restrict__ out, int ldo,
-                                                                int r, unsigned total4, int lC4, int lr)
+__global__ void __launch_bounds__(256, 5) affine_act_padded_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ A,
+                                                                   const float* __restrict__ Bc, int C, OUT* __restrict__ out, int ldo,
+                                                                   int r, unsigned total4, int lC4, int lr)
 {
     P2PB_PDL_SYNC();
     const unsigned r3 = r * r * r;
     const unsigned C4 = C >> 2;
     const int P = r + 1;
     for (unsigned base = blockIdx.x * (blockDim.x * 4); base < total4; base += gridDim.x * (blockDim.x * 4)) {
-    const unsigned e0 = base + threadIdx.x;
-    float4 xv[4], a[4], bb[4];
-    size_t orow[4];
-    int c[4];
+        const unsigned e0 = base + threadIdx.x;
+        float4 xv[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {      // 4 float4 per thread, loads first (see affine_act_kernel)
-        const unsigned e = e0 + k * blockDim.x;
-        if (e < total4) {
-            const unsigned vrow = lC4 >= 0 ? (e >> lC4) : e / C4;
-            c[k] = (int)(e - vrow * C4) * 4;
-            int b;
-            if (lr >= 0) {
-                b = (int)(vrow >> (3 * lr));
-                const unsigned v = vrow & (r3 - 1);
-                const int vx = (int)(v >> (2 * lr)), vy = (int)((v >> lr) & (unsigned)(r - 1)), vz = (int)(v & (unsigned)(r - 1));
-                orow[k] = (size_t)b * P * P * P + (size_t)(vx + 1) * P * P + (size_t)(vy + 1) * P + (vz + 1);
-            } else {
-                b = (int)(vrow / r3);
-                orow[k] = padded_row(b, (int)(vrow - (unsigned)b * r3), r);
+        for (int k = 0; k < 4; ++k) {      // 4 float4 per thread; only the x loads are live while in flight (see affine_act_kernel)
+            const unsigned e = e0 + k * blockDim.x;
+            if (e < total4) {
+                const unsigned vrow = lC4 >= 0 ? (e >> lC4) : e / C4;
+                xv[k] = ld_stream4(x + (size_t)vrow * ldx + (e - vrow * C4) * 4);
             }
-            xv[k] = *reinterpret_cast<const float4*>(x + (size_t)vrow * ldx + c[k]);
-            a[k] = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c[k]));
-            bb[k] = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c[k]));
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const unsigned e = e0 + k * blockDim.x;
-        if (e < total4) store4(out + orow[k] * ldo + c[k], affine4<1>(xv[k], a[k], bb[k]));
-    }
+        for (int k = 0; k < 4; ++k) {
+            const unsigned e = e0 + k * blockDim.x;
+            if (e < total4) {
+                const unsigned vrow = lC4 >= 0 ? (e >> lC4) : e / C4;
+                const int c = (int)(e - vrow * C4) * 4;
+                int b;
+                size_t orow;
+                if (lr >= 0) {
+                    b = (int)(vrow >> (3 * lr));
+                    const unsigned v = vrow & (r3 - 1);
+                    const int vx = (int)(v >> (2 * lr)), vy = (int)((v >> lr) & (unsigned)(r - 1)), vz = (int)(v & (unsigned)(r - 1));
+                    orow = (size_t)b * P * P * P + (size_t)(vx + 1) * P * P + (size_t)(vy + 1) * P + (vz + 1);
+                } else {
+                    b = (int)(vrow / r3);
+                    orow = padded_row(b, (int)(vrow - (unsigned)b * r3), r);
+                }
+                const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)b * C + c));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc + (size_t)b * C + c));
+                store4(out + orow * ldo + c, affine4<1>(xv[k], a, bb));
+            }
+        }
     }
 }
 
@@ -1529,8 +1538,8 @@ P2PB_API int p2pb_affine_act_padded_f16(const float* x, int ldx, const float* A,
     P2PB_CHECK_U32(total4, "affine_act_padded_f16");
     if (total4 == 0) return P2PB_OK;
     p2pb_prefer_max_smem((const void*)affine_act_padded_kernel<__half>);
-    (void)p2pb_launch(affine_act_padded_kernel<__half>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
-        x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
+    (void)p2pb_launch(affine_act_padded_kernel<__half>, dim3(p2pb_act_grid(total4)), dim3(256), (size_t)(0), (cudaStream_t)stream,
+            x, ldx, A, Bc, C, reinterpret_cast<__half*>(out), ldo, r, total4, p2pb_log2_exact(C / 4), p2pb_log2_exact(r));
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

@@ -32,6 +32,7 @@ constexpr int PBM = 128;
 constexpr int PBK = 32;
 constexpr int P_THREADS = 320;   // warp 0: TMA producer, 1: MMA issuer, 2-9: epilogue (two warps per TMEM lane quarter)
 constexpr int PA_STAGE = PBM * PBK * 4;  // 16 KiB
+constexpr int P_SIDE_KB = 28;            // shared memory left free per SM for a co-resident side-stream CTA (see p_launch)
 
 struct PArgs {
     int M, n_total, n_tiles, m_tiles, total_items;
@@ -232,7 +233,7 @@ struct PCfg {
 };
 
 template <int BN, int CL>
-__global__ void __launch_bounds__(P_THREADS, 1)
+__global__ void __launch_bounds__(512, 1)      // 320 threads are launched; 512 caps the kernel at 128 registers (see p_launch: P_SIDE_KB)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ CUtensorMap mapD, const PArgs a)
@@ -569,7 +570,11 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
     using Cfg = PCfg<BN>;
     const int fixed = 1024 + Cfg::C_BYTES + Cfg::STAT_BYTES + 512;
     constexpr int b_stage = CL == 3 ? Cfg::B_STAGE / 2 : Cfg::B_STAGE;
-    int stages = (g_p2pb_smem_budget_kb * 1024 - fixed) / (PA_STAGE + b_stage);
+    // P_SIDE_KB of shared memory (and, through __launch_bounds__, a quarter of every sub-partition's registers) stay free for a CTA of
+    // the geometry stream's kernels (FPS, ball query: 24 KB of staged coordinates, <= 64 registers x 256 threads): a persistent GEMM
+    // that owns the whole SM would otherwise wait for those CTAs to finish on 64 of the 148 SMs and, with its static tile schedule,
+    // take twice as long (tools/bench_overlap.py: 283 -> 193 us for the three global-PointNet GEMMs next to FPS)
+    int stages = ((g_p2pb_smem_budget_kb - P_SIDE_KB) * 1024 - fixed) / (PA_STAGE + b_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     a.stages = stages;
@@ -577,7 +582,8 @@ int p_launch(const CUtensorMap* maps, PArgs& a, cudaStream_t s)
     static bool attr_set = false;
     if (!attr_set) {
         P2PB_CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        p2pb_prefer_max_smem((const void*)gemm_persist_kernel<BN, CL>);      // same carve-out as every other kernel: CTAs of the
+        attr_set = true;                                                     // side-stream geometry kernels can share the SM
     }
     constexpr int NCTA = CL == 1 ? 1 : 2;
     const int m_items = (a.m_tiles + NCTA - 1) / NCTA;

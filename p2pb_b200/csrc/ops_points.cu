@@ -31,7 +31,7 @@ __device__ __forceinline__ int fps_key_to_index(unsigned key)
 }
 
 template <int P, int T>
-__global__ void __launch_bounds__(T, 1) fps_reg_kernel(const float* __restrict__ coords, int N, int M,
+__global__ void __launch_bounds__(T, (P <= 8 && T <= 256) ? 1024 / T : 1) fps_reg_kernel(const float* __restrict__ coords, int N, int M,
                                                        int* __restrict__ idx, float* __restrict__ centers)
 {
     P2PB_PDL_SYNC();

@@ -20,10 +20,13 @@ raw = torch.randn(B * r ** 3, C, device="cuda"); A = torch.randn(B, C, device="c
 outp = dense.alloc_padded(B, C, r, "cuda", torch.float16)
 M = 64 * 2048 * 8
 x = torch.randn(M, 64, device="cuda"); y = torch.empty(M, 64, device="cuda", dtype=torch.float16)
+ref1 = ref2 = None
 for g in (0, 4, 8, 16, 32):
     lib().p2pb_set_act_grid(g)
     t1 = timeit(lambda: call("p2pb_affine_act_padded_f16", p(raw), C, p(A), p(Bc), B, C, r, p(outp), C, s()))
     t2 = timeit(lambda: call("p2pb_affine_act_f16", p(x), 64, p(A), p(Bc), M // 64, M, 64, 1, p(y), 64, s()))
+    if ref1 is None: ref1, ref2 = outp.clone(), y.clone()
+    assert torch.equal(ref1, outp) and torch.equal(ref2, y), "variant differs"
     b1 = raw.numel() * 4 + B * r ** 3 * C * 2; b2 = x.numel() * 6
     print(f"grid {g:2d} CTAs/SM: padded {t1*1e3:6.1f} us {b1/t1/1e6:6.0f} GB/s | rows {t2*1e3:6.1f} us {b2/t2/1e6:6.0f} GB/s")
 lib().p2pb_set_act_grid(0)
