@@ -112,6 +112,66 @@ P2PB_API int p2pb_coords_to_rows(const float* coords, float* rows, int B, int N,
     return P2PB_OK;
 }
 
+// Scatter-mean of one voxel for the 4 channels c0..c0+3: sum over the voxel's n points (CSR order = ascending point index, the
+// oracle's order; vox_gpu.cu:70-75 adds with atomics in no particular order) of feat[p, c] * (1/n); channels Cf <= c < Cf+E get the
+// same mean of the broadcast time embedding, channels beyond that 0.  The loads of 16 points are in flight together and a chunk that
+// straddles Cf still uses 16-byte loads (rows are padded to ldf; what is read beyond Cf is discarded): a voxel that holds hundreds
+// of points is otherwise a chain of dependent L2 round trips, three of them per point in the straddling chunk (late bridge steps
+// concentrate the points: measured 66 -> 270 us for the first voxelisation between the 1st and the 24th step of the bench).
+__device__ __forceinline__ float4 voxel_mean4(const float* __restrict__ feat, int ldf, int Cf, const float* __restrict__ temb_b, int E,
+                                              const int* __restrict__ ord, int n, int c0)
+{
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const float inv = (float)(1.0 / (double)(float)n);
+    if (c0 < Cf) {
+        if ((ldf & 3) == 0 && c0 + 3 < ldf) {
+            int i = 0;
+            for (; i + 16 <= n; i += 16) {
+                int o[16];
+                float4 f[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) o[u] = ord[i + u];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) f[u] = __ldg(reinterpret_cast<const float4*>(feat + (size_t)o[u] * ldf + c0));
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    a[0] = __fadd_rn(a[0], __fmul_rn(f[u].x, inv));
+                    a[1] = __fadd_rn(a[1], __fmul_rn(f[u].y, inv));
+                    a[2] = __fadd_rn(a[2], __fmul_rn(f[u].z, inv));
+                    a[3] = __fadd_rn(a[3], __fmul_rn(f[u].w, inv));
+                }
+            }
+            for (; i < n; ++i) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + (size_t)ord[i] * ldf + c0));
+                a[0] = __fadd_rn(a[0], __fmul_rn(f.x, inv));
+                a[1] = __fadd_rn(a[1], __fmul_rn(f.y, inv));
+                a[2] = __fadd_rn(a[2], __fmul_rn(f.z, inv));
+                a[3] = __fadd_rn(a[3], __fmul_rn(f.w, inv));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (c0 + k >= Cf) continue;
+                float s = 0.f;
+                for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + (size_t)ord[i] * ldf + c0 + k), inv));
+                a[k] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        if (c < Cf) continue;
+        float s = 0.f;
+        if (c < Cf + E) {
+            const float t = __fmul_rn(__ldg(temb_b + (c - Cf)), inv);
+            for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
+        }
+        a[k] = s;
+    }
+    return make_float4(a[0], a[1], a[2], a[3]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // voxelize_cl: out[b, v, c] for every voxel v and channel c < Cp (each element written exactly once)
 //   c <  Cf        : sum over the voxel's points (ascending index) of feat[b, p, c] * (1/cnt)    (vox_gpu.cu:70-75)
@@ -134,35 +194,9 @@ __global__ void __launch_bounds__(256) voxelize_cl_kernel(const float* __restric
     const int b = (int)(vrow / (unsigned)r3);
     const int n = cnt[vrow];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n > 0) {
-        const float inv = (float)(1.0 / (double)(float)n);
-        const int* ord = order + (size_t)b * N + start[vrow];
-        float* a = reinterpret_cast<float*>(&acc);
-        if (c0 + 3 < Cf && (ldf & 3) == 0) {
-            for (int i = 0; i < n; ++i) {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + ord[i]) * ldf + c0));
-                acc.x = __fadd_rn(acc.x, __fmul_rn(f.x, inv));
-                acc.y = __fadd_rn(acc.y, __fmul_rn(f.y, inv));
-                acc.z = __fadd_rn(acc.z, __fmul_rn(f.z, inv));
-                acc.w = __fadd_rn(acc.w, __fmul_rn(f.w, inv));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + j;
-                if (c < Cf) {
-                    float s = 0.f;
-                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
-                    a[j] = s;
-                } else if (c < Cf + E) {
-                    const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
-                    float s = 0.f;
-                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
-                    a[j] = s;
-                }
-            }
-        }
-    }
+    if (n > 0)
+        acc = voxel_mean4(feat + (size_t)b * N * ldf, ldf, Cf, temb != nullptr ? temb + (size_t)b * E : nullptr, E,
+                          order + (size_t)b * N + start[vrow], n, c0);
     store4(out + (size_t)e * 4, acc);
 }
 
@@ -1327,36 +1361,11 @@ __global__ void __launch_bounds__(256) voxelize_padded_kernel(const float* __res
     const int b = (int)(vrow / r3);
     const int v = (int)(vrow - (unsigned)b * r3);
     const int n = cnt[vrow];
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    if (n > 0) {
-        const float inv = (float)(1.0 / (double)(float)n);
-        const int* ord = order + (size_t)b * N + start[vrow];
-        if (c0 + 3 < Cf && (ldf & 3) == 0) {
-            for (int i = 0; i < n; ++i) {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + ord[i]) * ldf + c0));
-                a[0] = __fadd_rn(a[0], __fmul_rn(f.x, inv));
-                a[1] = __fadd_rn(a[1], __fmul_rn(f.y, inv));
-                a[2] = __fadd_rn(a[2], __fmul_rn(f.z, inv));
-                a[3] = __fadd_rn(a[3], __fmul_rn(f.w, inv));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + j;
-                if (c < Cf) {
-                    float s = 0.f;
-                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
-                    a[j] = s;
-                } else if (c < Cf + E) {
-                    const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
-                    float s = 0.f;
-                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
-                    a[j] = s;
-                }
-            }
-        }
-    }
-    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * Cp + c0) = make_float4(a[0], a[1], a[2], a[3]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n > 0)
+        acc = voxel_mean4(feat + (size_t)b * N * ldf, ldf, Cf, temb != nullptr ? temb + (size_t)b * E : nullptr, E,
+                          order + (size_t)b * N + start[vrow], n, c0);
+    *reinterpret_cast<float4*>(out + padded_row(b, v, r) * Cp + c0) = acc;
 }
 
 P2PB_API int p2pb_voxelize_padded(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order,
@@ -1399,37 +1408,11 @@ __global__ void __launch_bounds__(256) voxelize_sparse_kernel(const float* __res
     const int v = ind[(size_t)b * N + p];
     const size_t vrow = (size_t)b * r3 + v;
     if (start[vrow] != j) return;            // not the first point of its voxel
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!clear) {
-        const int n = cnt[vrow];
-        const float inv = (float)(1.0 / (double)(float)n);
-        const int* ord = order + (size_t)b * N + j;
-        if (c0 + 3 < Cf && (ldf & 3) == 0) {
-            for (int i = 0; i < n; ++i) {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * N + ord[i]) * ldf + c0));
-                a[0] = __fadd_rn(a[0], __fmul_rn(f.x, inv));
-                a[1] = __fadd_rn(a[1], __fmul_rn(f.y, inv));
-                a[2] = __fadd_rn(a[2], __fmul_rn(f.z, inv));
-                a[3] = __fadd_rn(a[3], __fmul_rn(f.w, inv));
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = c0 + k;
-                if (c < Cf) {
-                    float s = 0.f;
-                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__ldg(feat + ((size_t)b * N + ord[i]) * ldf + c), inv));
-                    a[k] = s;
-                } else if (c < Cf + E) {
-                    const float t = __fmul_rn(__ldg(temb + (size_t)b * E + (c - Cf)), inv);
-                    float s = 0.f;
-                    for (int i = 0; i < n; ++i) s = __fadd_rn(s, t);
-                    a[k] = s;
-                }
-            }
-        }
-    }
-    store4(out + padded_row(b, v, r) * Cp + c0, make_float4(a[0], a[1], a[2], a[3]));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!clear)
+        acc = voxel_mean4(feat + (size_t)b * N * ldf, ldf, Cf, temb != nullptr ? temb + (size_t)b * E : nullptr, E,
+                          order + (size_t)b * N + j, cnt[vrow], c0);
+    store4(out + padded_row(b, v, r) * Cp + c0, acc);
 }
 
 static int voxelize_sparse_impl(const float* feat, int ldf, int Cf, const float* temb, int E, const int* order, const int* ind,

@@ -542,22 +542,24 @@ P2PB_API int p2pb_grouping(const float* feat, const int* idx, float* out, int B,
 // hit, all-zero row when the ball is empty.  One WARP per centre: 32 points tested per step, ballot + popc
 // compaction preserves index order, early exit when U are found.  Points staged in shared memory per CTA.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int BQ_TILE = 2048;     // points staged per pass (24 KB: a CTA fits next to a persistent GEMM / conv CTA of the main stream)
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) ball_query_kernel(const float* __restrict__ centers,
                                                                 const float* __restrict__ points, int M, int N,
                                                                 float r2, int U, int* __restrict__ out)
 {
     P2PB_PDL_SYNC();
-    extern __shared__ float s_pts[];  // [3][N]
+    extern __shared__ float s_pts[];  // [3][BQ_TILE]
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     points += (size_t)b * 3 * N;
     centers += (size_t)b * 3 * M;
-    for (int i = threadIdx.x; i < 3 * N; i += WARPS * 32) s_pts[i] = points[i];
-    __syncthreads();
-    // Each warp handles CQ = 4 centres per pass: a staged point is read from shared memory once and tested against 4 centres
-    // (the scan is bound by the 3 LDS + loop overhead per 32 points, not by the 6 flops of a distance).
+    // Each warp handles CQ = 4 centres per round: a staged point is read from shared memory once and tested against 4 centres
+    // (the scan is bound by the 3 LDS + loop overhead per 32 points, not by the 6 flops of a distance).  The points are staged in
+    // tiles of BQ_TILE in index order; a CTA stops staging as soon as all its centres have their U neighbours.
     constexpr int CQ = 4;
-    for (int j0 = (blockIdx.x * WARPS + warp) * CQ; j0 < M; j0 += gridDim.x * WARPS * CQ) {
+    for (int base = blockIdx.x * WARPS * CQ; base < M; base += gridDim.x * WARPS * CQ) {      // uniform over the CTA
+        const int j0 = base + warp * CQ;
         float cx[CQ], cy[CQ], cz[CQ];
         int cnt[CQ], first[CQ];
 #pragma unroll
@@ -569,24 +571,36 @@ __global__ void __launch_bounds__(WARPS * 32) ball_query_kernel(const float* __r
             cnt[q] = j0 + q < M ? 0 : U;      // centres past the end count as finished
             first[q] = 0;
         }
-        for (int k0 = 0; k0 < N; k0 += 32) {
-            if (cnt[0] >= U && cnt[1] >= U && cnt[2] >= U && cnt[3] >= U) break;
-            const int k = k0 + lane;
-            float px = 0.f, py = 0.f, pz = 0.f;
-            if (k < N) {
-                px = s_pts[k];
-                py = s_pts[k + N];
-                pz = s_pts[k + 2 * N];
+        for (int t0 = 0; t0 < N; t0 += BQ_TILE) {
+            const bool done = cnt[0] >= U && cnt[1] >= U && cnt[2] >= U && cnt[3] >= U;
+            if (__syncthreads_and(done)) break;        // (also: every warp is past the previous tile)
+            const int tn = min(BQ_TILE, N - t0);
+            for (int i = threadIdx.x; i < tn; i += WARPS * 32) {
+                s_pts[i] = points[t0 + i];
+                s_pts[i + BQ_TILE] = points[N + t0 + i];
+                s_pts[i + 2 * BQ_TILE] = points[2 * N + t0 + i];
             }
+            __syncthreads();
+            if (done) continue;
+            for (int k0 = 0; k0 < tn; k0 += 32) {
+                if (cnt[0] >= U && cnt[1] >= U && cnt[2] >= U && cnt[3] >= U) break;
+                const int k = k0 + lane;
+                float px = 0.f, py = 0.f, pz = 0.f;
+                if (k < tn) {
+                    px = s_pts[k];
+                    py = s_pts[k + BQ_TILE];
+                    pz = s_pts[k + 2 * BQ_TILE];
+                }
 #pragma unroll
-            for (int q = 0; q < CQ; ++q) {
-                const bool hit = k < N && cnt[q] < U && sqdist3(cx[q] - px, cy[q] - py, cz[q] - pz) < r2;
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    if (cnt[q] == 0) first[q] = k0 + __ffs(m) - 1;
-                    const int slot = cnt[q] + __popc(m & ((1u << lane) - 1u));
-                    if (hit && slot < U) out[((size_t)b * M + j0 + q) * U + slot] = k;
-                    cnt[q] += __popc(m);
+                for (int q = 0; q < CQ; ++q) {
+                    const bool hit = k < tn && cnt[q] < U && sqdist3(cx[q] - px, cy[q] - py, cz[q] - pz) < r2;
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        if (cnt[q] == 0) first[q] = t0 + k0 + __ffs(m) - 1;
+                        const int slot = cnt[q] + __popc(m & ((1u << lane) - 1u));
+                        if (hit && slot < U) out[((size_t)b * M + j0 + q) * U + slot] = t0 + k;
+                        cnt[q] += __popc(m);
+                    }
                 }
             }
         }
@@ -598,6 +612,7 @@ __global__ void __launch_bounds__(WARPS * 32) ball_query_kernel(const float* __r
             // pad with the first hit (or zeros when empty: reference output is zero-initialised)
             for (int v = c + lane; v < U; v += 32) o[v] = first[q];
         }
+        __syncthreads();      // the next round restages tile 0
     }
 }
 
@@ -607,14 +622,12 @@ P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, i
     P2PB_CHECK_ARG(B >= 0 && M >= 0 && N > 0 && U > 0, "ball_query: bad sizes");
     if (B == 0 || M == 0) return P2PB_OK;
     const float r2 = radius * radius;  // pvcnn_ball_query.cpp:25 (fp32 product)
-    const size_t smem = (size_t)3 * N * sizeof(float);
-    P2PB_CHECK_ARG(smem <= 200 * 1024, "ball_query: N=%d too large for shared-memory staging", N);
+    const size_t smem = (size_t)3 * BQ_TILE * sizeof(float);
     constexpr int WARPS = 8;
-    if (smem > 48 * 1024)
-        P2PB_CUDA_OK(cudaFuncSetAttribute(ball_query_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int gx = p2pb_cdiv(M, WARPS * 4);
-    // enough CTAs per patch to fill the chip, but not so many that staging the points dominates
-    const int want = p2pb_cdiv(2 * p2pb_num_sms(), B);
+    // enough CTAs per patch to fill the chip, but at most ~4 (1024 of the 2048 thread slots) per SM: the kernel runs on the geometry
+    // stream next to the main stream's kernels
+    const int want = p2pb_cdiv(4 * p2pb_num_sms(), B);
     if (gx > want) gx = want < 1 ? 1 : want;
     p2pb_prefer_max_smem((const void*)ball_query_kernel<WARPS>);
     (void)p2pb_launch(ball_query_kernel<WARPS>, dim3(dim3(gx, B)), dim3(WARPS * 32), (size_t)(smem), (cudaStream_t)stream, centers, points, M, N, r2, U, out);
@@ -632,37 +645,55 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
                                                        int N, int M, int* __restrict__ idx, float* __restrict__ w)
 {
     P2PB_PDL_SYNC();
-    extern __shared__ float s_c[];  // [3][M]
+    extern __shared__ __align__(16) float s_c[];  // [3][Mp], Mp = M rounded up to 4 (pad entries are never compared)
     const int b = blockIdx.y;
+    const int Mp = (M + 3) & ~3;
     points += (size_t)b * 3 * N;
     centers += (size_t)b * 3 * M;
-    for (int i = threadIdx.x; i < 3 * M; i += blockDim.x) s_c[i] = centers[i];
-    __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    const float ux = points[j], uy = points[j + N], uz = points[j + 2 * N];
-    float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY;
-    int i0 = 0, i1 = 0, i2 = 0;
-    for (int k = 0; k < M; ++k) {
-        const float d = sqdist3(ux - s_c[k], uy - s_c[k + M], uz - s_c[k + 2 * M]);
-        if (d < b2) {
-            b2 = d; i2 = k;
-            if (d < b1) {
-                b2 = b1; i2 = i1; b1 = d; i1 = k;
-                if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = k; }
-            }
-        }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        s_c[i] = centers[i];
+        s_c[i + Mp] = centers[i + M];
+        s_c[i + 2 * Mp] = centers[i + 2 * M];
     }
-    b0 = fmaxf(fminf(1e10f, b0), 1e-10f);
-    b1 = fmaxf(fminf(1e10f, b1), 1e-10f);
-    b2 = fmaxf(fminf(1e10f, b2), 1e-10f);
-    const float d0d1 = __fmul_rn(b0, b1), d0d2 = __fmul_rn(b0, b2), d1d2 = __fmul_rn(b1, b2);
-    const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+    __syncthreads();
     int* ix = idx + (size_t)b * 3 * N;
     float* ww = w + (size_t)b * 3 * N;
-    ww[j] = __fmul_rn(d1d2, inv); ix[j] = i0;
-    ww[j + N] = __fmul_rn(d0d2, inv); ix[j + N] = i1;
-    ww[j + 2 * N] = __fmul_rn(d0d1, inv); ix[j + 2 * N] = i2;
+    // grid-stride over blocks of 256 points: the launcher caps the grid so that this (ALU-bound, side-stream) kernel never fills
+    // the thread slots of an SM -- the main stream's small kernels have to be able to start next to it
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const float ux = points[j], uy = points[j + N], uz = points[j + 2 * N];
+        float b0 = INFINITY, b1 = INFINITY, b2 = INFINITY;
+        int i0 = 0, i1 = 0, i2 = 0;
+        auto visit = [&](float cx, float cy, float cz, int k) {
+            const float d = sqdist3(ux - cx, uy - cy, uz - cz);
+            if (d < b2) {
+                b2 = d; i2 = k;
+                if (d < b1) {
+                    b2 = b1; i2 = i1; b1 = d; i1 = k;
+                    if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = k; }
+                }
+            }
+        };
+        const int M4 = M & ~3;
+        for (int k = 0; k < M4; k += 4) {       // one 16-byte broadcast load per coordinate and four centres, visited in index order
+            const float4 cx = *reinterpret_cast<const float4*>(s_c + k);
+            const float4 cy = *reinterpret_cast<const float4*>(s_c + Mp + k);
+            const float4 cz = *reinterpret_cast<const float4*>(s_c + 2 * Mp + k);
+            visit(cx.x, cy.x, cz.x, k);
+            visit(cx.y, cy.y, cz.y, k + 1);
+            visit(cx.z, cy.z, cz.z, k + 2);
+            visit(cx.w, cy.w, cz.w, k + 3);
+        }
+        for (int k = M4; k < M; ++k) visit(s_c[k], s_c[k + Mp], s_c[k + 2 * Mp], k);
+        b0 = fmaxf(fminf(1e10f, b0), 1e-10f);
+        b1 = fmaxf(fminf(1e10f, b1), 1e-10f);
+        b2 = fmaxf(fminf(1e10f, b2), 1e-10f);
+        const float d0d1 = __fmul_rn(b0, b1), d0d2 = __fmul_rn(b0, b2), d1d2 = __fmul_rn(b1, b2);
+        const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+        ww[j] = __fmul_rn(d1d2, inv); ix[j] = i0;
+        ww[j + N] = __fmul_rn(d0d2, inv); ix[j + N] = i1;
+        ww[j + 2 * N] = __fmul_rn(d0d1, inv); ix[j + 2 * N] = i2;
+    }
 }
 
 // out[b,c,j] = f[c,i2]*w2 (+fma) f[c,i1]*w1 (+fma) f[c,i3]*w3   (contraction order of the reference build, see oracle)
@@ -693,12 +724,17 @@ P2PB_API int p2pb_three_nn(const float* points, const float* centers, int B, int
 {
     P2PB_CHECK_ARG(B >= 0 && N > 0 && M > 0, "three_nn: bad sizes");
     if (B == 0) return P2PB_OK;
-    const size_t smem = (size_t)3 * M * sizeof(float);
+    const size_t smem = (size_t)3 * ((M + 3) & ~3) * sizeof(float);
     P2PB_CHECK_ARG(smem <= 200 * 1024, "three_nn: M=%d too large for shared-memory staging", M);
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p2pb_prefer_max_smem((const void*)three_nn_kernel);
-    (void)p2pb_launch(three_nn_kernel, dim3(dim3(p2pb_cdiv(N, 256), B)), dim3(256), (size_t)(smem), (cudaStream_t)stream, points, centers, N, M, idx, w);
+    // at most ~4 CTAs (1024 of the 2048 thread slots) per SM, in whole passes over the point blocks
+    const int nblk = p2pb_cdiv(N, 256);
+    int cap = (4 * p2pb_num_sms()) / B;
+    if (cap < 1) cap = 1;
+    const int gx = p2pb_cdiv(nblk, p2pb_cdiv(nblk, cap));
+    (void)p2pb_launch(three_nn_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(smem), (cudaStream_t)stream, points, centers, N, M, idx, w);
     P2PB_LAUNCH_OK();
     return P2PB_OK;
 }

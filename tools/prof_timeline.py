@@ -21,15 +21,25 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--out", default="gpurun_out/timeline.md")
 ap.add_argument("--steps", type=int, default=6)
+ap.add_argument("--pvdl", action="store_true", help="BASELINE config 3: PVDL, 32 patches of 8192 points")
 args = ap.parse_args()
 ENG.OPTIONS.no_graph = not args.graph
 dev = torch.device("cuda:0")
-cfg = Config.wrap(bench.load_cfg_dict()); cfg.gpu = str(dev); cfg.model.ema = False; cfg.backend = "engine"
+if args.pvdl:
+    import yaml
+    from tests.helpers import patch_input
+    cd = yaml.safe_load(open(os.path.join(bench.ROOT, "p2pb_b200", "configs", "PVDL_SNPP.yaml")))
+    cd["data"]["npoints"] = bench.PVDL_N; cd["model"]["extra_feature_channels"] = 0
+    cfg = Config.wrap(cd)
+    x = patch_input(bench.PVDL_B_PER_GPU, bench.PVDL_N, seed=7).to(dev)
+else:
+    cfg = Config.wrap(bench.load_cfg_dict())
+    x = bench.synth_patches(64, bench.NPTS, seed=1000).to(dev)
+cfg.gpu = str(dev); cfg.model.ema = False; cfg.backend = "engine"
 net = PVCNN2Unet(cfg); net.load_state_dict(seeded_state_dict(net, seed=0), strict=True)
 model = P2PB(cfg, net.to(dev)).eval()
-x = bench.synth_patches(64, bench.NPTS, seed=1000).to(dev)
 run = lambda T: model.sample(x_start=x, steps=T, log_count=1, verbose=False, use_ema=False)["x_pred"]
-run(bench.TSTEPS); torch.cuda.synchronize()
+run(args.steps); run(args.steps); torch.cuda.synchronize()       # steady state of THIS step count (tables, graph)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run(args.steps); torch.cuda.synchronize()
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
@@ -66,5 +76,33 @@ lines += ["", "per launch, in order (main stream = *):", ""]
 for e in win:
     n = re.sub(r"\(.*", "", e["name"].replace("(anonymous namespace)::", "").replace("void ", ""))[:60]
     lines.append(f"{'*' if e['args'].get('stream') == main else ' '} {e['ts'] - t0:8.0f} {e['dur']:7.1f}  {n}  grid={e['args'].get('grid')}")
+# step-to-step drift: per-kernel totals of the fastest and the slowest evaluation of the call
+def window_totals(i):
+    d = collections.defaultdict(float)
+    for e in ev[heads[i] + 1:heads[i + 1] + 1]:
+        d[re.sub(r"\(.*", "", e["name"].replace("(anonymous namespace)::", "").replace("void ", "")).strip()[:64]] += e["dur"]
+    return d
+if len(heads) > 3:
+    per = [(ev[heads[i + 1]]["ts"] + ev[heads[i + 1]]["dur"]) - (ev[heads[i]]["ts"] + ev[heads[i]]["dur"]) for i in range(len(heads) - 1)]
+    ia, ib = per.index(min(per)), per.index(max(per))
+    da, db = window_totals(ia), window_totals(ib)
+    lines += ["", f"fastest evaluation (#{ia + 1}, {per[ia]:.0f} us) vs slowest (#{ib + 1}, {per[ib]:.0f} us), kernels that differ by more than 5 us:"]
+    for n in sorted(da, key=lambda n: -(db.get(n, 0) - da[n])):
+        if abs(db.get(n, 0) - da[n]) > 5: lines.append(f"  {n:64s} {da[n]:8.0f} -> {db.get(n, 0):8.0f}")
+    for nm in ("voxelize_sparse", "voxel_prep"):
+        la = [e["dur"] for e in ev[heads[ia] + 1:heads[ia + 1] + 1] if nm in e["name"]]
+        lb = [e["dur"] for e in ev[heads[ib] + 1:heads[ib + 1] + 1] if nm in e["name"]]
+        lines.append(f"  {nm} per launch: " + " ".join(f"{x:.0f}->{y:.0f}" for x, y in zip(la, lb)))
+# what one sample() call does outside its network evaluations
+first_sv = next(i for i, e in enumerate(ev) if "step_vectors" in e["name"])
+span = ev[-1]["ts"] + ev[-1]["dur"] - ev[0]["ts"]
+per_eval = [(ev[heads[i + 1]]["ts"] + ev[heads[i + 1]]["dur"]) - (ev[heads[i]]["ts"] + ev[heads[i]]["dur"]) for i in range(len(heads) - 1)]
+lines += ["", f"whole sample() call ({args.steps} steps): first kernel -> last kernel {span:.0f} us; evaluation periods (head_bridge end to "
+          f"head_bridge end): {', '.join(f'{p:.0f}' for p in per_eval)} us", "kernels before the first evaluation:"]
+for e in ev[:first_sv]:
+    lines.append(f"  {e['ts'] - ev[0]['ts']:8.0f} {e['dur']:7.1f}  {e['name'][:90]}")
+lines.append("kernels after the last evaluation:")
+for e in ev[heads[-1] + 1:]:
+    lines.append(f"  {e['ts'] - ev[0]['ts']:8.0f} {e['dur']:7.1f}  {e['name'][:90]}")
 open(args.out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:45]))
