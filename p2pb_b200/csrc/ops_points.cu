@@ -542,6 +542,12 @@ P2PB_API int p2pb_grouping(const float* feat, const int* idx, float* out, int B,
 // hit, all-zero row when the ball is empty.  One WARP per centre: 32 points tested per step, ballot + popc
 // compaction preserves index order, early exit when U are found.  Points staged in shared memory per CTA.
 // ---------------------------------------------------------------------------------------------------------
+// Resident CTAs (of 256 threads) per SM that the ALU-bound geometry kernels (ball query, 3-NN search) are launched with.  They run on
+// the side stream NEXT TO the main stream's kernels and must leave thread slots for them (a full-occupancy 3-NN search kept a 5 us
+// GroupNorm-coefficient kernel of the main stream waiting for 260 us at N = 8192).  Measured at 1 / 2 / 4 CTAs per SM: 397 / 402 / 402
+// patches/s on PVDS, 64.7 / 64.4 / 65.6 on PVDL (fewer CTAs make the geometry late for its consumers).
+constexpr int SIDE_CTAS_PER_SM = 4;
+
 constexpr int BQ_TILE = 2048;     // points staged per pass (24 KB: a CTA fits next to a persistent GEMM / conv CTA of the main stream)
 
 template <int WARPS>
@@ -625,9 +631,9 @@ P2PB_API int p2pb_ball_query(const float* centers, const float* points, int B, i
     const size_t smem = (size_t)3 * BQ_TILE * sizeof(float);
     constexpr int WARPS = 8;
     int gx = p2pb_cdiv(M, WARPS * 4);
-    // enough CTAs per patch to fill the chip, but at most ~4 (1024 of the 2048 thread slots) per SM: the kernel runs on the geometry
-    // stream next to the main stream's kernels
-    const int want = p2pb_cdiv(4 * p2pb_num_sms(), B);
+    // enough CTAs per patch to fill the chip, but only about SIDE_CTAS_PER_SM per SM: the kernel runs on the geometry stream next
+    // to the main stream's kernels
+    const int want = p2pb_cdiv(SIDE_CTAS_PER_SM * p2pb_num_sms(), B);
     if (gx > want) gx = want < 1 ? 1 : want;
     p2pb_prefer_max_smem((const void*)ball_query_kernel<WARPS>);
     (void)p2pb_launch(ball_query_kernel<WARPS>, dim3(dim3(gx, B)), dim3(WARPS * 32), (size_t)(smem), (cudaStream_t)stream, centers, points, M, N, r2, U, out);
@@ -729,9 +735,9 @@ P2PB_API int p2pb_three_nn(const float* points, const float* centers, int B, int
     if (smem > 48 * 1024)
         P2PB_CUDA_OK(cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p2pb_prefer_max_smem((const void*)three_nn_kernel);
-    // at most ~4 CTAs (1024 of the 2048 thread slots) per SM, in whole passes over the point blocks
+    // about SIDE_CTAS_PER_SM CTAs per SM, in whole passes over the point blocks
     const int nblk = p2pb_cdiv(N, 256);
-    int cap = (4 * p2pb_num_sms()) / B;
+    int cap = (SIDE_CTAS_PER_SM * p2pb_num_sms()) / B;
     if (cap < 1) cap = 1;
     const int gx = p2pb_cdiv(nblk, p2pb_cdiv(nblk, cap));
     (void)p2pb_launch(three_nn_kernel, dim3(dim3(gx, B)), dim3(256), (size_t)(smem), (cudaStream_t)stream, points, centers, N, M, idx, w);
