@@ -44,6 +44,8 @@ def parse():
                     help="eager = the validation path (torch library layers); the bench line of record is the engine")
     ap.add_argument("--no-graph", action="store_true", help="profiling aid: enqueue kernels directly (ncu launch lists)")
     ap.add_argument("--chains", type=int, default=1, help="development aid: part-batch chains inside the graph")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=0|1",
+                    help="development aid: set a boolean of p2pb_b200.engine.OPTIONS (A/B runs on one box)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="patches per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -291,6 +293,11 @@ def run_b200(args):
 
     ENG.OPTIONS.no_graph = bool(args.no_graph)
     ENG.OPTIONS.chains = int(args.chains)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        if not isinstance(getattr(ENG.OPTIONS, k, None), bool):
+            raise SystemExit(f"--opt {k}: not a boolean option of engine.OPTIONS")
+        setattr(ENG.OPTIONS, k, bool(int(v)))
     cfg_dict = load_cfg_dict()
     cfg = Config.wrap(cfg_dict)
     cfg.gpu = str(dev)

@@ -35,7 +35,6 @@
 namespace {
 
 constexpr int HBM = 128;
-constexpr int HALO_SIDE_KB = 28;    // shared memory the un-stacked kernel leaves to a co-resident side-stream CTA
 constexpr int HALO_THREADS = 352;   // warp 0: window producer, 1: MMA issuer, 2-5: epilogue set 0, 6: weight producer, 7-10: epilogue set 1
 
 struct HaloArgs {
@@ -193,12 +192,8 @@ __device__ __forceinline__ void h_tmem_ld32(uint32_t taddr, float* v)
 // and the convolution is  out[q] = P_-1[q-1] + P_0[q] + P_+1[q+1]:  a +-1 shift along the TMEM LANES, done in the epilogue with
 // two warp shuffles per value (+ a shared-memory hand-over of the two rows at every warp boundary).  Rows 0 and 127 of a tile
 // have no complete sum, so tiles advance by 126 rows (1.6 % more tiles).
-// The un-stacked kernel is capped at 128 registers (launch bound 512; 352 threads are launched) and its launcher leaves HALO_SIDE_KB
-// of shared memory unused: a 256-thread, <= 64-register, <= 24 KB CTA of the geometry stream (FPS, ball query, 3-NN) then fits on the
-// same SM instead of keeping this persistent kernel off it until it has finished (see gemm_persist.cu: P_SIDE_KB).  The stacked form
-// needs its registers (it would spill) and its deep rings, and keeps the SM to itself.
 template <bool PAIR, bool F16, bool STACK>
-__global__ void __launch_bounds__(STACK ? HALO_THREADS : 512, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const HaloArgs a)
 {
     P2PB_PDL_SYNC();
@@ -696,10 +691,7 @@ static int conv3d_halo_impl(const void* X, const void* W, const float* bias, flo
     const int sub_bytes = 3 * (pair ? Cout / 2 : Cout) * 128;     // per CTA: pair mode keeps half of the output channels
     const int a_stage_stride = ((a.W * 128) + 1023) & ~1023;
     const int stage_bytes = 8 * 4096 + 1024 + 4096;      // epilogue staging tiles (+ alignment) + boundary rows of the stacked form
-    const int fixed_bytes = 1024 + 256 + 8 * Cout * 2 * 4 + stage_bytes;
-    int budget = (g_p2pb_smem_budget_kb - 2 - (stack ? 0 : HALO_SIDE_KB)) * 1024 - fixed_bytes;
-    // shapes whose rings do not fit beside a side-stream CTA (fp32-stored operands at Cout = 128) take the whole SM
-    if (2 * sub_bytes + (a.G + 1) * a_stage_stride > budget) budget = (g_p2pb_smem_budget_kb - 2) * 1024 - fixed_bytes;
+    const int budget = (g_p2pb_smem_budget_kb - 2) * 1024 - 1024 - 256 - 8 * Cout * 2 * 4 - stage_bytes;
     a.w_stages = (3 * sub_bytes + (a.G + 1) * a_stage_stride <= budget) ? 3 : 2;
     a.a_stages = (budget - a.w_stages * sub_bytes) / a_stage_stride;
     int a_cap = 2 * a.G;

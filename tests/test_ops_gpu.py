@@ -42,7 +42,10 @@ def test_fps_gather_ball_group_bit_exact(mods, B, N, M, snap):
     assert torch.equal(g.cpu(), OO.grouping_forward(feats, ref_n))
 
 
-@pytest.mark.parametrize("B,N,M,C", [(2, 2048, 512, 16), (3, 512, 128, 5), (2, 32, 8, 64), (1, 8192, 2048, 4)])
+# (1, 1000, 250, 3): M not a multiple of 4 (scalar tail of the 16-byte centre loads); (40, 4096, 64, 2): more point blocks per patch than
+# the launcher's residency cap allows CTAs -> the grid-stride loop over point blocks
+@pytest.mark.parametrize("B,N,M,C", [(2, 2048, 512, 16), (3, 512, 128, 5), (2, 32, 8, 64), (1, 8192, 2048, 4), (1, 1000, 250, 3),
+                                     (40, 4096, 64, 2)])
 def test_three_nn_interpolate_bit_exact(mods, B, N, M, C):
     OO, ops, P = mods
     pts = cloud(B, N, seed=3)
