@@ -56,6 +56,29 @@ struct HaloArgs {
     float* stats;             // [total_tiles, cout, 2] or null
 };
 
+// explicit shared-space accesses for the epilogue (staging tile, boundary rows, statistics): through generic pointers (the dynamic
+// shared-memory base is aligned at run time) the compiler emits generic ST.E / LD.E instead of STS / LDS (see gemm_persist.cu)
+__device__ __forceinline__ void h_sts128(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 h_lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float h_lds32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void h_sts64(uint32_t addr, float x, float y)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+
 __device__ __forceinline__ uint32_t h_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // one elected lane of a converged warp: ptxas then feeds tcgen05/TMA instructions from uniform registers directly
 // (with `if (lane == 0)` it emits an ELECT + R2UR "waterfall" loop around every tcgen05.mma, ~100 cycles each)
@@ -488,27 +511,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         h_tmem_ld32(tcol + (uint32_t)a.cout, vv);
                         h_tmem_ld32(tcol + (uint32_t)(2 * a.cout), vp);
                         float* eb = s_edge + (size_t)((eset * 2 + epar) * 4) * 64;     // [warp][{last row of P_-1, first row of P_+1}][32]
+                        const uint32_t eb_s = h_smem_u32(eb);
                         epar ^= 1;         // double-buffered: the barrier of use k+1 separates the reads of use k from the writes of use k+2
                         if (lane == 31) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                *reinterpret_cast<float4*>(eb + qd * 64 + 4 * j) = make_float4(vm[4 * j], vm[4 * j + 1], vm[4 * j + 2], vm[4 * j + 3]);
+                                h_sts128(eb_s + (qd * 64 + 4 * j) * 4, make_float4(vm[4 * j], vm[4 * j + 1], vm[4 * j + 2], vm[4 * j + 3]));
                         }
                         if (lane == 0) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                *reinterpret_cast<float4*>(eb + qd * 64 + 32 + 4 * j) = make_float4(vp[4 * j], vp[4 * j + 1], vp[4 * j + 2], vp[4 * j + 3]);
+                                h_sts128(eb_s + (qd * 64 + 32 + 4 * j) * 4, make_float4(vp[4 * j], vp[4 * j + 1], vp[4 * j + 2], vp[4 * j + 3]));
                         }
                         if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
                         else asm volatile("bar.sync 2, 128;" ::: "memory");
                         // branch-free: every lane reads the neighbour warps' boundary rows (broadcast), lanes 0 / 31 select them
                         // (rows 0 and 127 of the tile have no neighbour: they are masked halo rows anyway)
-                        const float4* pu = reinterpret_cast<const float4*>(eb + (qd > 0 ? qd - 1 : qd) * 64);
-                        const float4* pd = reinterpret_cast<const float4*>(eb + (qd < 3 ? qd + 1 : qd) * 64 + 32);
+                        const uint32_t pu = eb_s + ((qd > 0 ? qd - 1 : qd) * 64) * 4;
+                        const uint32_t pd = eb_s + ((qd < 3 ? qd + 1 : qd) * 64 + 32) * 4;
                         const bool l0 = lane == 0, l31 = lane == 31;
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 u = pu[j4], d = pd[j4];
+                            const float4 u = h_lds128(pu + 16 * j4), d = h_lds128(pd + 16 * j4);
                             const float ua[4] = {u.x, u.y, u.z, u.w}, da[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -522,8 +546,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         h_tmem_ld32(tcol, vv);
                     }
                     __syncwarp();              // the previous chunk's readers are done with the staging tile
+                    const uint32_t stg_s = h_smem_u32(stg);
                     if (ok) {
-                        uint8_t* rowp = stg + pos * 128;
+                        const uint32_t rowp = stg_s + pos * 128;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 t = make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
@@ -531,27 +556,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                                 const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + 4 * j));
                                 t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
                             }
-                            *reinterpret_cast<float4*>(rowp + ((j ^ (pos & 7)) << 4)) = t;
+                            h_sts128(rowp + ((j ^ (pos & 7)) << 4), t);
                         }
                     }
                     __syncwarp();
                     // rows [0, nv) of the staging tile -> nv consecutive dense rows, 8 lanes per 128-byte row segment
                     for (int i = lane; i < nv * 8; i += 32) {
                         const int rr = i >> 3, j = i & 7;
-                        const float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((j ^ (rr & 7)) << 4));
+                        const float4 t = h_lds128(stg_s + rr * 128 + ((j ^ (rr & 7)) << 4));
                         *reinterpret_cast<float4*>(dbase + (size_t)rr * a.ldd + c * 32 + j * 4) = t;
                     }
                     if (a.stats != nullptr) {
                         // column `lane`: element (rr, lane) sits at rr*128 + (((lane>>2) ^ (rr&7))<<4) + (lane&3)*4 (conflict-free)
                         float s1 = 0.f, s2 = 0.f;
-                        const uint8_t* colp = stg + (lane & 3) * 4;
+                        const uint32_t colp = stg_s + (lane & 3) * 4;
                         for (int rr = 0; rr < nv; ++rr) {
-                            const float xx = *reinterpret_cast<const float*>(colp + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4));
+                            const float xx = h_lds32(colp + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4));
                             s1 += xx;
                             s2 = fmaf(xx, xx, s2);
                         }
-                        s_stats_set[((qd * a.cout) + c * 32 + lane) * 2 + 0] = s1;
-                        s_stats_set[((qd * a.cout) + c * 32 + lane) * 2 + 1] = s2;
+                        h_sts64(h_smem_u32(s_stats_set) + (((qd * a.cout) + c * 32 + lane) * 2) * 4, s1, s2);
                     }
                 }
                 if (a.stats != nullptr) {
@@ -562,8 +586,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
                         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
-                            s1 += s_stats_set[((w * a.cout) + n) * 2 + 0];
-                            s2 += s_stats_set[((w * a.cout) + n) * 2 + 1];
+                            s1 += h_lds32(h_smem_u32(s_stats_set) + (((w * a.cout) + n) * 2 + 0) * 4);
+                            s2 += h_lds32(h_smem_u32(s_stats_set) + (((w * a.cout) + n) * 2 + 1) * 4);
                         }
                         float* o = a.stats + ((size_t)tile * a.cout + n) * 2;
                         o[0] = s1;

@@ -52,6 +52,18 @@ struct PArgs {
 };
 
 __device__ __forceinline__ uint32_t p_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// explicit shared-space accesses for the epilogue's staging tile: through a generic pointer (the dynamic shared-memory base is carved
+// up at run time) the compiler emits generic ST.E / LD.E, which are slower than STS / LDS (ncu source page of the epilogue)
+__device__ __forceinline__ void p_sts128(uint32_t addr, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float p_lds32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool p_elect_one()
 {
     uint32_t pred = 0;
@@ -455,12 +467,24 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     }
                 }
                 const int nb = n0 + c * 32;
+                // bias / per-sample bias: 16-byte loads (nb is a multiple of 32 floats, the rows are 16-byte aligned: checked on the host)
+                if (a.bias != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = v[j];
-                    if (a.bias != nullptr) x += __ldg(a.bias + nb + j);
-                    if (bias2_row != nullptr) x += __ldg(bias2_row + nb + j);
-                    v[j] = row_ok ? x : 0.f;
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + nb) + j4);
+                        v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+                    }
+                }
+                if (bias2_row != nullptr) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias2_row + nb) + j4);
+                        v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+                    }
+                }
+                if (!row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
                 }
                 uint8_t* buf = myC + (size_t)cbuf * 4096;
                 // the TMA store that last read this staging buffer must have finished reading it
@@ -469,12 +493,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 }
                 __syncwarp();
+                const uint32_t buf_s = p_smem_u32(buf);
                 {
-                    uint8_t* rowp = buf + lane * 128;
+                    const uint32_t rowp = buf_s + lane * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
-                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        p_sts128(rowp + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
                 if (a.store && nvalid > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -485,12 +509,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 if (want_stats || want_mm) {
                     // column `lane` of the 32 x 32 block: element (r, lane) sits at r*128 + (((lane>>2) ^ (r&7))<<4) + (lane&3)*4
                     float s1 = 0.f, s2 = 0.f, mx = -INFINITY, mn = INFINITY;
-                    const uint8_t* colp = buf + (lane & 3) * 4;
+                    const uint32_t colp = buf_s + (lane & 3) * 4;
                     if (nvalid == 32) {
                         float x[32];
 #pragma unroll
                         for (int r = 0; r < 32; ++r)
-                            x[r] = *reinterpret_cast<const float*>(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
+                            x[r] = p_lds32(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
 #pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             s1 += x[r];
@@ -500,7 +524,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                         }
                     } else {
                         for (int r = 0; r < nvalid; ++r) {
-                            const float x = *reinterpret_cast<const float*>(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
+                            const float x = p_lds32(colp + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
                             s1 += x;
                             s2 = fmaf(x, x, s2);
                             mx = fmaxf(mx, x);
@@ -629,6 +653,8 @@ static int gemm_persist_launch(const CUtensorMap* mapsA, int nseg, const int* se
 {
     P2PB_CHECK_ARG(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
     P2PB_CHECK_ARG(D == nullptr || ((reinterpret_cast<uintptr_t>(D) & 15) == 0 && ldd % 4 == 0), "gemm: D must be 16-byte aligned with ldd %% 4 == 0");
+    P2PB_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias2) & 15) == 0,
+                   "gemm: bias / per-sample bias must be 16-byte aligned (the epilogue reads them with 16-byte loads)");
     const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
     PArgs a = {};
     a.M = M; a.n_total = N; a.n_tiles = N / bn; a.m_tiles = p2pb_cdiv(M, PBM);
