@@ -792,7 +792,7 @@ P2PB_API int p2pb_group_rows_f16(const float* feat, int ldf, int Cf, const float
 // Replaces group_rows + the [B*M*32, C_in] grouped buffer + the first GEMM's [B*M*32, C] output + its activation pass.
 // ---------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) group_project_kernel(const float* __restrict__ Pf, int ldp, const float* __restrict__ Wx,
+__global__ void __launch_bounds__(256, 4) group_project_kernel(const float* __restrict__ Pf, int ldp, const float* __restrict__ Wx,
                                                             const float* __restrict__ coords, const float* __restrict__ centers,
                                                             const int* __restrict__ idx, const float* __restrict__ A,
                                                             const float* __restrict__ Bc, float* __restrict__ stats,
