@@ -90,8 +90,8 @@ def dominant_kernel_roofline(model, B: int, dev, iters: int = 20):
             # ceiling of THIS layer shape on this hardware, and the measured tensor-pipe activity of the last committed capture
             "shape_ceiling": {"what": "an N = Cout = 64 tcgen05.mma stream costs max(48.9, N/2) cycles per MMA (tools/ubench/mma_rate.cu): the "
                                       "tensor pipe can be busy at most 32 / 48.9 of the time for this layer shape",
-                              "tensor_active_ceiling_pct": 100.0 * 32.0 / 48.9, "tensor_active_pct_ncu": 66.0,
-                              "evidence": "profiles/r02_ncu_conv.md (ncu --set full of this launch: 636.7 k elapsed cycles vs 641 k = "
-                                          "121.4 tiles/SM x 108 MMAs x 48.9 cycles)"},
+                              "tensor_active_ceiling_pct": 100.0 * 32.0 / 48.9, "tensor_active_pct_ncu": 67.2,
+                              "evidence": "profiles/r02_ncu_conv.md (ncu --set full of this launch: 617.8 k elapsed cycles = 121.4 tiles/SM x 108 "
+                                          "MMAs x 47.1 cycles; the micro-benchmark's per-MMA cost is 48.9)"},
             "algorithmic_bytes_per_launch": B * (esz * (r + 1) ** 3 * cin + 4.0 * r ** 3 * cout),
             "peak_source": f"{how}: dense 16-bit rate {bf16_peak:.1f} TFLOP/s" + ("" if HALO_F16 else " / 2 for TF32")}
